@@ -1,0 +1,97 @@
+// Batched strided 1-D FFT plans: CUDA side of the executors (device twiddle table, launches on a stream).
+// Replaces heffte::plan_cufft / plan_cufft_r2c and the cufftExec* calls
+// (reference: include/heffte_backend_cuda.h:346-422, 494-524, 580-621, 694-727).
+#include "fft_host_plan.h"
+#include "runtime.h"
+
+#include <cstring>
+
+namespace b200 {
+
+thread_local std::string last_error_text;
+std::atomic<long long> launch_counter{0};
+
+void set_error(std::string const &message){ last_error_text = message; }
+int fail(int code, std::string const &message){ set_error(message); return code; }
+int check_cuda(cudaError_t status, const char *what){
+    if (status == cudaSuccess) return B200_SUCCESS;
+    set_error(std::string(what) + ": " + cudaGetErrorString(status));
+    return B200_ERR_CUDA;
+}
+void allow_smem(const void *kernel, size_t){
+    static std::mutex guard;
+    static std::unordered_set<const void*> done;
+    std::lock_guard<std::mutex> lock(guard);
+    if (done.count(kernel)) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    done.insert(kernel);
+}
+
+} // namespace b200
+
+using namespace b200;
+
+struct b200_fft1d_plan_s {
+    host_plan host;
+    void *twiddle = nullptr;   // device table
+};
+
+extern "C" {
+
+const char* b200_last_error(void){ return last_error_text.c_str(); }
+long long b200_launch_count(void){ return launch_counter.load(); }
+int b200_device_count(void){
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+
+int b200_fft1d_create(const b200_fft1d_desc *desc, b200_fft1d_plan *out){
+    if (desc == nullptr or out == nullptr) return fail(B200_ERR_INVALID, "null argument");
+    auto *plan = new b200_fft1d_plan_s();
+    const char *why = "";
+    int rc = make_host_plan(*desc, plan->host, &why);
+    if (rc){ delete plan; return fail(rc, why); }
+    if (b200_device_count() < 1){ delete plan; return fail(B200_ERR_NO_DEVICE, "no CUDA device: the b200 backend has no CPU fallback"); }
+    size_t bytes = 0;
+    if (desc->precision == B200_PREC_FLOAT){
+        auto table = make_twiddle_table<float>(plan->host);
+        bytes = table.size() * sizeof(float);
+        rc = check_cuda(cudaMalloc(&plan->twiddle, bytes), "cudaMalloc(twiddle)");
+        if (!rc) rc = check_cuda(cudaMemcpy(plan->twiddle, table.data(), bytes, cudaMemcpyHostToDevice), "cudaMemcpy(twiddle)");
+    }else{
+        auto table = make_twiddle_table<double>(plan->host);
+        bytes = table.size() * sizeof(double);
+        rc = check_cuda(cudaMalloc(&plan->twiddle, bytes), "cudaMalloc(twiddle)");
+        if (!rc) rc = check_cuda(cudaMemcpy(plan->twiddle, table.data(), bytes, cudaMemcpyHostToDevice), "cudaMemcpy(twiddle)");
+    }
+    if (rc){ if (plan->twiddle) cudaFree(plan->twiddle); delete plan; return rc; }
+    *out = plan;
+    return B200_SUCCESS;
+}
+
+int b200_fft1d_destroy(b200_fft1d_plan plan){
+    if (plan == nullptr) return B200_SUCCESS;
+    if (plan->twiddle) cudaFree(plan->twiddle);
+    delete plan;
+    return B200_SUCCESS;
+}
+
+const char* b200_fft1d_kernel_name(b200_fft1d_plan plan){
+    if (plan == nullptr) return "null";
+    switch(plan->host.family){
+        case family_strided: return "strided";
+        case family_contig: return "contig";
+        default: return "generic";
+    }
+}
+
+int b200_fft1d_execute(b200_fft1d_plan plan, int direction, const void *in, void *out, double scale, void *stream){
+    if (plan == nullptr) return fail(B200_ERR_INVALID, "null plan");
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    int rc = run_host_plan(plan->host, plan->twiddle, direction, in, out, scale, L);
+    if (rc == -1) return fail(B200_ERR_UNSUPPORTED, "no kernel for this length");
+    return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,571 @@
+// Device-side building blocks of the batched 1-D FFT executors (sm_100a).
+//
+// Replaces the cuFFT calls of the reference's CUDA backend (reference: include/heffte_backend_cuda.h:356-415,
+// 494-524, 592-727 -- cufftMakePlanMany + cufftExec{C2C,Z2Z,R2C,D2Z,C2R,Z2D}) with hand-written kernels:
+//   * fft_strided_kernel   : lines whose neighbours are adjacent in memory (FFT along the middle / slow axis of a
+//                            box).  A CTA owns a tile of LPB adjacent lines, so every global access is a full
+//                            128-byte row; in-place decimation-in-frequency passes in shared memory, the digit
+//                            reversal is absorbed into the row index of the final store (free, because coalescing
+//                            runs across lines, not along the transform).
+//   * fft_contig_kernel    : lines contiguous in memory (FFT along the fast axis).  Stockham auto-sort passes so
+//                            that both the first global load and the last global store are unit-stride.
+//   * fft_generic_kernel   : any length (mixed radix by prime factors, O(N*p) per factor p), used for
+//                            non-power-of-two sizes and as the r2c/c2r/r2r engine for such sizes.
+// Butterflies are register resident (radix 2/4/8/16); data is exchanged between passes through shared memory.
+// The inverse transform reuses the forward code through the identity  ifft(x) = swap(fft(swap(x)))  where
+// swap exchanges real and imaginary parts, so direction costs nothing.
+#pragma once
+
+#include "cuda_compat.h"
+#include <stdint.h>
+
+namespace b200 {
+
+template<typename T> struct cplx_of;
+template<> struct cplx_of<float>  { using type = float2; };
+template<> struct cplx_of<double> { using type = double2; };
+template<typename T> using cplx = typename cplx_of<T>::type;
+
+template<typename T> __device__ __forceinline__ cplx<T> mk(T x, T y){ cplx<T> r; r.x = x; r.y = y; return r; }
+template<typename C> __device__ __forceinline__ C cadd(C a, C b){ C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template<typename C> __device__ __forceinline__ C csub(C a, C b){ C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template<typename C> __device__ __forceinline__ C cmul(C a, C b){
+    C r;
+    r.x = a.x * b.x - a.y * b.y;
+    r.y = a.x * b.y + a.y * b.x;
+    return r;
+}
+// multiply by -i  (forward quarter turn)
+template<typename C> __device__ __forceinline__ C mul_mi(C a){ C r; r.x = a.y; r.y = -a.x; return r; }
+template<typename C> __device__ __forceinline__ C cswap(C a){ C r; r.x = a.y; r.y = a.x; return r; }
+
+// ---------------------------------------------------------------------------------------------------------
+// register butterflies: forward DFT of length R, input and output in natural order
+// ---------------------------------------------------------------------------------------------------------
+template<typename T, int R> struct butterfly;
+
+template<typename T> struct butterfly<T, 2>{
+    __device__ __forceinline__ static void run(cplx<T> (&v)[2]){
+        cplx<T> a = v[0];
+        v[0] = cadd(a, v[1]);
+        v[1] = csub(a, v[1]);
+    }
+};
+
+template<typename T> struct butterfly<T, 4>{
+    __device__ __forceinline__ static void run(cplx<T> (&v)[4]){
+        cplx<T> s02 = cadd(v[0], v[2]), d02 = csub(v[0], v[2]);
+        cplx<T> s13 = cadd(v[1], v[3]), d13 = mul_mi(csub(v[1], v[3]));
+        v[0] = cadd(s02, s13);
+        v[2] = csub(s02, s13);
+        v[1] = cadd(d02, d13);
+        v[3] = csub(d02, d13);
+    }
+};
+
+template<typename T> struct butterfly<T, 8>{
+    __device__ __forceinline__ static void run(cplx<T> (&v)[8]){
+        const T h = static_cast<T>(0.70710678118654752440084436210485);
+        // split into even part a (k + k+4 sums) and twiddled odd part b
+        cplx<T> a[4], b[4];
+        #pragma unroll
+        for(int k=0; k<4; k++){
+            a[k] = cadd(v[k], v[k+4]);
+            b[k] = csub(v[k], v[k+4]);
+        }
+        // b[k] *= W8^k : W8 = (1 - i)/sqrt2, W8^2 = -i, W8^3 = (-1 - i)/sqrt2
+        b[1] = mk<T>((b[1].x + b[1].y) * h, (b[1].y - b[1].x) * h);
+        b[2] = mul_mi(b[2]);
+        b[3] = mk<T>((b[3].y - b[3].x) * h, -(b[3].x + b[3].y) * h);
+        butterfly<T, 4>::run(a);
+        butterfly<T, 4>::run(b);
+        #pragma unroll
+        for(int k=0; k<4; k++){
+            v[2*k]   = a[k];
+            v[2*k+1] = b[k];
+        }
+    }
+};
+
+template<typename T> struct butterfly<T, 16>{
+    __device__ __forceinline__ static void run(cplx<T> (&v)[16]){
+        // 16 = 4 x 4: four radix-4 over stride 4, twiddle by W16^(j*k), four radix-4 over the columns
+        const T c1 = static_cast<T>(0.92387953251128675612818318939679); // cos(pi/8)
+        const T s1 = static_cast<T>(0.38268343236508977172845998403040); // sin(pi/8)
+        const T h  = static_cast<T>(0.70710678118654752440084436210485);
+        cplx<T> col[4][4];
+        #pragma unroll
+        for(int j=0; j<4; j++){
+            cplx<T> t[4] = {v[j], v[j+4], v[j+8], v[j+12]};
+            butterfly<T, 4>::run(t);
+            #pragma unroll
+            for(int k=0; k<4; k++) col[j][k] = t[k];
+        }
+        // twiddles W16^(j*k), forward sign: W16^m = cos(m pi/8) - i sin(m pi/8)
+        col[1][1] = cmul(col[1][1], mk<T>( c1, -s1));
+        col[1][2] = mk<T>((col[1][2].x + col[1][2].y) * h, (col[1][2].y - col[1][2].x) * h);
+        col[1][3] = cmul(col[1][3], mk<T>( s1, -c1));
+        col[2][1] = mk<T>((col[2][1].x + col[2][1].y) * h, (col[2][1].y - col[2][1].x) * h);
+        col[2][2] = mul_mi(col[2][2]);
+        col[2][3] = mk<T>((col[2][3].y - col[2][3].x) * h, -(col[2][3].x + col[2][3].y) * h);
+        col[3][1] = cmul(col[3][1], mk<T>( s1, -c1));
+        col[3][2] = mk<T>((col[3][2].y - col[3][2].x) * h, -(col[3][2].x + col[3][2].y) * h);
+        col[3][3] = cmul(col[3][3], mk<T>(-c1,  s1)); // W16^9 = -W16^1
+        #pragma unroll
+        for(int k=0; k<4; k++){
+            cplx<T> t[4] = {col[0][k], col[1][k], col[2][k], col[3][k]};
+            butterfly<T, 4>::run(t);
+            #pragma unroll
+            for(int j=0; j<4; j++) v[k + 4*j] = t[j];
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// addressing of a batch of lines: line l = (a, b) with a = l % count_a; element i of the line lives at
+//   base + a*stride_a + b*stride_b + i*stride      (all in elements of the scalar type of that side)
+// ---------------------------------------------------------------------------------------------------------
+struct line_geom {
+    long long stride;
+    long long stride_a;
+    long long stride_b;
+};
+
+struct fft_args {
+    const void *in;
+    void *out;
+    const void *twiddle;   // W_N^k, k = 0..N-1, forward sign, complex of the working precision
+    line_geom ig, og;
+    long long nlines;
+    int count_a;
+    int backward;          // 0 forward, 1 backward
+    double scale;          // applied on the final store
+};
+
+__device__ __forceinline__ long long line_offset(line_geom const &g, int count_a, long long line){
+    long long b = line / count_a;
+    long long a = line - b * count_a;
+    return a * g.stride_a + b * g.stride_b;
+}
+
+template<typename T> __device__ __forceinline__ cplx<T> ldg_c(const cplx<T> *p){ return __ldg(p); }
+
+__host__ __device__ constexpr int cmax(int a, int b){ return a > b ? a : b; }
+__host__ __device__ constexpr int ilog2(int n){ return n <= 1 ? 0 : 1 + ilog2(n / 2); }
+
+// apply W^(o*r*step) to v[r], r = 1..R-1; table holds W_N^k.  FEW_LOADS: fetch only the power-of-two entries
+// from the table and form the others by one or two products (error <= 2 roundings).
+template<typename T, int R, bool FEW_LOADS>
+__device__ __forceinline__ void apply_twiddles(cplx<T> (&v)[R], const cplx<T> *tw, int base){
+    if constexpr (!FEW_LOADS || R <= 4){
+        #pragma unroll
+        for(int r=1; r<R; r++) v[r] = cmul(v[r], ldg_c<T>(tw + r * base));
+    }else{
+        cplx<T> w1 = ldg_c<T>(tw + base), w2 = ldg_c<T>(tw + 2 * base), w4 = ldg_c<T>(tw + 4 * base);
+        cplx<T> w3 = cmul(w1, w2), w5 = cmul(w1, w4), w6 = cmul(w2, w4), w7 = cmul(w3, w4);
+        v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+        v[5] = cmul(v[5], w5); v[6] = cmul(v[6], w6); v[7] = cmul(v[7], w7);
+        if constexpr (R == 16){
+            cplx<T> w8 = ldg_c<T>(tw + 8 * base);
+            v[8]  = cmul(v[8],  w8);
+            v[9]  = cmul(v[9],  cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
+            v[12] = cmul(v[12], cmul(w8, w4)); v[13] = cmul(v[13], cmul(w8, w5)); v[14] = cmul(v[14], cmul(w8, w6));
+            v[15] = cmul(v[15], cmul(w8, w7));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// strided kernel: tile of LPB adjacent lines, in-place DIF in shared memory laid out [position][line]
+// ---------------------------------------------------------------------------------------------------------
+template<int R0, int R1, int R2, int R3> struct radix_list {
+    static constexpr int N = R0 * R1 * R2 * R3;
+    static constexpr int passes = (R1 == 1) ? 1 : ((R2 == 1) ? 2 : ((R3 == 1) ? 3 : 4));
+    static constexpr int rmax = cmax(cmax(R0, R1), cmax(R2, R3));
+    __host__ __device__ static constexpr int radix(int s){ return s == 0 ? R0 : (s == 1 ? R1 : (s == 2 ? R2 : R3)); }
+    // stride of pass s: N / (R0 * ... * Rs)
+    __host__ __device__ static constexpr int stride(int s){ return s == 0 ? N / R0 : stride(s - 1) / radix(s); }
+};
+
+// natural index k of the value that ends at in-place position p after all DIF passes
+template<typename RL>
+__device__ __forceinline__ int dif_output_index(int p){
+    int k = 0, mult = 1;
+    #pragma unroll
+    for(int s=0; s<RL::passes; s++){
+        int d = (p / RL::stride(s)) % RL::radix(s);
+        k += d * mult;
+        mult *= RL::radix(s);
+    }
+    return k;
+}
+
+template<typename T, typename RL, int S, int TPL, int LPB, bool FIRST, bool LAST>
+__device__ __forceinline__ void strided_pass(cplx<T> *sm, int t, int j, bool valid,
+                                             const cplx<T> *gin, cplx<T> *gout, long long istride, long long ostride,
+                                             const cplx<T> *tw, bool backward, T scale, bool do_scale){
+    constexpr int R = RL::radix(S);
+    constexpr int ST = RL::stride(S);          // distance between butterfly legs
+    constexpr int NB = RL::N / R;              // butterflies per line
+    #pragma unroll
+    for(int u=0; u<NB/TPL; u++){
+        int q = j + u * TPL;
+        int blk = q / ST, o = q % ST;
+        int p0 = blk * ST * R + o;
+        cplx<T> v[R];
+        if (FIRST){
+            if (valid){
+                #pragma unroll
+                for(int r=0; r<R; r++){
+                    cplx<T> x = gin[(long long)(p0 + r * ST) * istride];
+                    v[r] = backward ? cswap(x) : x;
+                }
+            }else{
+                #pragma unroll
+                for(int r=0; r<R; r++) v[r] = mk<T>(0, 0);
+            }
+        }else{
+            #pragma unroll
+            for(int r=0; r<R; r++) v[r] = sm[(p0 + r * ST) * LPB + t];
+        }
+        butterfly<T, R>::run(v);
+        if (!LAST){
+            // DIF twiddle after the butterfly: W_{ST*R}^(o*r) = W_N^(o*r*N/(ST*R))
+            apply_twiddles<T, R, false>(v, tw, o * (RL::N / (ST * R)));
+            #pragma unroll
+            for(int r=0; r<R; r++) sm[(p0 + r * ST) * LPB + t] = v[r];
+        }else if (valid){
+            #pragma unroll
+            for(int r=0; r<R; r++){
+                int k = dif_output_index<RL>(p0 + r * ST);
+                cplx<T> x = backward ? cswap(v[r]) : v[r];
+                if (do_scale){ x.x *= scale; x.y *= scale; }
+                gout[(long long)k * ostride] = x;
+            }
+        }
+    }
+}
+
+template<typename T, typename RL, int TPL, int LPB, int MINB>
+__global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a){
+    B200_DYN_SMEM(smem_raw);
+    cplx<T> *sm = reinterpret_cast<cplx<T>*>(smem_raw);
+    const int t = threadIdx.x % LPB, j = threadIdx.x / LPB;
+    const long long line = (long long)blockIdx.x * LPB + t;
+    const bool valid = line < a.nlines;
+    const cplx<T> *gin = reinterpret_cast<const cplx<T>*>(a.in) + (valid ? line_offset(a.ig, a.count_a, line) : 0);
+    cplx<T> *gout = reinterpret_cast<cplx<T>*>(a.out) + (valid ? line_offset(a.og, a.count_a, line) : 0);
+    const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
+    const bool bwd = a.backward != 0;
+    const T scale = static_cast<T>(a.scale);
+    const bool do_scale = a.scale != 1.0;
+    constexpr int P = RL::passes;
+
+    strided_pass<T, RL, 0, TPL, LPB, true, P == 1>(sm, t, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+    if constexpr (P > 1){
+        __syncthreads();
+        strided_pass<T, RL, 1, TPL, LPB, false, P == 2>(sm, t, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+    }
+    if constexpr (P > 2){
+        __syncthreads();
+        strided_pass<T, RL, 2, TPL, LPB, false, P == 3>(sm, t, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+    }
+    if constexpr (P > 3){
+        __syncthreads();
+        strided_pass<T, RL, 3, TPL, LPB, false, P == 4>(sm, t, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// contiguous kernel: Stockham auto-sort, LPB lines per CTA, TPL = N / rmax threads per line, padded rows
+// ---------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int pad_index(int i){ return i + (i >> 3); }
+
+template<typename T, typename RL, int S, int NS, int TPL, bool FIRST, bool LAST>
+__device__ __forceinline__ void contig_pass(cplx<T> *row, int j, bool valid,
+                                            const cplx<T> *gin, cplx<T> *gout, long long istride, long long ostride,
+                                            const cplx<T> *tw, bool backward, T scale, bool do_scale){
+    constexpr int R = RL::radix(S);
+    constexpr int NB = RL::N / R;
+    constexpr int BPT = NB / TPL;              // butterflies per thread in this pass
+    cplx<T> v[BPT][R];
+    #pragma unroll
+    for(int u=0; u<BPT; u++){
+        int q = j + u * TPL;
+        if (FIRST){
+            #pragma unroll
+            for(int r=0; r<R; r++){
+                cplx<T> x = valid ? gin[(long long)(q + r * NB) * istride] : mk<T>(0, 0);
+                v[u][r] = backward ? cswap(x) : x;
+            }
+        }else{
+            #pragma unroll
+            for(int r=0; r<R; r++) v[u][r] = row[pad_index(q + r * NB)];
+        }
+    }
+    if (!FIRST) __syncthreads();   // every leg has been read before anybody overwrites the row
+    #pragma unroll
+    for(int u=0; u<BPT; u++){
+        int q = j + u * TPL;
+        int k = q % NS;
+        if (NS > 1) apply_twiddles<T, R, true>(v[u], tw, k * (RL::N / (NS * R)));
+        butterfly<T, R>::run(v[u]);
+        int o = (q / NS) * NS * R + k;
+        if (!LAST){
+            #pragma unroll
+            for(int r=0; r<R; r++) row[pad_index(o + r * NS)] = v[u][r];
+        }else if (valid){
+            #pragma unroll
+            for(int r=0; r<R; r++){
+                cplx<T> x = backward ? cswap(v[u][r]) : v[u][r];
+                if (do_scale){ x.x *= scale; x.y *= scale; }
+                gout[(long long)(o + r * NS) * ostride] = x;
+            }
+        }
+    }
+}
+
+template<typename T, typename RL, int LPB, int MINB>
+__global__ void __launch_bounds__((RL::N / RL::rmax) * LPB, MINB) fft_contig_kernel(fft_args a){
+    B200_DYN_SMEM(smem_raw);
+    constexpr int TPL = RL::N / RL::rmax;
+    constexpr int PITCH = pad_index(RL::N) + 1;
+    const int j = threadIdx.x % TPL, t = threadIdx.x / TPL;
+    cplx<T> *row = reinterpret_cast<cplx<T>*>(smem_raw) + t * PITCH;
+    const long long line = (long long)blockIdx.x * LPB + t;
+    const bool valid = line < a.nlines;
+    const cplx<T> *gin = reinterpret_cast<const cplx<T>*>(a.in) + (valid ? line_offset(a.ig, a.count_a, line) : 0);
+    cplx<T> *gout = reinterpret_cast<cplx<T>*>(a.out) + (valid ? line_offset(a.og, a.count_a, line) : 0);
+    const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
+    const bool bwd = a.backward != 0;
+    const T scale = static_cast<T>(a.scale);
+    const bool do_scale = a.scale != 1.0;
+    constexpr int P = RL::passes;
+    constexpr int N1 = RL::radix(0), N2 = N1 * RL::radix(1), N3 = N2 * RL::radix(2);
+
+    contig_pass<T, RL, 0, 1, TPL, true, P == 1>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+    if constexpr (P > 1){
+        __syncthreads();
+        contig_pass<T, RL, 1, N1, TPL, false, P == 2>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+    }
+    if constexpr (P > 2){
+        __syncthreads();
+        contig_pass<T, RL, 2, N2, TPL, false, P == 3>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+    }
+    if constexpr (P > 3){
+        __syncthreads();
+        contig_pass<T, RL, 3, N3, TPL, false, P == 4>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// generic kernel: any N that fits shared memory twice.  Stockham passes by prime factor; each thread produces
+// one output element per pass:  out[o] = sum_r in[q + r*N/p] * W_N^(r*base mod N).
+// Load/store "modes" make it the engine for c2c, r2c, c2r and the r2r (DCT/DST) transforms:
+// ---------------------------------------------------------------------------------------------------------
+enum generic_mode : int {
+    mode_c2c = 0,
+    mode_r2c = 1,     // real input line of length N, complex output of length N/2+1
+    mode_c2r = 2,     // complex input N/2+1 (Hermitian half), real output N (unnormalised)
+    mode_dct2 = 3,    // REDFT10:   y_k = 2 sum x_i cos(pi (2i+1) k / 2n)                 (heffte cos forward)
+    mode_dct3 = 4,    // 2*REDFT01: y_i = 2 x_0 + 4 sum_{k>=1} x_k cos(pi k (2i+1) / 2n)  (heffte cos backward)
+    mode_dst2 = 5,    // RODFT10:   y_k = 2 sum x_i sin(pi (2i+1)(k+1) / 2n)              (heffte sin forward)
+    mode_dst3 = 6,    // 2*RODFT01                                                        (heffte sin backward)
+    mode_dct1 = 7     // cos1: REDFT00 (forward), 2*REDFT00 (backward) -- selected by args.backward
+};
+
+struct generic_args {
+    const void *in;
+    void *out;
+    const void *twiddle;     // W_M^k for k < M where M = engine length (N, or 4n / 4(n-1) for some r2r modes)
+    line_geom ig, og;
+    long long nlines;
+    int count_a;
+    int backward;
+    double scale;
+    int n;                   // user-visible line length
+    int m;                   // engine (complex FFT) length
+    int mode;
+    int lpb;                 // lines per block
+    int lines_fast;          // 1: thread index runs across lines first (neighbour lines adjacent in memory)
+    int nfactors;
+    int factors[24];
+};
+
+template<typename T>
+__device__ __forceinline__ cplx<T> generic_load(generic_args const &a, const void *base, long long off, int i){
+    // returns element i (0 <= i < m) of the complex engine input built from the user line
+    const int n = a.n;
+    switch(a.mode){
+        case mode_c2c: {
+            cplx<T> x = reinterpret_cast<const cplx<T>*>(base)[off + (long long)i * a.ig.stride];
+            return a.backward ? cswap(x) : x;
+        }
+        case mode_r2c: {
+            T x = reinterpret_cast<const T*>(base)[off + (long long)i * a.ig.stride];
+            return mk<T>(x, 0);
+        }
+        case mode_c2r: {
+            // Hermitian extension, then backward = swap trick
+            int h = n / 2;
+            cplx<T> x;
+            if (i <= h) x = reinterpret_cast<const cplx<T>*>(base)[off + (long long)i * a.ig.stride];
+            else { x = reinterpret_cast<const cplx<T>*>(base)[off + (long long)(n - i) * a.ig.stride]; x.y = -x.y; }
+            if (i == 0 || (2 * i == n)) x.y = 0;   // c2r ignores the imaginary part of the self-conjugate entries
+            return cswap(x);
+        }
+        case mode_dct2: {
+            // Makhoul reordering: v_i = x_{2i} (i < ceil(n/2)), v_{n-1-i} = x_{2i+1}
+            int src = (2 * i < n) ? 2 * i : 2 * (n - 1 - i) + 1;
+            T x = reinterpret_cast<const T*>(base)[off + (long long)src * a.ig.stride];
+            return mk<T>(x, 0);
+        }
+        case mode_dst2: {
+            // DST-II of x equals the reversed DCT-II of (-1)^i x_i
+            int src = (2 * i < n) ? 2 * i : 2 * (n - 1 - i) + 1;
+            T x = reinterpret_cast<const T*>(base)[off + (long long)src * a.ig.stride];
+            return mk<T>((src & 1) ? -x : x, 0);
+        }
+        default: {
+            // dct3 / dst3 / dct1 build their spectrum in a pre-pass (see generic kernel), never through here
+            return mk<T>(0, 0);
+        }
+    }
+}
+
+template<typename T>
+__global__ void fft_generic_kernel(generic_args a){
+    B200_DYN_SMEM(smem_raw);
+    const int m = a.m, n = a.n;
+    const int lpb = a.lpb;
+    cplx<T> *buf0 = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T> *buf1 = buf0 + (size_t)lpb * m;
+    const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
+    const long long line0 = (long long)blockIdx.x * lpb;
+    const int total = lpb * m;
+
+    // ---- load ------------------------------------------------------------------------------------------
+    for(int idx = threadIdx.x; idx < total; idx += blockDim.x){
+        int t, i;
+        if (a.lines_fast){ t = idx % lpb; i = idx / lpb; } else { i = idx % m; t = idx / m; }
+        long long line = line0 + t;
+        cplx<T> x = mk<T>(0, 0);
+        if (line < a.nlines){
+            long long off = line_offset(a.ig, a.count_a, line);
+            if (a.mode == mode_dct3 || a.mode == mode_dst3){
+                // inverse of the Makhoul post-twiddle: V_k = e^{+i pi k / 2n} (y_k - i y_{n-k}), y_n := 0;
+                // for the sine variant y is replaced by the reversed input (y_k -> x_{n-1-k}).
+                const T *src = reinterpret_cast<const T*>(a.in);
+                T yk, ynk;
+                if (a.mode == mode_dct3){
+                    yk  = src[off + (long long)i * a.ig.stride];
+                    ynk = (i == 0) ? T(0) : src[off + (long long)(n - i) * a.ig.stride];
+                }else{
+                    yk  = src[off + (long long)(n - 1 - i) * a.ig.stride];
+                    ynk = (i == 0) ? T(0) : src[off + (long long)(i - 1) * a.ig.stride];
+                }
+                // e^{+i pi k/2n} = conj(W_{4n}^k); the table for these modes holds W_{4n}^k, k < 4n ... stored after the first m entries
+                cplx<T> w = ldg_c<T>(tw + m + i);
+                cplx<T> z = mk<T>(yk, -ynk);
+                x = cmul(z, mk<T>(w.x, -w.y));
+                x = cswap(x); // backward engine
+            }else if (a.mode == mode_dct1){
+                // even extension of length m = 2(n-1): s_i = x_i (i < n), s_{m-i} = x_i
+                int src = (i < n) ? i : m - i;
+                T v = reinterpret_cast<const T*>(a.in)[off + (long long)src * a.ig.stride];
+                x = mk<T>(v, 0);
+            }else{
+                x = generic_load<T>(a, a.in, off, i);
+            }
+        }
+        buf0[t * m + i] = x;
+    }
+    __syncthreads();
+
+    // ---- Stockham passes by factor -----------------------------------------------------------------------
+    cplx<T> *src = buf0, *dst = buf1;
+    int ns = 1;
+    for(int f=0; f<a.nfactors; f++){
+        const int p = a.factors[f];
+        const int np = m / p;            // butterflies per line
+        const int step = m / (ns * p);
+        for(int idx = threadIdx.x; idx < total; idx += blockDim.x){
+            int t = idx / m, o = idx - t * m;
+            int k = o % ns;
+            int rp = (o / ns) % p;
+            int blk = o / (ns * p);
+            int q = blk * ns + k;
+            long long base = ((long long)k * step + (long long)rp * np) % m;
+            const cplx<T> *s = src + t * m + q;
+            cplx<T> acc = s[0];
+            int e = 0;
+            for(int r=1; r<p; r++){
+                e += (int)base; if (e >= m) e -= m;
+                acc = cadd(acc, cmul(s[r * np], ldg_c<T>(tw + e)));
+            }
+            dst[t * m + o] = acc;
+        }
+        __syncthreads();
+        cplx<T> *tmp = src; src = dst; dst = tmp;
+        ns *= p;
+    }
+
+    // ---- store -------------------------------------------------------------------------------------------
+    const T scale = static_cast<T>(a.scale);
+    int nout;
+    switch(a.mode){
+        case mode_r2c: nout = n / 2 + 1; break;
+        default: nout = n;
+    }
+    const int total_out = lpb * nout;
+    for(int idx = threadIdx.x; idx < total_out; idx += blockDim.x){
+        int t, i;
+        if (a.lines_fast){ t = idx % lpb; i = idx / lpb; } else { i = idx % nout; t = idx / nout; }
+        long long line = line0 + t;
+        if (line >= a.nlines) continue;
+        long long off = line_offset(a.og, a.count_a, line);
+        const cplx<T> *res = src + t * m;
+        switch(a.mode){
+            case mode_c2c: {
+                cplx<T> x = res[i];
+                if (a.backward) x = cswap(x);
+                x.x *= scale; x.y *= scale;
+                reinterpret_cast<cplx<T>*>(a.out)[off + (long long)i * a.og.stride] = x;
+            } break;
+            case mode_r2c: {
+                cplx<T> x = res[i];
+                x.x *= scale; x.y *= scale;
+                reinterpret_cast<cplx<T>*>(a.out)[off + (long long)i * a.og.stride] = x;
+            } break;
+            case mode_c2r: {
+                // engine ran forward on swapped input: result = swap(ifft); real part sits in .y
+                reinterpret_cast<T*>(a.out)[off + (long long)i * a.og.stride] = res[i].y * scale;
+            } break;
+            case mode_dct2: {
+                // y_k = 2 Re( e^{-i pi k / 2n} V_k ),  e^{-i pi k/2n} = W_{4n}^k
+                cplx<T> w = ldg_c<T>(tw + m + i);
+                cplx<T> z = cmul(res[i], w);
+                reinterpret_cast<T*>(a.out)[off + (long long)i * a.og.stride] = T(2) * z.x * scale;
+            } break;
+            case mode_dst2: {
+                cplx<T> w = ldg_c<T>(tw + m + (n - 1 - i));
+                cplx<T> z = cmul(res[n - 1 - i], w);
+                reinterpret_cast<T*>(a.out)[off + (long long)i * a.og.stride] = T(2) * z.x * scale;
+            } break;
+            case mode_dct3: case mode_dst3: {
+                // v = ifft(V) * n is in res (swapped: real part in .y); x_{2i} = v_i, x_{2i+1} = v_{n-1-i}
+                int srcpos = (i & 1) ? (n - 1 - (i >> 1)) : (i >> 1);
+                T v = res[srcpos].y * T(2);
+                if (a.mode == mode_dst3 && (i & 1)) v = -v;
+                reinterpret_cast<T*>(a.out)[off + (long long)i * a.og.stride] = v * scale;
+            } break;
+            case mode_dct1: {
+                T v = res[i].x;
+                if (a.backward) v *= T(2);
+                reinterpret_cast<T*>(a.out)[off + (long long)i * a.og.stride] = v * scale;
+            } break;
+        }
+    }
+}
+
+} // namespace b200

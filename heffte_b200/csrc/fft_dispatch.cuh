@@ -1,0 +1,67 @@
+// Kernel selection for the batched 1-D FFT executors: maps (precision, length, access pattern) to one
+// instantiation of the kernels in fft_device.cuh.  The Launcher policy is the only thing that differs between the
+// product (CUDA launch on a stream) and the CPU emulation used by tests/emul.
+#pragma once
+
+#include "fft_device.cuh"
+
+namespace b200 {
+
+// tile shape of the strided kernel: a row of the tile is LPB adjacent lines = 128 bytes when possible
+template<typename T> struct row_lines { static constexpr int value = 128 / (2 * sizeof(T)); }; // 8 (fp64) / 16 (fp32)
+
+constexpr bool is_pow2(long long n){ return n > 0 && (n & (n - 1)) == 0; }
+
+// largest power-of-two length handled by the register/shared-memory kernels
+constexpr int pow2_max = 4096;
+constexpr int pow2_min = 16;
+
+template<typename T, typename RL, int TPL, int LPB, int MINB, typename Launcher>
+int launch_strided(fft_args const &a, Launcher &L){
+    long long blocks = (a.nlines + LPB - 1) / LPB;
+    size_t smem = sizeof(cplx<T>) * (size_t)RL::N * LPB;
+    return L.launch(fft_strided_kernel<T, RL, TPL, LPB, MINB>, blocks, TPL * LPB, smem, a);
+}
+template<typename T, typename RL, int LPB, int MINB, typename Launcher>
+int launch_contig(fft_args const &a, Launcher &L){
+    long long blocks = (a.nlines + LPB - 1) / LPB;
+    constexpr int PITCH = pad_index(RL::N) + 1;
+    size_t smem = sizeof(cplx<T>) * (size_t)PITCH * LPB;
+    return L.launch(fft_contig_kernel<T, RL, LPB, MINB>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
+}
+
+// M = lines-per-row multiplier: 1 for double (8 lines = 128 B), 2 for float (16 lines = 128 B)
+template<typename T, typename Launcher>
+int dispatch_strided(int n, fft_args const &a, Launcher &L){
+    constexpr int M = row_lines<T>::value / 8;
+    switch(n){
+        case 16:   return launch_strided<T, radix_list<4, 4, 1, 1>,   4 / M, 32 * M, 2>(a, L);
+        case 32:   return launch_strided<T, radix_list<8, 4, 1, 1>,   4 / M, 32 * M, 2>(a, L);
+        case 64:   return launch_strided<T, radix_list<8, 8, 1, 1>,   8 / M, 16 * M, 2>(a, L);
+        case 128:  return launch_strided<T, radix_list<8, 4, 4, 1>,  16 / M,  8 * M, 2>(a, L);
+        case 256:  return launch_strided<T, radix_list<8, 8, 4, 1>,  32 / M,  8 * M, 2>(a, L);
+        case 512:  return launch_strided<T, radix_list<8, 8, 8, 1>,  32 / M,  8 * M, 3>(a, L);
+        case 1024: return launch_strided<T, radix_list<16, 8, 8, 1>, 32 / M,  8 * M, 1>(a, L);
+        case 2048: return launch_strided<T, radix_list<8, 8, 8, 4>, 128 / M,  4 * M, 1>(a, L);
+        case 4096: return launch_strided<T, radix_list<8, 8, 8, 8>, 256 / M,  2 * M, 1>(a, L);
+        default: return -1;
+    }
+}
+
+template<typename T, typename Launcher>
+int dispatch_contig(int n, fft_args const &a, Launcher &L){
+    switch(n){
+        case 16:   return launch_contig<T, radix_list<4, 4, 1, 1>,   64, 2>(a, L);
+        case 32:   return launch_contig<T, radix_list<8, 4, 1, 1>,   64, 2>(a, L);
+        case 64:   return launch_contig<T, radix_list<8, 8, 1, 1>,   32, 2>(a, L);
+        case 128:  return launch_contig<T, radix_list<8, 4, 4, 1>,   16, 2>(a, L);
+        case 256:  return launch_contig<T, radix_list<8, 8, 4, 1>,    8, 2>(a, L);
+        case 512:  return launch_contig<T, radix_list<8, 8, 8, 1>,    4, 3>(a, L);
+        case 1024: return launch_contig<T, radix_list<16, 8, 8, 1>,   4, 2>(a, L);
+        case 2048: return launch_contig<T, radix_list<8, 8, 8, 4>,    1, 2>(a, L);
+        case 4096: return launch_contig<T, radix_list<8, 8, 8, 8>,    1, 1>(a, L);
+        default: return -1;
+    }
+}
+
+} // namespace b200

@@ -1,0 +1,153 @@
+// Pure host-side planning of a batched 1-D transform (no CUDA calls): kernel family, engine length,
+// factorisation, tile shape and the twiddle table.  Shared by fft1d.cu and by the CPU emulation in tests/emul.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "../../include/heffte_b200_kernels.h"
+#include "fft_dispatch.cuh"
+
+namespace b200 {
+
+enum kernel_family { family_strided = 0, family_contig = 1, family_generic = 2 };
+
+struct host_plan {
+    b200_fft1d_desc desc;
+    kernel_family family = family_generic;
+    int m = 0;              // engine (complex FFT) length
+    int lpb = 1;            // generic: lines per block
+    int lines_fast = 0;     // generic: neighbouring lines are adjacent in memory
+    int nfactors = 0;
+    int factors[24];
+    size_t smem = 0;        // generic: dynamic shared memory
+    int threads = 256;      // generic: block size
+    long long table_main = 0, table_extra_mod = 1, table_extra = 0;  // twiddle table layout
+};
+
+inline std::vector<int> factorize(int m){
+    std::vector<int> f;
+    while(m % 4 == 0){ f.push_back(4); m /= 4; }
+    while(m % 2 == 0){ f.push_back(2); m /= 2; }
+    for(int p = 3; (long long)p * p <= m; p += 2)
+        while(m % p == 0){ f.push_back(p); m /= p; }
+    if (m > 1) f.push_back(m);
+    return f;
+}
+
+// W_m^k = exp(-2 pi i k / m) evaluated in long double, rounded once to the working precision
+template<typename T>
+void fill_twiddles(std::vector<T> &table, size_t offset, long long m, long long count){
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for(long long k=0; k<count; k++){
+        long double angle = two_pi * static_cast<long double>(k % m) / static_cast<long double>(m);
+        table[2 * (offset + k)]     = static_cast<T>(cosl(angle));
+        table[2 * (offset + k) + 1] = static_cast<T>(-sinl(angle));
+    }
+}
+template<typename T>
+std::vector<T> make_twiddle_table(host_plan const &plan){
+    std::vector<T> table(2 * (plan.table_main + plan.table_extra));
+    fill_twiddles<T>(table, 0, plan.table_main, plan.table_main);
+    if (plan.table_extra > 0) fill_twiddles<T>(table, plan.table_main, plan.table_extra_mod, plan.table_extra);
+    return table;
+}
+
+// returns 0 or a B200_ERR_* code; `why` receives the reason on failure
+inline int make_host_plan(b200_fft1d_desc const &desc, host_plan &plan, const char **why){
+    *why = "";
+    if (desc.n < 1 or desc.count_a < 0 or desc.count_b < 0){ *why = "bad sizes"; return B200_ERR_INVALID; }
+    if (desc.precision != B200_PREC_FLOAT and desc.precision != B200_PREC_DOUBLE){ *why = "bad precision"; return B200_ERR_INVALID; }
+    if (desc.kind < B200_C2C or desc.kind > B200_COS1){ *why = "bad kind"; return B200_ERR_INVALID; }
+    if (desc.n > 2147483647LL / 8){ *why = "length too large"; return B200_ERR_UNSUPPORTED; }
+    if (desc.kind == B200_COS1 and desc.n < 2){ *why = "DCT-I needs at least 2 points"; return B200_ERR_INVALID; }
+    plan.desc = desc;
+    const int n = static_cast<int>(desc.n);
+    const size_t csize = (desc.precision == B200_PREC_FLOAT) ? 8 : 16;
+
+    bool const fast_path = (desc.kind == B200_C2C) and is_pow2(n) and n >= pow2_min and n <= pow2_max;
+    if (fast_path){
+        bool const contiguous = (desc.in.stride == 1 or desc.out.stride == 1);
+        plan.family = contiguous ? family_contig : family_strided;
+        plan.m = n;
+        plan.table_main = n;
+        return B200_SUCCESS;
+    }
+    plan.family = family_generic;
+    plan.m = (desc.kind == B200_COS1) ? 2 * (n - 1) : n;
+    auto f = factorize(plan.m);
+    if (f.size() > 24){ *why = "too many prime factors"; return B200_ERR_UNSUPPORTED; }
+    plan.nfactors = static_cast<int>(f.size());
+    for(size_t i=0; i<f.size(); i++) plan.factors[i] = f[i];
+    // lines per block: aim at ~4096 points per CTA; the two Stockham buffers must fit shared memory
+    size_t const per_line = 2 * csize * static_cast<size_t>(plan.m);
+    size_t const budget = 200 * 1024;
+    if (per_line > budget){ *why = "transform length exceeds the shared-memory engine"; return B200_ERR_UNSUPPORTED; }
+    long long lpb = std::max<long long>(1, 4096 / plan.m);
+    lpb = std::min<long long>(lpb, static_cast<long long>(budget / per_line));
+    lpb = std::min<long long>(lpb, 64);
+    long long const nlines = desc.count_a * desc.count_b;
+    lpb = std::max<long long>(1, std::min<long long>(lpb, nlines));
+    plan.lpb = static_cast<int>(lpb);
+    plan.smem = per_line * lpb;
+    plan.lines_fast = (desc.in.stride != 1 and desc.in.stride_a == 1) ? 1 : 0;
+    long long const work = lpb * plan.m;
+    plan.threads = (work >= 256) ? 256 : ((work >= 128) ? 128 : ((work >= 64) ? 64 : 32));
+    plan.table_main = plan.m;
+    if (desc.kind == B200_COS or desc.kind == B200_SIN){ plan.table_extra_mod = 4LL * n; plan.table_extra = n; }
+    return B200_SUCCESS;
+}
+
+inline line_geom to_geom(b200_line_geom const &g){ return line_geom{g.stride, g.stride_a, g.stride_b}; }
+
+// runs the plan through a Launcher (CUDA stream launcher in the product, thread emulation in tests/emul)
+template<typename Launcher>
+int run_host_plan(host_plan const &plan, const void *twiddle, int direction, const void *in, void *out, double scale, Launcher &L){
+    b200_fft1d_desc const &d = plan.desc;
+    long long const nlines = d.count_a * d.count_b;
+    if (nlines == 0) return B200_SUCCESS;
+    bool const backward = (direction == B200_BACKWARD);
+    bool const is_float = (d.precision == B200_PREC_FLOAT);
+
+    if (plan.family != family_generic){
+        fft_args a;
+        a.in = in; a.out = out; a.twiddle = twiddle;
+        a.ig = to_geom(backward ? d.out : d.in);   // backward swaps the roles of the two geometries
+        a.og = to_geom(backward ? d.in : d.out);
+        a.nlines = nlines;
+        a.count_a = static_cast<int>(d.count_a);
+        a.backward = backward ? 1 : 0;
+        a.scale = scale;
+        if (plan.family == family_strided)
+            return is_float ? dispatch_strided<float>(static_cast<int>(d.n), a, L) : dispatch_strided<double>(static_cast<int>(d.n), a, L);
+        return is_float ? dispatch_contig<float>(static_cast<int>(d.n), a, L) : dispatch_contig<double>(static_cast<int>(d.n), a, L);
+    }
+
+    generic_args g;
+    g.in = in; g.out = out; g.twiddle = twiddle;
+    g.ig = to_geom(backward ? d.out : d.in);
+    g.og = to_geom(backward ? d.in : d.out);
+    g.nlines = nlines;
+    g.count_a = static_cast<int>(d.count_a);
+    g.backward = backward ? 1 : 0;
+    g.scale = scale;
+    g.n = static_cast<int>(d.n);
+    g.m = plan.m;
+    g.lpb = plan.lpb;
+    g.lines_fast = plan.lines_fast;
+    g.nfactors = plan.nfactors;
+    for(int i=0; i<24; i++) g.factors[i] = (i < plan.nfactors) ? plan.factors[i] : 1;
+    switch(d.kind){
+        case B200_C2C:  g.mode = mode_c2c; break;
+        case B200_R2C:  g.mode = backward ? mode_c2r : mode_r2c; break;
+        case B200_COS:  g.mode = backward ? mode_dct3 : mode_dct2; break;
+        case B200_SIN:  g.mode = backward ? mode_dst3 : mode_dst2; break;
+        default:        g.mode = mode_dct1; break;
+    }
+    long long const blocks = (nlines + plan.lpb - 1) / plan.lpb;
+    if (is_float) return L.launch(fft_generic_kernel<float>, blocks, plan.threads, plan.smem, g);
+    return L.launch(fft_generic_kernel<double>, blocks, plan.threads, plan.smem, g);
+}
+
+} // namespace b200

@@ -1,0 +1,37 @@
+// Host-side runtime helpers shared by the translation units of libheffte_b200.so:
+// error reporting for the C ABI, the launch counter and the CUDA launcher policy.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_set>
+
+#include "../../include/heffte_b200_kernels.h"
+
+namespace b200 {
+
+void set_error(std::string const &message);
+int fail(int code, std::string const &message);
+int check_cuda(cudaError_t status, const char *what);
+extern std::atomic<long long> launch_counter;
+
+// raises the dynamic shared-memory limit of a kernel once (needed above 48 KB)
+void allow_smem(const void *kernel, size_t bytes);
+
+struct cuda_launcher {
+    cudaStream_t stream;
+    template<typename kernel_t, typename args_t>
+    int launch(kernel_t kernel, long long blocks, int threads, size_t smem, args_t const &args){
+        if (blocks <= 0) return B200_SUCCESS;
+        if (blocks > 2147483647LL) return fail(B200_ERR_UNSUPPORTED, "grid too large");
+        if (smem > 48 * 1024) allow_smem(reinterpret_cast<const void*>(kernel), smem);
+        kernel<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(args);
+        launch_counter.fetch_add(1, std::memory_order_relaxed);
+        return check_cuda(cudaPeekAtLastError(), "kernel launch");
+    }
+};
+
+} // namespace b200

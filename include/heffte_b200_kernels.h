@@ -1,0 +1,112 @@
+/*
+ * heffte_b200_kernels.h -- C ABI of the device layer of the B200 backend (libheffte_b200.so).
+ *
+ * This is the thin layer the host C++ (heffte::backend::b200 plug-in, include/heffte_b200.hpp) calls instead of
+ * cuFFT and the reference's own CUDA kernels.  Plain pointers, sizes and a cudaStream_t (passed as void*);
+ * every function returns 0 on success or a non-zero error code (b200_last_error() gives the text) and never
+ * throws.  All data pointers are DEVICE pointers.  There is no CPU fallback: without a CUDA device the calls fail.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to icl-utk-edu/heffte v2.4.1).
+ */
+#ifndef HEFFTE_B200_KERNELS_H
+#define HEFFTE_B200_KERNELS_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* precision / transform selectors */
+#define B200_PREC_FLOAT  0
+#define B200_PREC_DOUBLE 1
+
+#define B200_FORWARD  0
+#define B200_BACKWARD 1
+
+/* kind of batched 1-D transform */
+#define B200_C2C   0   /* complex <-> complex, in-place capable                                              */
+#define B200_R2C   1   /* forward: real n -> complex n/2+1 ; backward: complex n/2+1 -> real n (unnormalised) */
+#define B200_COS   2   /* forward REDFT10 (DCT-II), backward 2*REDFT01 (DCT-III)  == reference cufft_cos      */
+#define B200_SIN   3   /* forward RODFT10 (DST-II), backward 2*RODFT01 (DST-III)  == reference cufft_sin      */
+#define B200_COS1  4   /* forward REDFT00 (DCT-I),  backward 2*REDFT00            == reference cufft_cos1     */
+
+/* error codes */
+#define B200_SUCCESS            0
+#define B200_ERR_INVALID        1
+#define B200_ERR_UNSUPPORTED    2
+#define B200_ERR_CUDA           3
+#define B200_ERR_NCCL           4
+#define B200_ERR_NO_DEVICE      5
+
+const char* b200_last_error(void);
+/* number of kernels launched by this library since load (used by bench.py for "gpu_launches") */
+long long b200_launch_count(void);
+int b200_device_count(void);
+
+/*
+ * Batched strided 1-D FFT plan.
+ * Replaces: heffte::plan_cufft / plan_cufft_r2c (include/heffte_backend_cuda.h:346-422, 580-621), i.e.
+ * cufftMakePlanMany(size, howmany, stride, dist) -- but with TWO batch dimensions so the "blocks" loop the
+ * reference needs for the middle dimension (heffte_backend_cuda.h:452, 496-499) is a single launch, and with
+ * separate input/output geometry so packing/transposition can be fused into the transform.
+ *
+ * Line l in [0, count_a*count_b): a = l % count_a, b = l / count_a.
+ * Element i of line l is at  base + a*stride_a + b*stride_b + i*stride  (units: elements of that side's type:
+ * complex for C2C, real on the real side of R2C / r2r).
+ */
+typedef struct {
+    long long stride, stride_a, stride_b;
+} b200_line_geom;
+
+typedef struct {
+    int precision;          /* B200_PREC_* */
+    int kind;               /* B200_C2C ... */
+    long long n;            /* transform length (real-space length for R2C and r2r) */
+    long long count_a, count_b;
+    b200_line_geom in;      /* geometry of the forward input  == backward output */
+    b200_line_geom out;     /* geometry of the forward output == backward input  */
+} b200_fft1d_desc;
+
+typedef struct b200_fft1d_plan_s* b200_fft1d_plan;
+
+int b200_fft1d_create(const b200_fft1d_desc *desc, b200_fft1d_plan *plan);
+int b200_fft1d_destroy(b200_fft1d_plan plan);
+/* Replaces cufftExec{C2C,Z2Z,R2C,D2Z,C2R,Z2D} (heffte_backend_cuda.h:494-524, 694-727) and, through `scale`,
+ * the separate scaling kernel (src/heffte_backend_cuda.cu:138-145, 471-478).  in == out is allowed for C2C/r2r
+ * when the two geometries coincide. */
+int b200_fft1d_execute(b200_fft1d_plan plan, int direction, const void *in, void *out, double scale, void *stream);
+/* name of the kernel family the plan resolved to ("strided", "contig", "generic"), for tests and profiling */
+const char* b200_fft1d_kernel_name(b200_fft1d_plan plan);
+
+/*
+ * Sub-box copy between a strided box and a dense buffer.
+ * Replaces heffte::cuda::direct_pack / direct_unpack (src/heffte_backend_cuda.cu:61-85, 385-402):
+ *   pack:   dst[(s*nmid + m)*nfast + f] = src[s*plane_stride + m*line_stride + f]
+ *   unpack: dst[s*plane_stride + m*line_stride + f] = src[(s*nmid + m)*nfast + f]
+ * elem_bytes in {4, 8, 16}.
+ */
+int b200_direct_pack(int elem_bytes, long long nfast, long long nmid, long long nslow,
+                     long long line_stride, long long plane_stride, const void *src, void *dst, void *stream);
+int b200_direct_unpack(int elem_bytes, long long nfast, long long nmid, long long nslow,
+                       long long line_stride, long long plane_stride, const void *src, void *dst, void *stream);
+/*
+ * Unpack with axis permutation.
+ * Replaces heffte::cuda::transpose_unpack (src/heffte_backend_cuda.cu:90-133, 404-441):
+ *   idx = (f, m, s);  dst[s*plane_stride + m*line_stride + f] = src[idx[map0] + idx[map1]*buff_line_stride + idx[map2]*buff_plane_stride]
+ */
+int b200_transpose_unpack(int elem_bytes, long long nfast, long long nmid, long long nslow,
+                          long long line_stride, long long plane_stride,
+                          long long buff_line_stride, long long buff_plane_stride,
+                          int map0, int map1, int map2, const void *src, void *dst, void *stream);
+/* Replaces heffte::cuda::scale_data (src/heffte_backend_cuda.cu:138-145, 471-478): data[i] *= factor over `count` reals. */
+int b200_scale(int precision, long long count, void *data, double factor, void *stream);
+/* Replaces heffte::cuda::convert (src/heffte_backend_cuda.cu:44-56, 352-361): real -> complex (zero imaginary) and complex -> real. */
+int b200_convert_r2c(int precision, long long count, const void *real_src, void *complex_dst, void *stream);
+int b200_convert_c2r(int precision, long long count, const void *complex_src, void *real_dst, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
