@@ -1,0 +1,52 @@
+// Communicator abstraction of the b200 backend.
+// The reference is hard-wired to MPI (MPI_Alltoallv / MPI_Send / MPI_Irecv in src/heffte_reshape3d.cpp:272, 402, 551-713;
+// MPI_Allgather of the boxes in include/heffte_geometry.h:707-718).  Here one rank drives one GPU and the data path is
+// NCCL grouped send/recv over NVLink, stream-ordered (no host synchronisation); the only host-side collective is the
+// plan-time allgather of the boxes.  The NCCL library is resolved at run time (dlopen of libnccl.so.2) so that the
+// copy already loaded by PyTorch is shared when the backend is used from Python.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <string>
+#include <vector>
+
+namespace b200 {
+
+struct transfer {
+    int peer;
+    void *data;          // device pointer
+    size_t bytes;
+};
+
+class communicator {
+public:
+    virtual ~communicator() = default;
+    int rank() const { return my_rank; }
+    int size() const { return nranks; }
+    // host-to-host allgather of `bytes` per rank (plan time only); returns 0 on success
+    virtual int allgather(const void *mine, void *all, size_t bytes) = 0;
+    // one grouped exchange of device buffers on `stream` (stream ordered, asynchronous to the host)
+    virtual int exchange(std::vector<transfer> const &sends, std::vector<transfer> const &recvs, cudaStream_t stream) = 0;
+    virtual int barrier(cudaStream_t stream) = 0;
+    virtual const char* kind() const = 0;
+protected:
+    int my_rank = 0, nranks = 1;
+};
+
+// single-rank communicator (no communication library involved)
+communicator* make_self_communicator();
+// NCCL communicator from a 128-byte unique id shared by all ranks; binds to the current CUDA device
+communicator* make_nccl_communicator(int rank, int size, const void *unique_id, std::string &error);
+// fills 128 bytes; returns 0 on success
+int nccl_unique_id(void *out128, std::string &error);
+
+// host-only communicator driven by callbacks (used by the CPU-side multi-process tests of the planning logic
+// and by callers that own a different transport); exchange() is the caller's callback
+typedef int (*allgather_callback)(void *context, const void *mine, void *all, size_t bytes);
+typedef int (*exchange_callback)(void *context, int nsend, const int *send_peer, void *const *send_ptr, const size_t *send_bytes,
+                                 int nrecv, const int *recv_peer, void *const *recv_ptr, const size_t *recv_bytes, void *stream);
+communicator* make_callback_communicator(int rank, int size, allgather_callback gather, exchange_callback exchange, void *context);
+
+} // namespace b200

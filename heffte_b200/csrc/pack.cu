@@ -1,0 +1,59 @@
+// C ABI of the packers, scaling and real<->complex conversion (see include/heffte_b200_kernels.h).
+#include "pack_host.h"
+#include "runtime.h"
+
+using namespace b200;
+
+extern "C" {
+
+int b200_direct_pack(int elem_bytes, long long nfast, long long nmid, long long nslow,
+                     long long line_stride, long long plane_stride, const void *src, void *dst, void *stream){
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    copy3d_args a{src, dst, nfast, nmid, nslow, line_stride, plane_stride, nfast, nfast * nmid};
+    int rc = launch_copy3d(elem_bytes, a, L);
+    return (rc == B200_ERR_INVALID) ? fail(rc, "element size must be 4, 8 or 16 bytes") : rc;
+}
+
+int b200_direct_unpack(int elem_bytes, long long nfast, long long nmid, long long nslow,
+                       long long line_stride, long long plane_stride, const void *src, void *dst, void *stream){
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    copy3d_args a{src, dst, nfast, nmid, nslow, nfast, nfast * nmid, line_stride, plane_stride};
+    int rc = launch_copy3d(elem_bytes, a, L);
+    return (rc == B200_ERR_INVALID) ? fail(rc, "element size must be 4, 8 or 16 bytes") : rc;
+}
+
+int b200_transpose_unpack(int elem_bytes, long long nfast, long long nmid, long long nslow,
+                          long long line_stride, long long plane_stride,
+                          long long buff_line_stride, long long buff_plane_stride,
+                          int map0, int map1, int map2, const void *src, void *dst, void *stream){
+    int seen[3] = {0, 0, 0};
+    int const map[3] = {map0, map1, map2};
+    for(int k=0; k<3; k++){
+        if (map[k] < 0 or map[k] > 2) return fail(B200_ERR_INVALID, "map must be a permutation of 0,1,2");
+        seen[map[k]]++;
+    }
+    if (seen[0] != 1 or seen[1] != 1 or seen[2] != 1) return fail(B200_ERR_INVALID, "map must be a permutation of 0,1,2");
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    permute_args a = transpose_unpack_args(nfast, nmid, nslow, line_stride, plane_stride, buff_line_stride, buff_plane_stride,
+                                           map0, map1, map2, src, dst);
+    int rc = launch_permute(elem_bytes, a, L);
+    if (rc == B200_ERR_INVALID) return fail(rc, "element size must be 4, 8 or 16 bytes");
+    if (rc == B200_ERR_UNSUPPORTED) return fail(rc, "box too large for the tiled permutation");
+    return rc;
+}
+
+int b200_scale(int precision, long long count, void *data, double factor, void *stream){
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    return launch_scale(precision, count, data, factor, L);
+}
+
+int b200_convert_r2c(int precision, long long count, const void *real_src, void *complex_dst, void *stream){
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    return launch_convert(precision, true, count, real_src, complex_dst, L);
+}
+int b200_convert_c2r(int precision, long long count, const void *complex_src, void *real_dst, void *stream){
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    return launch_convert(precision, false, count, complex_src, real_dst, L);
+}
+
+} // extern "C"

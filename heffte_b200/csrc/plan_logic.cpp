@@ -1,0 +1,227 @@
+#include "plan_logic.h"
+
+namespace b200 {
+
+namespace {
+
+// smallest dimension id not present in `taken`
+int unused_dim(std::array<int, 3> const &taken){
+    for(int d=0; d<3; d++) if (taken[0] != d and taken[1] != d and taken[2] != d) return d;
+    return -1;
+}
+
+// bring `dim` to the front of an order by swapping it with whatever is there
+std::array<int, 3> lead_with(std::array<int, 3> order, int dim){
+    for(int i=1; i<3; i++) if (order[0] != dim and order[i] == dim) std::swap(order[0], order[i]);
+    return order;
+}
+
+shape halve_all(shape const &boxes, int r2c_direction){
+    if (r2c_direction == -1) return boxes;
+    shape r; r.reserve(boxes.size());
+    for(auto const &b : boxes) r.push_back(b.halved(r2c_direction));
+    return r;
+}
+
+struct planner {
+    box3 world_in, world_out;
+    shape const &inboxes, &outboxes;
+    int r2c;
+    plan_options const &opt;
+    rank_subset const &subset;
+    std::array<int, 2> grid;
+    int nworking;
+
+    planner(shape const &in, shape const &out, int r2c_direction, plan_options const &o, rank_subset const &s)
+        : world_in(bounding_box(in)), world_out(bounding_box(out)), inboxes(in), outboxes(out), r2c(r2c_direction), opt(o), subset(s){
+        nworking = subset.everybody() ? static_cast<int>(in.size()) : subset.active;
+        grid = grid2d(nworking);
+    }
+
+    // geometry for an FFT along `dim`: jump straight to `target` when it already has full lines in all of `need`
+    shape stage_for(box3 const &world, int dim, shape const &current, box3 const &target_world, std::vector<int> const &need, shape const &target) const {
+        bool const target_ok = spans(target_world, target, need);
+        if (opt.use_reorder){
+            if (target_ok) return (target[0].order[0] == dim) ? target : with_order(target, lead_with(target.front().order, dim));
+            return pencils(world, grid, dim, current, lead_with(current.front().order, dim), subset);
+        }
+        return target_ok ? target : pencils(world, grid, dim, current, world.order, subset);
+    }
+
+    // first stage of an r2c transform: the output boxes are already shortened, so stretch them back before comparing
+    shape first_stage(int dim) const {
+        if (r2c != -1 and spans(world_out, outboxes, std::vector<int>{0, 1, 2})){
+            shape stretched;
+            for(auto const &b : outboxes){
+                box3 s = b;
+                s.low[r2c] = world_in.low[r2c];
+                s.high[r2c] = world_in.high[r2c];
+                stretched.push_back(s);
+            }
+            return stage_for(world_in, dim, inboxes, world_in, {0, 1, 2}, stretched);
+        }
+        return stage_for(world_in, dim, inboxes, world_out, {0, 1, 2}, outboxes);
+    }
+
+    shape slab_order(shape const &s, int dim) const {
+        if (not opt.use_reorder or s.front().order[0] == dim) return s;
+        return with_order(s, lead_with(s.front().order, dim));
+    }
+
+    logic_plan finish(shape const &s0, shape const &after0, shape const &s1, shape const &s2, std::array<int, 3> dirs) const {
+        logic_plan p;
+        p.in_shape[0] = inboxes; p.in_shape[1] = after0; p.in_shape[2] = s1; p.in_shape[3] = s2;
+        p.out_shape[0] = s0;     p.out_shape[1] = s1;    p.out_shape[2] = s2; p.out_shape[3] = outboxes;
+        p.fft_sizes = {{world_in.size(0), world_in.size(1), world_in.size(2)}};
+        p.fft_direction = dirs;
+        p.index_count = world_in.count();
+        p.options = opt;
+        p.rank = subset.my_rank;
+        return p;
+    }
+
+    logic_plan by_pencils() const {
+        std::array<int, 3> dir{{-1, -1, -1}};
+        // first direction: forced by r2c, else one in which the input already holds full lines
+        if (r2c != -1) dir[0] = r2c;
+        else for(int d=0; d<3 and dir[0] == -1; d++) if (spans(world_in, inboxes, d)) dir[0] = d;
+        // input that is a slab: its second full direction becomes the second transform
+        if (dir[0] != -1 and spans(world_in, inboxes, dir[0]))
+            for(int d=0; d<3 and dir[1] == -1; d++) if (d != dir[0] and spans(world_out, inboxes, d)) dir[1] = d;
+        // last direction: one in which the output holds full lines
+        for(int d=0; d<3 and dir[2] == -1; d++) if (d != dir[0] and d != dir[1] and spans(world_out, outboxes, d)) dir[2] = d;
+        if (dir[0] == -1) dir[0] = unused_dim(dir);
+
+        shape s0 = first_stage(dir[0]);
+        shape after0 = halve_all(s0, r2c);
+
+        if (dir[1] == -1){
+            // (the reference walks d = 0,1,2: a direction with full lines wins, the fallback is taken after d = 0)
+            for(int d=0; d<3; d++){
+                if (d != dir[0] and d != dir[2] and spans(world_out, after0, d)){ dir[1] = d; break; }
+                if (dir[1] == -1) dir[1] = unused_dim(dir);
+            }
+        }
+        if (dir[2] == -1) dir[2] = unused_dim(dir);
+
+        shape s1 = stage_for(world_out, dir[1], after0, world_out, {dir[1], dir[2]}, outboxes);
+        shape s2 = stage_for(world_out, dir[2], s1, world_out, {dir[2]}, outboxes);
+        return finish(s0, after0, s1, s2, dir);
+    }
+
+    logic_plan by_slabs() const {
+        if (world_in.is2d()) return by_pencils();
+        std::array<int, 3> dir{{-1, -1, -1}};
+
+        // (1) the input is already a slab
+        if (r2c == -1){
+            for(int a=0; a<3 and dir[0] == -1; a++)
+                for(int b=0; b<3; b++)
+                    if (a != b and spans2(world_in, inboxes, a, b)){ dir[0] = a; dir[1] = b; break; }
+        }else{
+            for(int b=0; b<3; b++)
+                if (b != r2c and spans2(world_in, inboxes, r2c, b)){ dir[0] = r2c; dir[1] = b; break; }
+        }
+        if (dir[0] != -1 and dir[1] != -1){
+            dir[2] = unused_dim(dir);
+            shape s0 = slab_order(inboxes, dir[0]);
+            shape after0 = halve_all(s0, r2c);
+            shape s1 = slab_order(after0, dir[1]);
+            shape s2 = stage_for(world_out, dir[2], s1, world_out, {dir[2]}, outboxes);
+            return finish(s0, after0, s1, s2, dir);
+        }
+
+        // (2) the output is a slab
+        for(int a=0; a<3 and dir[0] == -1; a++)
+            for(int b=0; b<3; b++)
+                if (a != b and a != r2c and b != r2c and spans2(world_out, outboxes, a, b)){ dir[1] = a; dir[2] = b; break; }
+        if (dir[1] != -1 and dir[2] != -1){
+            dir[0] = unused_dim(dir);
+            shape s0 = stage_for(world_in, dir[0], inboxes, world_out, {0, 1, 2}, outboxes);
+            shape after0 = halve_all(s0, r2c);
+            shape s1 = slab_order(outboxes, dir[1]);
+            shape s2 = slab_order(s1, dir[2]);
+            return finish(s0, after0, s1, s2, dir);
+        }
+
+        // (3) the input holds full lines in some direction
+        if (r2c == -1){
+            for(int d=0; d<3 and dir[0] == -1; d++) if (spans(world_in, inboxes, d)) dir[0] = d;
+        }else if (spans(world_in, inboxes, r2c)){
+            dir[0] = r2c;
+        }
+        if (dir[0] != -1){
+            dir[1] = unused_dim(dir);
+            dir[2] = unused_dim(dir);
+            shape s0 = stage_for(world_in, dir[0], inboxes, world_out, {0, 1, 2}, outboxes);
+            shape after0 = halve_all(s0, r2c);
+            shape sl = slabs(world_out, nworking, dir[1], dir[2], after0, world_out.order, subset);
+            shape s1 = slab_order(sl, dir[1]);
+            shape s2 = slab_order(sl, dir[2]);
+            return finish(s0, after0, s1, s2, dir);
+        }
+
+        // (4) bricks in, maybe full lines out: brick -> slab -> pencil (-> brick)
+        for(int d=0; d<3 and dir[2] == -1; d++) if (d != r2c and spans(world_out, outboxes, d)) dir[2] = d;
+        if (dir[2] != -1){
+            dir[0] = (r2c == -1) ? unused_dim(dir) : r2c;
+            dir[1] = unused_dim(dir);
+        }else{
+            dir[0] = (r2c != -1) ? r2c : 0;
+            dir[1] = unused_dim(dir);
+            dir[2] = unused_dim(dir);
+        }
+        shape sl = slabs(world_in, nworking, dir[0], dir[1], inboxes, world_in.order, subset);
+        shape s0 = slab_order(sl, dir[0]);
+        shape after0 = halve_all(s0, r2c);
+        shape s1 = slab_order(after0, dir[1]);
+        shape s2 = stage_for(world_out, dir[2], s1, world_out, {dir[2]}, outboxes);
+        return finish(s0, after0, s1, s2, dir);
+    }
+};
+
+bool one_order(shape const &s){
+    for(auto const &b : s) if (not b.same_order(s.front())) return false;
+    return true;
+}
+
+} // namespace
+
+logic_plan make_logic_plan(shape const &inboxes, shape const &outboxes, int r2c_direction, plan_options const &options, int rank){
+    if (inboxes.empty() or inboxes.size() != outboxes.size()) throw std::invalid_argument("need one input and one output box per rank");
+    rank_subset subset;
+    subset.my_rank = rank;
+    if (options.subranks > 0 and static_cast<size_t>(options.subranks) < inboxes.size())
+        subset.use_first(inboxes.size(), options.subranks);
+
+    box3 const world_in = bounding_box(inboxes), world_out = bounding_box(outboxes);
+    check_world(inboxes, world_in);
+    check_world(outboxes, world_out);
+    if (r2c_direction == -1){
+        if (not world_in.same_extent(world_out)) throw std::invalid_argument("input and output boxes span different index sets");
+    }else{
+        if (not world_in.halved(r2c_direction).same_extent(world_out)) throw std::invalid_argument("output boxes do not span the half-complex index set");
+    }
+    if (not one_order(inboxes) or not one_order(outboxes)) throw std::invalid_argument("all boxes of one side must share the same order");
+
+    planner p(inboxes, outboxes, r2c_direction, options, subset);
+    return options.use_pencils ? p.by_pencils() : p.by_slabs();
+}
+
+std::vector<std::array<int, 3>> stage_grids(logic_plan const &plan){
+    std::vector<std::array<int, 3>> grids;
+    for(int stage=0; stage<5; stage++){
+        shape const &s = (stage < 4) ? plan.in_shape[stage] : plan.out_shape[3];
+        std::vector<std::array<idx, 2>> seen[3];
+        for(auto const &b : s)
+            for(int d=0; d<3; d++){
+                std::array<idx, 2> range{{b.low[d], b.high[d]}};
+                if (range == std::array<idx, 2>{{0, -1}}) continue;
+                if (std::find(seen[d].begin(), seen[d].end(), range) == seen[d].end()) seen[d].push_back(range);
+            }
+        grids.push_back({{static_cast<int>(seen[0].size()), static_cast<int>(seen[1].size()), static_cast<int>(seen[2].size())}});
+    }
+    return grids;
+}
+
+} // namespace b200

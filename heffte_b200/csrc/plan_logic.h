@@ -1,0 +1,38 @@
+// Logic plan of the distributed transform: which boxes every rank holds before/after each of the four reshapes and
+// along which dimension each 1-D FFT stage runs.  The decisions reproduce the reference planner
+// (src/heffte_plan_logic.cpp:163-254 pencils, :273-422 slabs, :424-453 entry point; options in
+// include/heffte_plan_logic.h:48-57, 131-176) so that a b200 plan moves exactly the same sub-boxes between the same
+// ranks; tests/test_plan_logic.py compares every box with the reference's plan_operations().
+#pragma once
+
+#include "geometry.h"
+
+namespace b200 {
+
+// values match heffte::reshape_algorithm (include/heffte_plan_logic.h:48-57)
+enum reshape_algorithm : int { alg_alltoallv = 0, alg_p2p_plined = 1, alg_p2p = 2, alg_alltoall = 3 };
+
+struct plan_options {
+    bool use_reorder = false;       // default of the GPU backends (reference include/heffte_backend_cuda.h:854-857)
+    int algorithm = alg_alltoallv;
+    bool use_pencils = true;
+    bool use_gpu_aware = true;
+    int subranks = -1;
+};
+
+struct logic_plan {
+    shape in_shape[4], out_shape[4];
+    std::array<idx, 3> fft_sizes{{0, 0, 0}};
+    std::array<int, 3> fft_direction{{-1, -1, -1}};
+    idx index_count = 0;
+    plan_options options;
+    int rank = 0;
+};
+
+// r2c_direction = -1 for complex-to-complex and real-to-real transforms
+logic_plan make_logic_plan(shape const &inboxes, shape const &outboxes, int r2c_direction, plan_options const &options, int rank);
+
+// process-grid extents of the five stages (benchmark printout, reference src/heffte_plan_logic.cpp:460-487)
+std::vector<std::array<int, 3>> stage_grids(logic_plan const &plan);
+
+} // namespace b200

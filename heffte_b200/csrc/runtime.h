@@ -32,6 +32,14 @@ struct cuda_launcher {
         launch_counter.fetch_add(1, std::memory_order_relaxed);
         return check_cuda(cudaPeekAtLastError(), "kernel launch");
     }
+    template<typename kernel_t, typename args_t>
+    int launch3(kernel_t kernel, long long gx, long long gy, long long gz, int threads, size_t smem, args_t const &args){
+        if (gx <= 0 or gy <= 0 or gz <= 0) return B200_SUCCESS;
+        if (gx > 2147483647LL or gy > 65535 or gz > 65535) return fail(B200_ERR_UNSUPPORTED, "grid too large");
+        kernel<<<dim3((unsigned) gx, (unsigned) gy, (unsigned) gz), threads, smem, stream>>>(args);
+        launch_counter.fetch_add(1, std::memory_order_relaxed);
+        return check_cuda(cudaPeekAtLastError(), "kernel launch");
+    }
 };
 
 } // namespace b200

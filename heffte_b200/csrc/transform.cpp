@@ -1,0 +1,401 @@
+#include "transform.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace b200 {
+
+// defined in fft1d.cu
+void set_error(std::string const &message);
+int fail(int code, std::string const &message);
+
+namespace {
+
+inline char* advance(void *p, idx elements, int elem_bytes){ return static_cast<char*>(p) + elements * elem_bytes; }
+inline const char* advance(const void *p, idx elements, int elem_bytes){ return static_cast<const char*>(p) + elements * elem_bytes; }
+
+// geometry of the batch of lines of `box` that run along `dim`
+void line_layout(box3 const &box, int dim, b200_line_geom &g, long long &count_a, long long &count_b){
+    if (dim == box.order[0]){
+        g.stride = 1; g.stride_a = box.osize(0); g.stride_b = 0;
+        count_a = box.osize(1) * box.osize(2); count_b = 1;
+    }else if (dim == box.order[1]){
+        g.stride = box.osize(0); g.stride_a = 1; g.stride_b = box.osize(0) * box.osize(1);
+        count_a = box.osize(0); count_b = box.osize(2);
+    }else{
+        g.stride = box.osize(0) * box.osize(1); g.stride_a = 1; g.stride_b = 0;
+        count_a = box.osize(0) * box.osize(1); count_b = 1;
+    }
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// reshape
+// ------------------------------------------------------------------------------------------------------------
+reshape_op::reshape_op(shape const &in, shape const &out, int rank, communicator *c) : comm(c), me(rank){
+    box3 const &mine_in = in[me], &mine_out = out[me];
+    in_count = mine_in.count();
+    out_count = mine_out.count();
+    int const n = static_cast<int>(in.size());
+
+    auto receive_piece = [&](int peer, box3 const &source_box){
+        box3 ov = mine_out.overlap(source_box);
+        piece p{};
+        p.peer = peer;
+        p.offset = mine_out.offset_of(ov.low);
+        for(int d=0; d<3; d++) p.size[d] = ov.osize(d);
+        p.line = mine_out.osize(0);
+        p.plane = mine_out.osize(0) * mine_out.osize(1);
+        p.permuted = not source_box.same_order(mine_out);
+        p.buff_line = ov.size(source_box.order[0]);
+        p.buff_plane = ov.size(source_box.order[0]) * ov.size(source_box.order[1]);
+        for(int j=0; j<3; j++) p.map[j] = mine_out.position_of(source_box.order[j]);
+        p.count = ov.count();
+        return p;
+    };
+
+    if (extents_match(in, out)){
+        // same boxes, new order: a local permutation of my own data
+        local_permute = true;
+        if (not mine_out.empty()) recvs.push_back(receive_piece(me, mine_in));
+        return;
+    }
+
+    idx send_offset = 0, recv_offset = 0;
+    for(int i=0; i<n; i++){
+        int const peer = (i + me + 1) % n;      // same visiting order as the reference: self comes last
+        box3 ov = mine_in.overlap(out[peer]);
+        if (not ov.empty()){
+            piece p{};
+            p.peer = peer;
+            p.offset = mine_in.offset_of(ov.low);
+            for(int d=0; d<3; d++) p.size[d] = ov.osize(d);
+            p.line = mine_in.osize(0);
+            p.plane = mine_in.osize(0) * mine_in.osize(1);
+            p.count = ov.count();
+            p.buffer_offset = send_offset;
+            send_offset += p.count;
+            sends.push_back(p);
+        }
+        box3 ov_in = mine_out.overlap(in[peer]);
+        if (not ov_in.empty()){
+            piece p = receive_piece(peer, in[peer]);
+            p.buffer_offset = recv_offset;
+            recv_offset += p.count;
+            recvs.push_back(p);
+        }
+    }
+}
+
+int reshape_op::apply(int elem_bytes, const void *src, void *dst, void *workspace, cudaStream_t stream) const {
+    auto unpack = [&](piece const &p, const void *buffer) -> int {
+        void *target = advance(dst, p.offset, elem_bytes);
+        if (p.permuted)
+            return b200_transpose_unpack(elem_bytes, p.size[0], p.size[1], p.size[2], p.line, p.plane, p.buff_line, p.buff_plane,
+                                         p.map[0], p.map[1], p.map[2], buffer, target, stream);
+        return b200_direct_unpack(elem_bytes, p.size[0], p.size[1], p.size[2], p.line, p.plane, buffer, target, stream);
+    };
+
+    if (local_permute){
+        if (recvs.empty()) return B200_SUCCESS;
+        const void *from = src;
+        if (src == dst){
+            if (cudaMemcpyAsync(workspace, src, static_cast<size_t>(in_count) * elem_bytes, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+                return fail(B200_ERR_CUDA, "cudaMemcpyAsync failed in local reshape");
+            from = workspace;
+        }
+        return unpack(recvs[0], from);
+    }
+
+    char *send_buffer = static_cast<char*>(workspace);
+    char *recv_buffer = advance(workspace, in_count, elem_bytes);
+    const void *self_message = nullptr;
+
+    std::vector<transfer> outgoing, incoming;
+    for(auto const &p : sends){
+        char *slot = send_buffer + p.buffer_offset * elem_bytes;
+        int rc = b200_direct_pack(elem_bytes, p.size[0], p.size[1], p.size[2], p.line, p.plane,
+                                  advance(src, p.offset, elem_bytes), slot, stream);
+        if (rc) return rc;
+        if (p.peer == me) self_message = slot;
+        else outgoing.push_back({p.peer, slot, static_cast<size_t>(p.count) * elem_bytes});
+    }
+    for(auto const &p : recvs)
+        if (p.peer != me) incoming.push_back({p.peer, recv_buffer + p.buffer_offset * elem_bytes, static_cast<size_t>(p.count) * elem_bytes});
+
+    if (not outgoing.empty() or not incoming.empty()){
+        int rc = comm->exchange(outgoing, incoming, stream);
+        if (rc) return fail(B200_ERR_NCCL, "exchange failed in reshape");
+    }
+    for(auto const &p : recvs){
+        const void *message = (p.peer == me) ? self_message : recv_buffer + p.buffer_offset * elem_bytes;
+        if (message == nullptr) return fail(B200_ERR_INVALID, "inconsistent self overlap in reshape");
+        int rc = unpack(p, message);
+        if (rc) return rc;
+    }
+    return B200_SUCCESS;
+}
+
+std::unique_ptr<reshape_op> make_reshape(shape const &in, shape const &out, int me, communicator *comm){
+    if (extents_match(in, out)){
+        if (in[0].same_order(out[0])) return nullptr;
+        if (out[me].empty()) return nullptr;
+    }
+    return std::unique_ptr<reshape_op>(new reshape_op(in, out, me, comm));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// transform
+// ------------------------------------------------------------------------------------------------------------
+transform3d::transform3d(transform_kind kind, box3 const &inbox, box3 const &outbox, int r2c_direction,
+                         communicator *comm, plan_options const &options, cudaStream_t stream)
+    : tkind(kind), r2c_dir((kind == kind_r2c) ? r2c_direction : -1), ccomm(comm), cstream(stream){
+    for(int p=0; p<2; p++) for(int i=0; i<3; i++) exec[p][i] = nullptr;
+    me = comm->rank();
+    int const n = comm->size();
+
+    // plan-time allgather of (inbox, outbox): 18 64-bit integers per rank (reference include/heffte_geometry.h:707-718)
+    std::vector<long long> mine(18), all(18 * static_cast<size_t>(n));
+    for(int d=0; d<3; d++){
+        mine[d] = inbox.low[d]; mine[3+d] = inbox.high[d]; mine[6+d] = inbox.order[d];
+        mine[9+d] = outbox.low[d]; mine[12+d] = outbox.high[d]; mine[15+d] = outbox.order[d];
+    }
+    if (comm->allgather(mine.data(), all.data(), 18 * sizeof(long long)) != 0)
+        throw std::runtime_error("allgather of the boxes failed");
+    shape ins, outs;
+    for(int r=0; r<n; r++){
+        long long const *b = all.data() + 18 * r;
+        ins.push_back(box3({{b[0], b[1], b[2]}}, {{b[3], b[4], b[5]}}, {{(int) b[6], (int) b[7], (int) b[8]}}));
+        outs.push_back(box3({{b[9], b[10], b[11]}}, {{b[12], b[13], b[14]}}, {{(int) b[15], (int) b[16], (int) b[17]}}));
+    }
+
+    plan_options effective = options;
+    // the cosine / sine executors work on contiguous lines only in the reference (include/heffte_plan_logic.h:206-224);
+    // ours take any stride, but keeping the forced reorder keeps the intermediate shapes identical to cufft_cos/sin
+    if (kind == kind_cos or kind == kind_sin or kind == kind_cos1) effective.use_reorder = true;
+    lp = make_logic_plan(ins, outs, r2c_dir, effective, me);
+
+    inbox_count = lp.in_shape[0][me].count();
+    outbox_count = lp.out_shape[3][me].count();
+    base_scale = 1.0 / static_cast<double>(lp.index_count);
+    if (kind == kind_cos or kind == kind_sin) base_scale /= 64.0;
+    if (kind == kind_cos1) base_scale = 1.0 / (64.0 * (lp.fft_sizes[0] - 1) * (lp.fft_sizes[1] - 1) * (lp.fft_sizes[2] - 1));
+
+    for(int i=0; i<4; i++){
+        fwd[i] = make_reshape(lp.in_shape[i], lp.out_shape[i], me, comm);
+        bwd[3-i] = make_reshape(lp.out_shape[i], lp.in_shape[i], me, comm);
+    }
+
+    // workspace layout (reference include/heffte_fft3d.h:625-633, include/heffte_fft3d_r2c.h:335-339)
+    comm_count = 0;
+    for(int i=0; i<4; i++){
+        if (fwd[i]) comm_count = std::max(comm_count, fwd[i]->workspace_count());
+        if (bwd[i]) comm_count = std::max(comm_count, bwd[i]->workspace_count());
+    }
+    temp_count = 0;
+    for(int i=0; i<3; i++){
+        idx boxed = (i == 0 and kind == kind_r2c) ? lp.in_shape[1][me].count() : lp.out_shape[i][me].count();
+        temp_count = std::max(temp_count, boxed);
+    }
+    idx last_chunk = 0;
+    if (kind != kind_r2c and bwd[3]) last_chunk = (lp.out_shape[0][me].count() + 1) / 2;
+    workspace_count = comm_count + temp_count + last_chunk;
+}
+
+transform3d::~transform3d(){
+    for(int p=0; p<2; p++) for(int i=0; i<3; i++) if (exec[p][i]) b200_fft1d_destroy(exec[p][i]);
+    if (own_workspace) cudaFree(own_workspace);
+}
+
+double transform3d::scale_factor(int scaling) const {
+    if (scaling == 0) return 1.0;
+    return (scaling == 2) ? std::sqrt(base_scale) : base_scale;
+}
+
+int transform3d::ensure_executors(int precision){
+    if (exec_ready[precision]) return B200_SUCCESS;
+    for(int i=0; i<3; i++){
+        box3 const &box = lp.out_shape[i][me];
+        if (box.empty()) continue;
+        int const dim = lp.fft_direction[i];
+        b200_fft1d_desc d{};
+        d.precision = precision;
+        d.n = box.size(dim);
+        line_layout(box, dim, d.in, d.count_a, d.count_b);
+        d.out = d.in;
+        if (tkind == kind_r2c){
+            if (i == 0){
+                d.kind = B200_R2C;
+                long long ca, cb;
+                line_layout(lp.in_shape[1][me], dim, d.out, ca, cb);   // the shortened complex box
+            }else d.kind = B200_C2C;
+        }else d.kind = static_cast<int>(tkind);
+        int rc = b200_fft1d_create(&d, &exec[precision][i]);
+        if (rc) return rc;
+    }
+    exec_ready[precision] = true;
+    return B200_SUCCESS;
+}
+
+void* transform3d::ensure_workspace(int precision, int batch){
+    size_t const unit = (precision == B200_PREC_FLOAT ? 4 : 8) * ((tkind == kind_c2c or tkind == kind_r2c) ? 2 : 1);
+    size_t const need = static_cast<size_t>(workspace_count) * unit * static_cast<size_t>(std::max(batch, 1)) + 64;
+    if (need > own_workspace_bytes){
+        if (own_workspace){ cudaStreamSynchronize(cstream); cudaFree(own_workspace); own_workspace = nullptr; own_workspace_bytes = 0; }
+        if (cudaMalloc(&own_workspace, need) != cudaSuccess) return nullptr;
+        own_workspace_bytes = need;
+    }
+    return own_workspace;
+}
+
+int transform3d::forward(int precision, int batch, const void *in, void *out, void *workspace, int scaling){
+    if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
+    int rc = ensure_executors(precision);
+    if (rc) return rc;
+    if (workspace == nullptr){
+        workspace = ensure_workspace(precision, 1);
+        if (workspace == nullptr) return fail(B200_ERR_CUDA, "cannot allocate the workspace");
+    }
+    size_t const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
+    size_t const in_unit = (tkind == kind_c2c) ? 2 * real_bytes : real_bytes;
+    size_t const out_unit = (tkind == kind_c2c or tkind == kind_r2c) ? 2 * real_bytes : real_bytes;
+    for(int b=0; b<std::max(batch, 1); b++){
+        rc = run(precision, false, static_cast<const char*>(in) + b * inbox_count * in_unit,
+                 static_cast<char*>(out) + b * outbox_count * out_unit, workspace, scale_factor(scaling));
+        if (rc) return rc;
+    }
+    return B200_SUCCESS;
+}
+
+int transform3d::backward(int precision, int batch, const void *in, void *out, void *workspace, int scaling){
+    if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
+    int rc = ensure_executors(precision);
+    if (rc) return rc;
+    if (workspace == nullptr){
+        workspace = ensure_workspace(precision, 1);
+        if (workspace == nullptr) return fail(B200_ERR_CUDA, "cannot allocate the workspace");
+    }
+    size_t const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
+    size_t const in_unit = (tkind == kind_c2c or tkind == kind_r2c) ? 2 * real_bytes : real_bytes;
+    size_t const out_unit = (tkind == kind_c2c) ? 2 * real_bytes : real_bytes;
+    for(int b=0; b<std::max(batch, 1); b++){
+        rc = run(precision, true, static_cast<const char*>(in) + b * outbox_count * in_unit,
+                 static_cast<char*>(out) + b * inbox_count * out_unit, workspace, scale_factor(scaling));
+        if (rc) return rc;
+    }
+    return B200_SUCCESS;
+}
+
+int transform3d::run(int precision, bool is_backward, const void *in, void *out, void *workspace, double scale){
+    int const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
+    int const cplx_bytes = 2 * real_bytes;
+    std::unique_ptr<reshape_op> const *R = is_backward ? bwd : fwd;
+    int const E[3] = {is_backward ? 2 : 0, 1, is_backward ? 0 : 2};   // executor used after reshape s
+    int const direction = is_backward ? B200_BACKWARD : B200_FORWARD;
+    b200_fft1d_plan const *X = exec[precision];
+
+    int last_fft = -1;
+    for(int s=0; s<3; s++) if (X[E[s]]) last_fft = s;
+    auto stage_scale = [&](int s){ return (s == last_fft) ? scale : 1.0; };
+
+    // ---- complex-to-complex and real-to-real: one element type from end to end ---------------------------------
+    if (tkind != kind_r2c){
+        int const elem = (tkind == kind_c2c) ? cplx_bytes : real_bytes;
+        void *temp = advance(workspace, comm_count, elem);
+        int total_reshapes = 0, done_reshapes = 0;
+        for(int s=0; s<4; s++) if (R[s]) total_reshapes++;
+        const void *cur = in;
+        bool writable = (in == out);
+        for(int s=0; s<4; s++){
+            if (R[s]){
+                done_reshapes++;
+                void *dst = (done_reshapes == total_reshapes) ? out : temp;
+                int rc = R[s]->apply(elem, cur, dst, workspace, cstream);
+                if (rc) return rc;
+                cur = dst; writable = true;
+            }
+            if (s < 3 and X[E[s]]){
+                void *dst = writable ? const_cast<void*>(cur) : ((done_reshapes < total_reshapes) ? temp : out);
+                int rc = b200_fft1d_execute(X[E[s]], direction, cur, dst, stage_scale(s), cstream);
+                if (rc) return rc;
+                cur = dst; writable = true;
+            }
+        }
+        if (cur != out){
+            idx const count = is_backward ? inbox_count : outbox_count;
+            if (count > 0 and cudaMemcpyAsync(out, cur, static_cast<size_t>(count) * elem, cudaMemcpyDeviceToDevice, cstream) != cudaSuccess)
+                return fail(B200_ERR_CUDA, "cudaMemcpyAsync failed");
+        }
+        return B200_SUCCESS;
+    }
+
+    // ---- real-to-complex forward ----------------------------------------------------------------------------------
+    void *temp = advance(workspace, comm_count, cplx_bytes);
+    if (not is_backward){
+        const void *real_in = in;
+        if (R[0]){
+            void *staged = workspace;
+            void *scratch = advance(workspace, temp_count, cplx_bytes);
+            int rc = R[0]->apply(real_bytes, in, staged, scratch, cstream);
+            if (rc) return rc;
+            real_in = staged;
+        }
+        int remaining = 0;
+        for(int s=1; s<4; s++) if (R[s]) remaining++;
+        void *cur = (remaining > 0) ? temp : out;
+        if (X[0]){
+            int rc = b200_fft1d_execute(X[0], B200_FORWARD, real_in, cur, stage_scale(0), cstream);
+            if (rc) return rc;
+        }
+        for(int s=1; s<4; s++){
+            if (R[s]){
+                remaining--;
+                void *dst = (remaining == 0) ? out : temp;
+                int rc = R[s]->apply(cplx_bytes, cur, dst, workspace, cstream);
+                if (rc) return rc;
+                cur = dst;
+            }
+            if (s < 3 and X[E[s]]){
+                int rc = b200_fft1d_execute(X[E[s]], B200_FORWARD, cur, cur, stage_scale(s), cstream);
+                if (rc) return rc;
+            }
+        }
+        return B200_SUCCESS;
+    }
+
+    // ---- complex-to-real backward -------------------------------------------------------------------------------------
+    {
+        if (R[0]){
+            int rc = R[0]->apply(cplx_bytes, in, temp, workspace, cstream);
+            if (rc) return rc;
+        }else if (outbox_count > 0){
+            if (cudaMemcpyAsync(temp, in, static_cast<size_t>(outbox_count) * cplx_bytes, cudaMemcpyDeviceToDevice, cstream) != cudaSuccess)
+                return fail(B200_ERR_CUDA, "cudaMemcpyAsync failed");
+        }
+        for(int s=0; s<2; s++){
+            if (X[E[s]]){
+                int rc = b200_fft1d_execute(X[E[s]], B200_BACKWARD, temp, temp, stage_scale(s), cstream);
+                if (rc) return rc;
+            }
+            if (R[s+1]){
+                int rc = R[s+1]->apply(cplx_bytes, temp, temp, workspace, cstream);
+                if (rc) return rc;
+            }
+        }
+        if (R[3]){
+            void *real_buffer = workspace;
+            idx const real_count = lp.out_shape[0][me].count();
+            if (X[0]){
+                int rc = b200_fft1d_execute(X[0], B200_BACKWARD, temp, real_buffer, stage_scale(2), cstream);
+                if (rc) return rc;
+            }
+            void *scratch = advance(workspace, (real_count + 1) / 2, cplx_bytes);
+            return R[3]->apply(real_bytes, real_buffer, out, scratch, cstream);
+        }
+        if (X[0]) return b200_fft1d_execute(X[0], B200_BACKWARD, temp, out, stage_scale(2), cstream);
+        return B200_SUCCESS;
+    }
+}
+
+} // namespace b200

@@ -1,0 +1,97 @@
+// The distributed 3-D transform object behind heffte::fft3d<backend::b200> / fft3d_r2c<backend::b200>.
+// Replaces, for the b200 backend, the reference's fft3d::setup (include/heffte_fft3d.h:599-651), the reshape layer
+// (include/heffte_reshape3d.h, src/heffte_reshape3d.cpp:365-443) and the stage driver
+// (src/heffte_compute_transform.cpp:15-258).  Everything is enqueued on one CUDA stream; there is no host
+// synchronisation between stages (the reference blocks on cudaStreamSynchronize before every MPI call,
+// src/heffte_reshape3d.cpp:388).
+#pragma once
+
+#include <memory>
+#include <string>
+
+#include "../../include/heffte_b200_kernels.h"
+#include "comm.h"
+#include "plan_logic.h"
+
+namespace b200 {
+
+enum transform_kind : int { kind_c2c = B200_C2C, kind_r2c = B200_R2C, kind_cos = B200_COS, kind_sin = B200_SIN, kind_cos1 = B200_COS1 };
+
+struct piece {                 // one sub-box exchanged with one peer
+    int peer;
+    idx offset;                // position of the sub-box inside my box
+    idx size[3];               // fast, mid, slow extents (in the order of MY box)
+    idx line, plane;           // strides of my box
+    idx buff_line, buff_plane; // receive side: strides of the packed message (sender order)
+    int map[3];                // receive side: permutation (reference pack_plan_3d::map)
+    bool permuted;             // receive side: orders differ
+    idx count;
+    idx buffer_offset;         // position of the message inside the send / receive buffer
+};
+
+// in_shape -> out_shape redistribution for one rank
+class reshape_op {
+public:
+    reshape_op(shape const &in, shape const &out, int me, communicator *comm);
+    idx input_count() const { return in_count; }
+    idx output_count() const { return out_count; }
+    idx workspace_count() const { return in_count + out_count; }
+    bool is_local() const { return local_permute; }
+    size_t num_peers_out() const { return sends.size(); }
+    // src and dst may alias; workspace holds workspace_count() elements of elem_bytes
+    int apply(int elem_bytes, const void *src, void *dst, void *workspace, cudaStream_t stream) const;
+    std::vector<piece> const& send_list() const { return sends; }
+    std::vector<piece> const& recv_list() const { return recvs; }
+private:
+    communicator *comm;
+    int me;
+    idx in_count = 0, out_count = 0;
+    bool local_permute = false;
+    std::vector<piece> sends, recvs;
+};
+
+// builds a reshape if the two shapes differ (null = no-op), mirroring the decision table of
+// make_reshape3d (reference include/heffte_reshape3d.h:504-556)
+std::unique_ptr<reshape_op> make_reshape(shape const &in, shape const &out, int me, communicator *comm);
+
+class transform3d {
+public:
+    transform3d(transform_kind kind, box3 const &inbox, box3 const &outbox, int r2c_direction,
+                communicator *comm, plan_options const &options, cudaStream_t stream);
+    ~transform3d();
+
+    idx size_inbox() const { return inbox_count; }
+    idx size_outbox() const { return outbox_count; }
+    idx size_workspace() const { return workspace_count; }
+    double scale_factor(int scaling) const;
+    logic_plan const& plan() const { return lp; }
+    transform_kind kind() const { return tkind; }
+    int r2c_direction() const { return r2c_dir; }
+    cudaStream_t stream() const { return cstream; }
+    communicator* comm() const { return ccomm; }
+
+    // precision B200_PREC_*; workspace may be null (a plan-owned buffer is used); scaling 0 none / 1 full / 2 symmetric
+    int forward(int precision, int batch, const void *in, void *out, void *workspace, int scaling);
+    int backward(int precision, int batch, const void *in, void *out, void *workspace, int scaling);
+
+private:
+    int run(int precision, bool is_backward, const void *in, void *out, void *workspace, double scale);
+    int ensure_executors(int precision);
+    void* ensure_workspace(int precision, int batch);
+
+    transform_kind tkind;
+    int r2c_dir;
+    communicator *ccomm;
+    cudaStream_t cstream;
+    logic_plan lp;
+    int me;
+    idx inbox_count, outbox_count, workspace_count, comm_count, temp_count;
+    double base_scale;
+    std::unique_ptr<reshape_op> fwd[4], bwd[4];
+    b200_fft1d_plan exec[2][3];
+    bool exec_ready[2] = {false, false};
+    void *own_workspace = nullptr;
+    size_t own_workspace_bytes = 0;
+};
+
+} // namespace b200

@@ -1,0 +1,160 @@
+/*
+ * heffte_b200.h -- the drop-in C ABI of the B200 backend: the same entry points, argument meaning, return codes
+ * and struct layouts as the reference's C interface (icl-utk-edu/heffte v2.4.1, include/heffte_c.h:25-256 and
+ * include/heffte_c_defines.h:54-162, implemented in src/heffte_c.cpp:193-498), for the new backend id
+ * Heffte_BACKEND_B200.  This is what the reference's Python (python/heffte.py:42-100, ctypes) and Fortran bindings
+ * load; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * One deliberate difference: the image has no MPI, and the data path is NCCL over NVLink, so the communicator
+ * argument is a `heffte_comm` handle created by the functions at the top of this file instead of an MPI_Comm.
+ * With a real MPI the maintainer-side stub builds the handle from the MPI communicator.
+ *
+ * All `input`/`output`/`workspace` pointers are DEVICE pointers, exactly like the reference's cuFFT backend.
+ * The *_host variants at the end are the end-to-end convenience path (pinned-host staging + H2D/D2H inside).
+ */
+#ifndef HEFFTE_B200_H
+#define HEFFTE_B200_H
+
+#include "heffte_b200_kernels.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- constants: reference include/heffte_c_defines.h:54-162 ------------------------------------------------ */
+#define Heffte_BACKEND_STOCK   0
+#define Heffte_BACKEND_FFTW    1
+#define Heffte_BACKEND_MKL     2
+#define Heffte_BACKEND_CUFFT  10
+#define Heffte_BACKEND_ROCFFT 11
+#define Heffte_BACKEND_B200   12   /* new: c2c and r2c */
+#define Heffte_BACKEND_B200_COS   13   /* new: DCT-II/III  (reference template tag cufft_cos)  */
+#define Heffte_BACKEND_B200_SIN   14   /* new: DST-II/III  (reference template tag cufft_sin)  */
+#define Heffte_BACKEND_B200_COS1  15   /* new: DCT-I       (reference template tag cufft_cos1) */
+
+#define Heffte_SUCCESS 0
+
+#define Heffte_RESHAPE_ALGORITHM_ALLTOALLV  0
+#define Heffte_RESHAPE_ALGORITHM_P2P_PLINED 1
+#define Heffte_RESHAPE_ALGORITHM_P2P        2
+#define Heffte_RESHAPE_ALGORITHM_ALLTOALL   3
+
+#define Heffte_SCALE_NONE      0
+#define Heffte_SCALE_FULL      1
+#define Heffte_SCALE_SYMMETRIC 2
+
+/* reference include/heffte_c_defines.h:113-125 */
+typedef struct{
+    int use_reorder;
+    int algorithm;
+    int use_pencils;
+    int use_gpu_aware;
+} heffte_plan_options;
+
+/* reference include/heffte_c_defines.h:133-146 */
+typedef struct{
+    int backend_type;
+    int using_r2c;
+    void *fft;
+} heffte_fft_plan;
+typedef heffte_fft_plan* heffte_plan;
+
+/* ---- communicator handle (stands where the reference takes an MPI_Comm) -------------------------------------- */
+typedef struct heffte_comm_s* heffte_comm;
+
+/* single rank, no communication library */
+int heffte_comm_create_self(heffte_comm *comm);
+/* one rank per GPU over NCCL: rank 0 obtains an id, the caller ships the 128 bytes to every rank (torch.distributed,
+ * MPI_Bcast, a file ...), then every rank creates its communicator on its current CUDA device */
+int heffte_comm_nccl_unique_id(void *id128);
+int heffte_comm_create_nccl(int rank, int size, const void *id128, heffte_comm *comm);
+/* caller-provided transport: host allgather for planning and a device exchange callback (see csrc/comm.h) */
+typedef int (*heffte_allgather_fn)(void *context, const void *mine, void *all, size_t bytes);
+typedef int (*heffte_exchange_fn)(void *context, int nsend, const int *send_peer, void *const *send_ptr, const size_t *send_bytes,
+                                  int nrecv, const int *recv_peer, void *const *recv_ptr, const size_t *recv_bytes, void *stream);
+int heffte_comm_create_callbacks(int rank, int size, heffte_allgather_fn gather, heffte_exchange_fn exchange, void *context, heffte_comm *comm);
+int heffte_comm_rank(heffte_comm comm);
+int heffte_comm_size(heffte_comm comm);
+int heffte_comm_destroy(heffte_comm comm);
+
+/* ---- the reference C API (include/heffte_c.h) ----------------------------------------------------------------------- */
+/* heffte_c.h:33  */ int heffte_set_default_options(int backend, heffte_plan_options *options);
+/* heffte_c.h:67  */ int heffte_plan_create(int backend, int const inbox_low[3], int const inbox_high[3], int const *inbox_order,
+                                            int const outbox_low[3], int const outbox_high[3], int const *outbox_order,
+                                            heffte_comm const comm, heffte_plan_options const *options, heffte_plan *plan);
+/* heffte_c.h:77  */ int heffte_plan_create_r2c(int backend, int const inbox_low[3], int const inbox_high[3], int const *inbox_order,
+                                                int const outbox_low[3], int const outbox_high[3], int const *outbox_order,
+                                                int r2c_direction, heffte_comm const comm, heffte_plan_options const *options, heffte_plan *plan);
+/* same, on a caller-owned CUDA stream (C++ API: fft3d(stream, inbox, outbox, comm, options), include/heffte_fft3d.h:292-297) */
+int heffte_plan_create_stream(int backend, void *cuda_stream, int const inbox_low[3], int const inbox_high[3], int const *inbox_order,
+                              int const outbox_low[3], int const outbox_high[3], int const *outbox_order,
+                              int r2c_direction /* -1 unless r2c */, heffte_comm const comm, heffte_plan_options const *options, heffte_plan *plan);
+/* heffte_c.h:87  */ int heffte_plan_destroy(heffte_plan plan);
+/* heffte_c.h:93  */ int heffte_size_inbox(heffte_plan const plan);
+/* heffte_c.h:98  */ int heffte_size_outbox(heffte_plan const plan);
+/* heffte_c.h:103 */ int heffte_size_workspace(heffte_plan const plan);
+/* heffte_c.h:108 */ int heffte_get_backend(heffte_plan const plan);
+/* heffte_c.h:113 */ int heffte_is_r2c(heffte_plan const plan);
+/* 64-bit variants (the reference C API returns int) */
+long long heffte_size_inbox64(heffte_plan const plan);
+long long heffte_size_outbox64(heffte_plan const plan);
+long long heffte_size_workspace64(heffte_plan const plan);
+double heffte_get_scale_factor(heffte_plan const plan, int scale);
+
+/* heffte_c.h:136-175 forward transforms, device pointers */
+void heffte_forward_s2c(heffte_plan const plan, float const *input, void *output, int scale);
+void heffte_forward_c2c(heffte_plan const plan, void const *input, void *output, int scale);
+void heffte_forward_d2z(heffte_plan const plan, double const *input, void *output, int scale);
+void heffte_forward_z2z(heffte_plan const plan, void const *input, void *output, int scale);
+void heffte_forward_s2c_buffered(heffte_plan const plan, float const *input, void *output, void *workspace, int scale);
+void heffte_forward_c2c_buffered(heffte_plan const plan, void const *input, void *output, void *workspace, int scale);
+void heffte_forward_d2z_buffered(heffte_plan const plan, double const *input, void *output, void *workspace, int scale);
+void heffte_forward_z2z_buffered(heffte_plan const plan, void const *input, void *output, void *workspace, int scale);
+/* heffte_c.h:198-256 backward transforms */
+void heffte_backward_c2s(heffte_plan const plan, void const *input, float *output, int scale);
+void heffte_backward_c2c(heffte_plan const plan, void const *input, void *output, int scale);
+void heffte_backward_z2d(heffte_plan const plan, void const *input, double *output, int scale);
+void heffte_backward_z2z(heffte_plan const plan, void const *input, void *output, int scale);
+void heffte_backward_c2s_buffered(heffte_plan const plan, void const *input, float *output, void *workspace, int scale);
+void heffte_backward_c2c_buffered(heffte_plan const plan, void const *input, void *output, void *workspace, int scale);
+void heffte_backward_z2d_buffered(heffte_plan const plan, void const *input, double *output, void *workspace, int scale);
+void heffte_backward_z2z_buffered(heffte_plan const plan, void const *input, void *output, void *workspace, int scale);
+
+/* real-to-real (the reference C API has no r2r entry points; these follow its naming): s = float, d = double */
+void heffte_forward_s2s_buffered(heffte_plan const plan, float const *input, float *output, float *workspace, int scale);
+void heffte_forward_d2d_buffered(heffte_plan const plan, double const *input, double *output, double *workspace, int scale);
+void heffte_backward_s2s_buffered(heffte_plan const plan, float const *input, float *output, float *workspace, int scale);
+void heffte_backward_d2d_buffered(heffte_plan const plan, double const *input, double *output, double *workspace, int scale);
+
+/* generic entry used by the C++ header and the Python binding: precision B200_PREC_*, direction B200_FORWARD/BACKWARD,
+ * batch >= 1 (C++ API forward(batch, ...), include/heffte_fft3d.h:391-414); returns an error code instead of void */
+int heffte_execute(heffte_plan const plan, int precision, int direction, int batch, void const *input, void *output, void *workspace, int scale);
+/* same through pinned host staging: copies input host->device, transforms, copies the result device->host, synchronises */
+int heffte_execute_host(heffte_plan const plan, int precision, int direction, int batch, void const *host_input, void *host_output, int scale);
+/* error text of the last failing call on this thread */
+const char* heffte_last_error(void);
+
+/* ---- plan introspection (pure host logic, usable without a GPU; used by the parity tests) ------------------------- */
+/* boxes are 9 ints: low[3], high[3], order[3].  shapes_out receives 8*nranks boxes: in_shape[0..3] then out_shape[0..3]
+ * (reference logic_plan3d, include/heffte_plan_logic.h:275-291; plan_operations, src/heffte_plan_logic.cpp:424-453) */
+int heffte_b200_logic_plan(int nranks, int const *inboxes, int const *outboxes, int r2c_direction,
+                           int use_reorder, int algorithm, int use_pencils, int subranks, int rank,
+                           int *shapes_out, int *fft_direction, long long *index_count);
+/* reference include/heffte_geometry.h:337-349, 643-691, 409-436 */
+void heffte_b200_make_procgrid(int nprocs, int *grid2);
+void heffte_b200_proc_setup_min_surface(int const *world_box, int nprocs, int *grid3);
+void heffte_b200_split_world(int const *world_box, int const *grid3, int *boxes_out);
+/* send (receive = 0) or receive (receive = 1) list of rank `me` for the reshape in -> out; pieces_out receives per entry
+ * 14 long long: peer, offset, size[3], line, plane, buff_line, buff_plane, map[3], count, buffer_offset; returns the number
+ * of entries or a negative error (reference src/heffte_reshape3d.cpp:125-206) */
+int heffte_b200_reshape_pieces(int nranks, int const *inboxes, int const *outboxes, int me, int receive, long long *pieces_out, int max_pieces);
+/* workspace / box sizes of a plan without creating device state (uses the same code path as the real plan) */
+int heffte_b200_plan_sizes(int kind, int nranks, int const *inboxes, int const *outboxes, int r2c_direction,
+                           int use_reorder, int algorithm, int use_pencils, int subranks, int rank,
+                           long long *size_inbox, long long *size_outbox, long long *size_workspace);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
