@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""
+bench.py -- the measurement harness: heFFTe's speed3d metric for the b200 backend.
+
+Metric (reference benchmarks/speed3d.h:168-195, 224-230): one *step* = forward(scale::full) + backward on the same
+buffers; t = time / (2 * steps); GFlop/s = 5 * N * log2(N) * 1e-9 / t with N = nx*ny*nz, whole job (all ranks).
+Default workload: speed3d_c2c double 512^3 in place, bricks on the proc_setup_min_surface grid (1 GPU: the whole box).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # b200 arm (N > 1: launched by torchrun)
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the reference's own CPU path (oracle/_ref)
+
+Prints ONE JSON line on rank 0.  `value` = device-resident throughput, `e2e` = same metric through the host-buffer
+entry point (heffte_execute_host: H2D + transform + D2H per call), `roofline` = dominant FFT kernel against the
+measured HBM peak, `cpu_baseline` = the unmodified reference (stock backend, threads-as-ranks MPI stand-in) timed on
+this box's host cores.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, nargs=3, default=[512, 512, 512])
+    ap.add_argument("--precision", default="double", choices=["float", "double"])
+    ap.add_argument("--kind", default="c2c", choices=["c2c", "r2c"])
+    ap.add_argument("--reorder", action="store_true")
+    ap.add_argument("--slabs", action="store_true")
+    ap.add_argument("--io-pencils", action="store_true", help="pencil-shaped in/out boxes (speed3d -io_pencils)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-size", type=int, nargs=3, default=None, help="size of the CPU sample (default: the workload itself)")
+    return ap.parse_args()
+
+
+def gflops(n, seconds_per_transform):
+    N = float(n[0]) * n[1] * n[2]
+    return 5.0 * N * math.log2(N) * 1e-9 / seconds_per_transform
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return json.load(f), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+            except ValueError:
+                continue
+            for name, flag in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[4:8]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the reference arm / cpu baseline: oracle/_ref speed3d binaries (the unmodified reference, stock backend)
+# ----------------------------------------------------------------------------------------------------------------
+def usable_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_speed3d(kind, precision, size, nruns, options=()):
+    """Runs the reference's own speed3d_<kind> (stock backend) on thread-ranks; returns dict or None."""
+    from oracle import ref_lib
+    binary = ref_lib.binary("speed3d_" + kind)
+    if binary is None or not os.path.exists(binary):
+        return None
+    cores = usable_cores()
+    ranks = 1
+    while ranks * 2 <= min(cores, 64):
+        ranks *= 2
+    env = dict(os.environ, SHIM_NP=str(ranks))
+    cmd = [binary, "stock", precision, str(size[0]), str(size[1]), str(size[2]), "-n%d" % nruns] + list(options)
+    t0 = time.time()
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=3000)
+    wall = time.time() - t0
+    m = re.search(r"Performance:\s+([0-9.eE+-]+)\s+GFlops/s", out.stdout)
+    t = re.search(r"Time per run:\s+([0-9.eE+-]+)", out.stdout)
+    if out.returncode != 0 or m is None:
+        return {"error": (out.stdout + out.stderr)[-400:]}
+    return {"gflops": float(m.group(1)), "seconds_per_transform": float(t.group(1)) if t else None, "ranks": ranks,
+            "cores": cores, "wall_s": wall, "isa": os.path.basename(os.path.dirname(binary)),
+            "sample": "speed3d_%s stock %s %dx%dx%d -n%d on %d thread-ranks (reference compiled in place, %s)" % (
+                kind, precision, size[0], size[1], size[2], nruns, ranks, os.path.basename(os.path.dirname(binary)))}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    size = args.cpu_size or args.size
+    # each "step" is one bounded sample: the reference benchmark's own timed loop of one forward+backward pair
+    nruns = 1
+    results = []
+    for _ in range(max(1, min(args.steps, 2))):
+        r = run_reference_speed3d(args.kind, args.precision, size, nruns)
+        if r is None or "error" in r:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref speed3d binary missing or failed: %s" % (r or {}).get("error", "not built")}))
+            return
+        results.append(r)
+    best = max(results, key=lambda r: r["gflops"])
+    line = {
+        "impl": "reference", "metric": "speed3d_%s GFlop/s (5*N*log2(N)/t)" % args.kind, "value": best["gflops"], "unit": "GFlop/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 2e3 * best["seconds_per_transform"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if args.precision == "double" else "f32",
+        "data": "synthetic",
+        "config": {"workload": "speed3d_%s %s %dx%dx%d" % (args.kind, args.precision, size[0], size[1], size[2]),
+                   "backend": "stock (FFTW and MPI are absent from the image)", "ranks": best["ranks"]},
+        "cpu_baseline": {"value": best["gflops"], "unit": "GFlop/s", "cores": best["ranks"], "kind": "reference", "sample": best["sample"]},
+        "e2e": {"value": best["gflops"], "unit": "GFlop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the b200 arm
+# ----------------------------------------------------------------------------------------------------------------
+def b200_arm(args):
+    import numpy as np
+    import torch
+    import heffte_b200 as hf
+    from heffte_b200 import _lib, build
+    build.build_library()
+    lib = _lib.load()
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    distributed = world_size > 1
+    if distributed:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = hf.comm_from_torch()
+    else:
+        dist = None
+        comm = hf.comm_self()
+
+    n = tuple(args.size)
+    prec = 0 if args.precision == "float" else 1
+    rdtype = torch.float32 if prec == 0 else torch.float64
+    cdtype = torch.complex64 if prec == 0 else torch.complex128
+    world = hf.box3d((0, 0, 0), (n[0] - 1, n[1] - 1, n[2] - 1))
+
+    if args.io_pencils:
+        g2 = hf.heffte.make_procgrid(world_size)
+        in_grid, out_grid = [1, g2[0], g2[1]], [g2[0], g2[1], 1]
+    else:
+        in_grid = out_grid = hf.heffte.proc_setup_min_surface(world, world_size)
+    r2c = args.kind == "r2c"
+    inbox = hf.heffte.split_world(world, in_grid)[rank]
+    if r2c:
+        cworld = hf.box3d((0, 0, 0), (n[0] // 2, n[1] - 1, n[2] - 1))
+        outbox = hf.heffte.split_world(cworld, out_grid)[rank]
+    else:
+        outbox = hf.heffte.split_world(world, out_grid)[rank]
+
+    options = hf.plan_options(hf.backend.b200, use_reorder=args.reorder, use_pencils=not args.slabs)
+    fft = hf.fft3d_r2c(hf.backend.b200, inbox, outbox, 0, comm, options) if r2c else hf.fft3d(hf.backend.b200, inbox, outbox, comm, options)
+
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(4242 + rank)
+    nin, nout = fft.size_inbox(), fft.size_outbox()
+    if r2c:
+        data_in = torch.rand(nin, dtype=rdtype, device="cuda", generator=gen)
+        data_out = torch.empty(nout, dtype=cdtype, device="cuda")
+    else:
+        # speed3d: complex data with zero imaginary part, transformed in place
+        data_in = torch.complex(torch.rand(max(nin, nout), dtype=rdtype, device="cuda", generator=gen),
+                                torch.zeros(max(nin, nout), dtype=rdtype, device="cuda"))
+        data_out = data_in
+    reference_copy = data_in.clone()
+    work = torch.empty(fft.size_workspace(), dtype=cdtype, device="cuda")
+
+    def step():
+        fft.forward_buffered(data_in, data_out, work, hf.scale.full)
+        fft.backward_buffered(data_out, data_in, work, hf.scale.none)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # accuracy of the round trip (benchmarks/speed3d.h:213-220)
+    err = float((data_in - reference_copy).abs().max().item())
+    data_in.copy_(reference_copy)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.b200_launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        step()
+    stop.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = lib.b200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if distributed:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        e = torch.tensor([err], dtype=torch.float64, device="cuda")
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        err = float(e.item())
+    ms_per_step = elapsed_ms / args.steps
+    sec_per_transform = ms_per_step * 1e-3 / 2.0
+    value = gflops(n, sec_per_transform)
+
+    # ---- end to end: host buffers in, host buffers out, through the public plan API ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        real_bytes = 4 if prec == 0 else 8
+        host_in = torch.empty(nin if r2c else max(nin, nout), dtype=rdtype if r2c else cdtype).pin_memory()
+        host_mid = torch.empty(nout if r2c else max(nin, nout), dtype=cdtype).pin_memory()
+        host_in.copy_(reference_copy.cpu())
+        np_in, np_mid = host_in.numpy(), host_mid.numpy()
+        np_back = torch.empty_like(host_in).pin_memory().numpy()
+        e2e_steps = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            fft.forward(np_in, np_mid, hf.scale.full)      # H2D(in) + forward + D2H(out)
+            fft.backward(np_mid, np_back, hf.scale.none)   # H2D(out) + backward + D2H(in)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        if distributed:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        in_bytes = host_in.numel() * host_in.element_size()
+        mid_bytes = host_mid.numel() * host_mid.element_size()
+        e2e = {"value": gflops(n, e2e_s / 2.0), "unit": "GFlop/s", "h2d_bytes_per_step": in_bytes + mid_bytes,
+               "d2h_bytes_per_step": in_bytes + mid_bytes, "steps": e2e_steps,
+               "note": "per rank bytes; step = forward(host in -> host out) + backward(host out -> host in), pinned buffers"}
+
+    # ---- roofline of the dominant kernel: the batched 1-D FFT pass, timed alone with CUDA events -----------------------
+    roofline, stages = None, []
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        from heffte_b200._lib import b200_fft1d_desc, b200_line_geom
+        # the local box of the first FFT stage on this rank; on one GPU this is the whole world
+        stage_box = [int(v) for v in inbox.size]
+        if world_size > 1:
+            stage_box = None  # stage boxes differ per stage; report per-stage numbers only on one GPU
+        if stage_box is not None and not r2c:
+            n0, n1, n2 = stage_box
+            elems = n0 * n1 * n2
+            csize = 8 if prec == 0 else 16
+            geoms = [((1, n0, 0), n1 * n2, 1, n0), ((n0, 1, n0 * n1), n0, n2, n1), ((n0 * n1, 1, 0), n0 * n1, 1, n2)]
+            for dim, (g, ca, cb, length) in enumerate(geoms):
+                d = b200_fft1d_desc(prec, 0, length, ca, cb, b200_line_geom(*g), b200_line_geom(*g))
+                plan = ctypes.c_void_p()
+                if lib.b200_fft1d_create(ctypes.byref(d), ctypes.byref(plan)) != 0:
+                    continue
+                ptr = ctypes.c_void_p(data_in.data_ptr())
+                for _ in range(3):
+                    lib.b200_fft1d_execute(plan, 0, ptr, ptr, ctypes.c_double(1.0), None)
+                torch.cuda.synchronize()
+                reps = 10
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    lib.b200_fft1d_execute(plan, 0, ptr, ptr, ctypes.c_double(1.0), None)
+                b.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / reps
+                name = lib.b200_fft1d_kernel_name(plan).decode()
+                lib.b200_fft1d_destroy(plan)
+                algo_bytes = 2.0 * elems * csize    # one read + one write of the local box per pass
+                stages.append({"dim": dim, "kernel": name, "n": length, "ms": ms, "GB/s": algo_bytes / ms * 1e-6,
+                               "frac_of_%s_hbm" % peak_kind: algo_bytes / ms * 1e-6 / peaks["hbm_gbs"]})
+            if stages:
+                dominant = max(stages, key=lambda s: s["ms"])
+                total_ms = sum(s["ms"] for s in stages)
+                roofline = {"bound": "hbm", "achieved": dominant["GB/s"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": dominant["GB/s"] / peaks["hbm_gbs"], "traffic": None,
+                            "kernel": "fft_%s_kernel (dim %d)" % (dominant["kernel"], dominant["dim"]),
+                            "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650 GB/s",
+                            "algorithmic_bytes_per_launch": 2.0 * elems * csize,
+                            "whole_transform": {"algorithmic_GB": 3 * 2.0 * elems * csize * 1e-9, "sum_of_passes_ms": total_ms,
+                                                "measured_ms": sec_per_transform * 1e3,
+                                                "frac_of_hbm_roofline": (3 * 2.0 * elems * csize / (peaks["hbm_gbs"] * 1e9)) / sec_per_transform}}
+
+    # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample ------------------------------
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        size = args.cpu_size or args.size
+        r = run_reference_speed3d(args.kind, args.precision, size, 1)
+        if r is not None and "error" not in r:
+            cpu = {"value": r["gflops"], "unit": "GFlop/s", "cores": r["ranks"], "kind": "reference", "sample": r["sample"],
+                   "host_cores_available": r["cores"]}
+        else:
+            cpu = {"value": None, "unit": "GFlop/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ((r or {}).get("error", "oracle/_ref not built"))}
+
+    if rank == 0:
+        grid = "x".join(str(v) for v in in_grid)
+        line = {
+            "metric": "speed3d_%s GFlop/s (5*N*log2(N)/t)" % args.kind, "value": value, "unit": "GFlop/s", "n_gpus": world_size,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64" if prec == 1 else "f32", "data": "synthetic",
+            "config": {"workload": "speed3d_%s %s %dx%dx%d, bricks %s, %s, %s, in-place, step = forward(scale full)+backward" % (
+                           args.kind, args.precision, n[0], n[1], n[2], grid, "reorder" if args.reorder else "no-reorder",
+                           "slabs" if args.slabs else "pencils"),
+                       "l2": "working set %.0f MB per GPU exceeds the 126 MB L2" % (max(nin, nout) * (8 if prec == 0 else 16) / 1e6),
+                       "comm": "nccl send/recv" if distributed else "none"},
+            "max_roundtrip_error": err,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "e2e": e2e,
+            "roofline": roofline,
+            "stages": stages,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()
