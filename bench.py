@@ -67,51 +67,67 @@ def measured_peaks():
 # clocks sampling during the timed region
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clocks and throttle reasons through NVML (same counters as the nvidia-smi clocks line) every 5 ms."""
 
     def __init__(self, device_index):
         self.device_index = device_index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.running = False
+        self.thread = None
+        self.error = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = self.device_index
+            if visible:
+                try:
+                    index = int(visible.split(",")[self.device_index])
+                except Exception:
+                    pass
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.running = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:
+            self.error = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _loop(self):
+        n = self.nvml
+        masks = {}
+        for name, attr in [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")]:
+            alt = attr.replace("ClocksEventReason", "ClocksThrottleReason")
+            masks[name] = getattr(n, attr, getattr(n, alt, 0))
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+        while self.running:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    bits = get_reasons(self.handle)
+                    for name, mask in masks.items():
+                        if mask and (bits & mask):
+                            self.reasons.add(name)
+            except Exception as e:
+                self.error = repr(e)
+                break
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                smax = float(parts[2])
-            except ValueError:
-                continue
-            for name, flag in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[4:8]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        self.running = False
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        sm = sorted(self.samples)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm)}
+        if self.error:
+            out["error"] = self.error
+        return out
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -352,8 +368,14 @@ def b200_arm(args):
             if stages:
                 dominant = max(stages, key=lambda s: s["ms"])
                 total_ms = sum(s["ms"] for s in stages)
+                traffic = None
+                try:
+                    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                        traffic = json.load(f).get("fft_%s_kernel/%d/%s" % (dominant["kernel"], dominant["n"], "f64" if prec == 1 else "f32"))
+                except Exception:
+                    pass
                 roofline = {"bound": "hbm", "achieved": dominant["GB/s"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                            "frac": dominant["GB/s"] / peaks["hbm_gbs"], "traffic": None,
+                            "frac": dominant["GB/s"] / peaks["hbm_gbs"], "traffic": traffic,
                             "kernel": "fft_%s_kernel (dim %d)" % (dominant["kernel"], dominant["dim"]),
                             "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650 GB/s",
                             "algorithmic_bytes_per_launch": 2.0 * elems * csize,

@@ -150,6 +150,19 @@ __device__ __forceinline__ long long line_offset(line_geom const &g, int count_a
 
 template<typename T> __device__ __forceinline__ cplx<T> ldg_c(const cplx<T> *p){ return __ldg(p); }
 
+// asynchronous global -> shared copy of one complex element (LDGSTS): no register staging, the whole tile is in flight
+#ifndef B200_HOST_EMULATION
+template<int BYTES> __device__ __forceinline__ void async_copy(void *smem_dst, const void *gsrc){
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(gsrc));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void async_wait_all(){ asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+#else
+template<int BYTES> inline void async_copy(void *smem_dst, const void *gsrc){ std::memcpy(smem_dst, gsrc, BYTES); }
+inline void async_wait_all(){}
+#endif
+
 __host__ __device__ constexpr int cmax(int a, int b){ return a > b ? a : b; }
 __host__ __device__ constexpr int ilog2(int n){ return n <= 1 ? 0 : 1 + ilog2(n / 2); }
 
@@ -176,185 +189,217 @@ __device__ __forceinline__ void apply_twiddles(cplx<T> (&v)[R], const cplx<T> *t
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// strided kernel: tile of LPB adjacent lines, in-place DIF in shared memory laid out [position][line]
+// radix schedules
 // ---------------------------------------------------------------------------------------------------------
 template<int R0, int R1, int R2, int R3> struct radix_list {
     static constexpr int N = R0 * R1 * R2 * R3;
     static constexpr int passes = (R1 == 1) ? 1 : ((R2 == 1) ? 2 : ((R3 == 1) ? 3 : 4));
     static constexpr int rmax = cmax(cmax(R0, R1), cmax(R2, R3));
+    // only ever called with compile-time arguments
     __host__ __device__ static constexpr int radix(int s){ return s == 0 ? R0 : (s == 1 ? R1 : (s == 2 ? R2 : R3)); }
-    // stride of pass s: N / (R0 * ... * Rs)
-    __host__ __device__ static constexpr int stride(int s){ return s == 0 ? N / R0 : stride(s - 1) / radix(s); }
+    // distance between the legs of a butterfly of pass s: N / (R0 * ... * Rs)
+    __host__ __device__ static constexpr int stride(int s){ return s == 0 ? N / R0 : (s == 1 ? N / (R0 * R1) : (s == 2 ? N / (R0 * R1 * R2) : 1)); }
 };
 
-// natural index k of the value that ends at in-place position p after all DIF passes
+// natural index k of the value that ends at in-place position p after all DIF passes (all powers of two: shifts/masks)
 template<typename RL>
-__device__ __forceinline__ int dif_output_index(int p){
-    int k = 0, mult = 1;
-    #pragma unroll
-    for(int s=0; s<RL::passes; s++){
-        int d = (p / RL::stride(s)) % RL::radix(s);
-        k += d * mult;
-        mult *= RL::radix(s);
-    }
+__device__ __forceinline__ unsigned dif_output_index(unsigned p){
+    constexpr unsigned r0 = RL::radix(0), s0 = RL::stride(0);
+    unsigned k = p / s0;
+    if constexpr (RL::passes > 1){ constexpr unsigned r1 = RL::radix(1), s1 = RL::stride(1); k += ((p / s1) % r1) * r0; }
+    if constexpr (RL::passes > 2){ constexpr unsigned r2 = RL::radix(2), s2 = RL::stride(2); k += ((p / s2) % r2) * (r0 * RL::radix(1)); }
+    if constexpr (RL::passes > 3){ constexpr unsigned r3 = RL::radix(3); k += (p % r3) * (r0 * RL::radix(1) * RL::radix(2)); }
     return k;
 }
 
-template<typename T, typename RL, int S, int TPL, int LPB, bool FIRST, bool LAST>
-__device__ __forceinline__ void strided_pass(cplx<T> *sm, int t, int j, bool valid,
-                                             const cplx<T> *gin, cplx<T> *gout, long long istride, long long ostride,
-                                             const cplx<T> *tw, bool backward, T scale, bool do_scale){
-    constexpr int R = RL::radix(S);
-    constexpr int ST = RL::stride(S);          // distance between butterfly legs
-    constexpr int NB = RL::N / R;              // butterflies per line
+__device__ __forceinline__ long long tile_line_offset(line_geom const &g, int count_a, unsigned line){
+    unsigned b = line / static_cast<unsigned>(count_a);
+    unsigned a = line - b * static_cast<unsigned>(count_a);
+    return static_cast<long long>(a) * g.stride_a + static_cast<long long>(b) * g.stride_b;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// strided kernel: a CTA owns a tile of LPB adjacent lines, shared memory is laid out [position][line]; the tile is
+// brought in with asynchronous copies (LDGSTS, all of it in flight at once, no registers held across the load), the
+// passes are in-place decimation-in-frequency, and the digit reversal is absorbed into the row index of the store.
+// ---------------------------------------------------------------------------------------------------------
+template<typename T, typename RL, int S, int TPL, int LPB, bool BWD>
+__device__ __forceinline__ void strided_pass(cplx<T> *sm, unsigned t, unsigned j, bool valid, cplx<T> *gout, long long ostride,
+                                             const cplx<T> *tw, T scale, bool do_scale){
+    constexpr unsigned R = RL::radix(S);
+    constexpr unsigned ST = RL::stride(S);         // distance between butterfly legs
+    constexpr unsigned NB = RL::N / R;             // butterflies per line
+    constexpr bool FIRST = (S == 0), LAST = (S == RL::passes - 1);
     #pragma unroll
-    for(int u=0; u<NB/TPL; u++){
-        int q = j + u * TPL;
-        int blk = q / ST, o = q % ST;
-        int p0 = blk * ST * R + o;
+    for(unsigned u=0; u<NB/TPL; u++){
+        const unsigned q = j + u * TPL;
+        const unsigned o = q % ST;
+        const unsigned p0 = (q / ST) * (ST * R) + o;
+        cplx<T> *cell = sm + p0 * LPB + t;
         cplx<T> v[R];
-        if (FIRST){
-            if (valid){
-                #pragma unroll
-                for(int r=0; r<R; r++){
-                    cplx<T> x = gin[(long long)(p0 + r * ST) * istride];
-                    v[r] = backward ? cswap(x) : x;
-                }
-            }else{
-                #pragma unroll
-                for(int r=0; r<R; r++) v[r] = mk<T>(0, 0);
-            }
-        }else{
-            #pragma unroll
-            for(int r=0; r<R; r++) v[r] = sm[(p0 + r * ST) * LPB + t];
+        #pragma unroll
+        for(unsigned r=0; r<R; r++){
+            cplx<T> x = cell[r * ST * LPB];
+            v[r] = (FIRST && BWD) ? cswap(x) : x;
         }
         butterfly<T, R>::run(v);
-        if (!LAST){
+        if constexpr (!LAST){
             // DIF twiddle after the butterfly: W_{ST*R}^(o*r) = W_N^(o*r*N/(ST*R))
-            apply_twiddles<T, R, false>(v, tw, o * (RL::N / (ST * R)));
+            apply_twiddles<T, R, true>(v, tw, o * (RL::N / (ST * R)));
             #pragma unroll
-            for(int r=0; r<R; r++) sm[(p0 + r * ST) * LPB + t] = v[r];
-        }else if (valid){
-            #pragma unroll
-            for(int r=0; r<R; r++){
-                int k = dif_output_index<RL>(p0 + r * ST);
-                cplx<T> x = backward ? cswap(v[r]) : v[r];
-                if (do_scale){ x.x *= scale; x.y *= scale; }
-                gout[(long long)k * ostride] = x;
+            for(unsigned r=0; r<R; r++) cell[r * ST * LPB] = v[r];
+        }else{
+            if (valid){
+                // last pass: ST == 1, p = q*R + r, so the natural index is k(q*R) + r * N/R
+                cplx<T> *dst = gout + static_cast<long long>(dif_output_index<RL>(p0)) * ostride;
+                const long long hop = static_cast<long long>(RL::N / R) * ostride;
+                #pragma unroll
+                for(unsigned r=0; r<R; r++){
+                    cplx<T> x = BWD ? cswap(v[r]) : v[r];
+                    if (do_scale){ x.x *= scale; x.y *= scale; }
+                    *dst = x;
+                    dst += hop;
+                }
             }
         }
     }
 }
 
-template<typename T, typename RL, int TPL, int LPB, int MINB>
+template<typename T, typename RL, int TPL, int LPB, int MINB, bool BWD>
 __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a){
     B200_DYN_SMEM(smem_raw);
     cplx<T> *sm = reinterpret_cast<cplx<T>*>(smem_raw);
-    const int t = threadIdx.x % LPB, j = threadIdx.x / LPB;
-    const long long line = (long long)blockIdx.x * LPB + t;
+    const unsigned t = threadIdx.x % LPB, j = threadIdx.x / LPB;
+    const unsigned line = blockIdx.x * LPB + t;
     const bool valid = line < a.nlines;
-    const cplx<T> *gin = reinterpret_cast<const cplx<T>*>(a.in) + (valid ? line_offset(a.ig, a.count_a, line) : 0);
-    cplx<T> *gout = reinterpret_cast<cplx<T>*>(a.out) + (valid ? line_offset(a.og, a.count_a, line) : 0);
     const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
-    const bool bwd = a.backward != 0;
     const T scale = static_cast<T>(a.scale);
     const bool do_scale = a.scale != 1.0;
     constexpr int P = RL::passes;
 
-    strided_pass<T, RL, 0, TPL, LPB, true, P == 1>(sm, t, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+    if (valid){
+        const cplx<T> *src = reinterpret_cast<const cplx<T>*>(a.in) + tile_line_offset(a.ig, a.count_a, line) + static_cast<long long>(j) * a.ig.stride;
+        const long long hop = static_cast<long long>(TPL) * a.ig.stride;
+        cplx<T> *dst = sm + j * LPB + t;
+        #pragma unroll 4
+        for(unsigned row = j; row < RL::N; row += TPL){
+            async_copy<sizeof(cplx<T>)>(dst, src);
+            src += hop;
+            dst += TPL * LPB;
+        }
+    }
+    cplx<T> *gout = reinterpret_cast<cplx<T>*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, line) : 0);
+    async_wait_all();
+    __syncthreads();
+
+    strided_pass<T, RL, 0, TPL, LPB, BWD>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale);
     if constexpr (P > 1){
         __syncthreads();
-        strided_pass<T, RL, 1, TPL, LPB, false, P == 2>(sm, t, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+        strided_pass<T, RL, 1, TPL, LPB, BWD>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale);
     }
     if constexpr (P > 2){
         __syncthreads();
-        strided_pass<T, RL, 2, TPL, LPB, false, P == 3>(sm, t, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+        strided_pass<T, RL, 2, TPL, LPB, BWD>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale);
     }
     if constexpr (P > 3){
         __syncthreads();
-        strided_pass<T, RL, 3, TPL, LPB, false, P == 4>(sm, t, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+        strided_pass<T, RL, 3, TPL, LPB, BWD>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// contiguous kernel: Stockham auto-sort, LPB lines per CTA, TPL = N / rmax threads per line, padded rows
+// contiguous kernel: Stockham auto-sort, LPB lines per CTA, TPL = N / rmax threads per line, padded rows.
+// The first pass loads straight from global memory into the butterfly registers (unit stride across the threads of
+// a line) and the last pass stores straight from registers (unit stride again: that is what auto-sort buys).
 // ---------------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int pad_index(int i){ return i + (i >> 3); }
+__host__ __device__ constexpr unsigned pad_index(unsigned i){ return i + (i >> 3); }
 
-template<typename T, typename RL, int S, int NS, int TPL, bool FIRST, bool LAST>
-__device__ __forceinline__ void contig_pass(cplx<T> *row, int j, bool valid,
-                                            const cplx<T> *gin, cplx<T> *gout, long long istride, long long ostride,
-                                            const cplx<T> *tw, bool backward, T scale, bool do_scale){
-    constexpr int R = RL::radix(S);
-    constexpr int NB = RL::N / R;
-    constexpr int BPT = NB / TPL;              // butterflies per thread in this pass
+template<typename T, typename RL, int S, int NS, int TPL, bool BWD>
+__device__ __forceinline__ void contig_pass(cplx<T> *row, unsigned j, bool valid, const cplx<T> *gin, cplx<T> *gout,
+                                            long long istride, long long ostride, const cplx<T> *tw, T scale, bool do_scale){
+    constexpr unsigned R = RL::radix(S);
+    constexpr unsigned NB = RL::N / R;
+    constexpr unsigned BPT = NB / TPL;              // butterflies per thread in this pass
+    constexpr bool FIRST = (S == 0), LAST = (S == RL::passes - 1);
     cplx<T> v[BPT][R];
     #pragma unroll
-    for(int u=0; u<BPT; u++){
-        int q = j + u * TPL;
-        if (FIRST){
-            #pragma unroll
-            for(int r=0; r<R; r++){
-                cplx<T> x = valid ? gin[(long long)(q + r * NB) * istride] : mk<T>(0, 0);
-                v[u][r] = backward ? cswap(x) : x;
+    for(unsigned u=0; u<BPT; u++){
+        const unsigned q = j + u * TPL;
+        if constexpr (FIRST){
+            if (valid){
+                const cplx<T> *src = gin + static_cast<long long>(q) * istride;
+                const long long hop = static_cast<long long>(NB) * istride;
+                #pragma unroll
+                for(unsigned r=0; r<R; r++){
+                    cplx<T> x = *src;
+                    src += hop;
+                    v[u][r] = BWD ? cswap(x) : x;
+                }
+            }else{
+                #pragma unroll
+                for(unsigned r=0; r<R; r++) v[u][r] = mk<T>(0, 0);
             }
         }else{
             #pragma unroll
-            for(int r=0; r<R; r++) v[u][r] = row[pad_index(q + r * NB)];
+            for(unsigned r=0; r<R; r++) v[u][r] = row[pad_index(q + r * NB)];
         }
     }
-    if (!FIRST) __syncthreads();   // every leg has been read before anybody overwrites the row
+    if constexpr (!FIRST) __syncthreads();   // every leg has been read before anybody overwrites the row
     #pragma unroll
-    for(int u=0; u<BPT; u++){
-        int q = j + u * TPL;
-        int k = q % NS;
-        if (NS > 1) apply_twiddles<T, R, true>(v[u], tw, k * (RL::N / (NS * R)));
+    for(unsigned u=0; u<BPT; u++){
+        const unsigned q = j + u * TPL;
+        const unsigned k = q % NS;
+        if constexpr (NS > 1) apply_twiddles<T, R, true>(v[u], tw, k * (RL::N / (NS * R)));
         butterfly<T, R>::run(v[u]);
-        int o = (q / NS) * NS * R + k;
-        if (!LAST){
+        const unsigned o = (q / NS) * (NS * R) + k;
+        if constexpr (!LAST){
             #pragma unroll
-            for(int r=0; r<R; r++) row[pad_index(o + r * NS)] = v[u][r];
-        }else if (valid){
-            #pragma unroll
-            for(int r=0; r<R; r++){
-                cplx<T> x = backward ? cswap(v[u][r]) : v[u][r];
-                if (do_scale){ x.x *= scale; x.y *= scale; }
-                gout[(long long)(o + r * NS) * ostride] = x;
+            for(unsigned r=0; r<R; r++) row[pad_index(o + r * NS)] = v[u][r];
+        }else{
+            if (valid){
+                cplx<T> *dst = gout + static_cast<long long>(o) * ostride;
+                const long long hop = static_cast<long long>(NS) * ostride;
+                #pragma unroll
+                for(unsigned r=0; r<R; r++){
+                    cplx<T> x = BWD ? cswap(v[u][r]) : v[u][r];
+                    if (do_scale){ x.x *= scale; x.y *= scale; }
+                    *dst = x;
+                    dst += hop;
+                }
             }
         }
     }
 }
 
-template<typename T, typename RL, int LPB, int MINB>
+template<typename T, typename RL, int LPB, int MINB, bool BWD>
 __global__ void __launch_bounds__((RL::N / RL::rmax) * LPB, MINB) fft_contig_kernel(fft_args a){
     B200_DYN_SMEM(smem_raw);
     constexpr int TPL = RL::N / RL::rmax;
-    constexpr int PITCH = pad_index(RL::N) + 1;
-    const int j = threadIdx.x % TPL, t = threadIdx.x / TPL;
+    constexpr unsigned PITCH = pad_index(RL::N) + 1;
+    const unsigned j = threadIdx.x % TPL, t = threadIdx.x / TPL;
     cplx<T> *row = reinterpret_cast<cplx<T>*>(smem_raw) + t * PITCH;
-    const long long line = (long long)blockIdx.x * LPB + t;
+    const unsigned line = blockIdx.x * LPB + t;
     const bool valid = line < a.nlines;
-    const cplx<T> *gin = reinterpret_cast<const cplx<T>*>(a.in) + (valid ? line_offset(a.ig, a.count_a, line) : 0);
-    cplx<T> *gout = reinterpret_cast<cplx<T>*>(a.out) + (valid ? line_offset(a.og, a.count_a, line) : 0);
+    const cplx<T> *gin = reinterpret_cast<const cplx<T>*>(a.in) + (valid ? tile_line_offset(a.ig, a.count_a, line) : 0);
+    cplx<T> *gout = reinterpret_cast<cplx<T>*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, line) : 0);
     const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
-    const bool bwd = a.backward != 0;
     const T scale = static_cast<T>(a.scale);
     const bool do_scale = a.scale != 1.0;
     constexpr int P = RL::passes;
     constexpr int N1 = RL::radix(0), N2 = N1 * RL::radix(1), N3 = N2 * RL::radix(2);
 
-    contig_pass<T, RL, 0, 1, TPL, true, P == 1>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+    contig_pass<T, RL, 0, 1, TPL, BWD>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale);
     if constexpr (P > 1){
         __syncthreads();
-        contig_pass<T, RL, 1, N1, TPL, false, P == 2>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+        contig_pass<T, RL, 1, N1, TPL, BWD>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale);
     }
     if constexpr (P > 2){
         __syncthreads();
-        contig_pass<T, RL, 2, N2, TPL, false, P == 3>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+        contig_pass<T, RL, 2, N2, TPL, BWD>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale);
     }
     if constexpr (P > 3){
         __syncthreads();
-        contig_pass<T, RL, 3, N3, TPL, false, P == 4>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, bwd, scale, do_scale);
+        contig_pass<T, RL, 3, N3, TPL, BWD>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale);
     }
 }
 

@@ -8,6 +8,7 @@
 #include <functional>
 #include <memory>
 #include <thread>
+#include <cstring>
 #include <vector>
 
 #define __global__
