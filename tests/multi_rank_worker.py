@@ -1,0 +1,170 @@
+"""
+Multi-rank GPU parity worker (one process per GPU, launched by torch.distributed.run from tests/test_gpu_multi.py or by
+hand:  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_rank_worker.py).
+
+Mirrors the reference's distributed tests (test/test_fft3d.h:160-330: world array -> get_subbox per rank -> forward ->
+compare with the matching sub-box of the single-rank result; test/test_fft3d_r2c.cpp; test/test_cos.cpp) with the numpy
+oracle standing where the reference uses forward_fft<backend::stock>() on the whole world.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import heffte_oracle as O  # noqa: E402
+from tests.helpers import TOL, bricks, to_h  # noqa: E402
+
+
+def grids_for(nranks):
+    """(in grid, out grid) pairs in the spirit of test/test_fft3d_np2/np4/np6/np8/np12.cpp"""
+    table = {
+        1: [((1, 1, 1), (1, 1, 1))],
+        2: [((1, 1, 2), (1, 1, 2)), ((2, 1, 1), (1, 2, 1)), ((1, 2, 1), (2, 1, 1))],
+        3: [((1, 3, 1), (3, 1, 1))],
+        4: [((1, 2, 2), (1, 2, 2)), ((4, 1, 1), (1, 1, 4)), ((2, 2, 1), (1, 2, 2))],
+        6: [((1, 2, 3), (3, 2, 1))],
+        8: [((2, 2, 2), (2, 2, 2)), ((1, 2, 4), (2, 4, 1)), ((8, 1, 1), (1, 1, 8)), ((2, 4, 1), (1, 2, 4))],
+    }
+    return table.get(nranks, [((1, 1, nranks), (nranks, 1, 1))])
+
+
+def configs(nranks, quick):
+    out = []
+    sizes = [(16, 16, 16), (20, 21, 22)] if quick else [(16, 16, 16), (20, 21, 22), (64, 64, 64), (32, 48, 40)]
+    for gi, (gin, gout) in enumerate(grids_for(nranks)):
+        for n in sizes:
+            for prec in (1, 0):
+                for reorder in (False, True):
+                    for pencils in (True, False):
+                        for alg in (0, 3, 2, 1) if (not quick and gi == 0 and n == sizes[0]) else (0,):
+                            out.append(dict(kind="c2c", n=n, prec=prec, reorder=reorder, pencils=pencils, alg=alg, gin=gin, gout=gout,
+                                            order_out=(0, 1, 2)))
+        # different order of the output boxes (test/test_fft3d.h:247-250 reordered io boxes)
+        out.append(dict(kind="c2c", n=sizes[-1], prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(2, 0, 1)))
+        for r2c_dir in (0, 1, 2):
+            for prec in (1, 0):
+                for reorder in (False, True):
+                    out.append(dict(kind="r2c", n=sizes[-1], prec=prec, reorder=reorder, pencils=True, alg=0, gin=gin, gout=gout,
+                                    order_out=(0, 1, 2), r2c_dir=r2c_dir))
+        for kind in ("cos", "sin", "cos1"):
+            out.append(dict(kind=kind, n=sizes[0], prec=1, reorder=True, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)))
+    # power-of-two sizes that take the fast kernels on every stage
+    n = (64, 64, 64) if quick else (128, 128, 128)
+    gin, gout = grids_for(nranks)[0]
+    for prec in (1, 0):
+        out.append(dict(kind="c2c", n=n, prec=prec, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)))
+        out.append(dict(kind="r2c", n=n, prec=prec, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2), r2c_dir=0))
+    return out
+
+
+def run_config(hf, torch, comm, rank, c, batch=1):
+    n, kind, prec = c["n"], c["kind"], c["prec"]
+    world = O.world_box(n)
+    r2c_dir = c.get("r2c_dir", 0)
+    oworld = world.r2c(r2c_dir) if kind == "r2c" else world
+    inboxes = bricks(world, c["gin"])
+    outboxes = bricks(oworld, c["gout"], c["order_out"])
+    inbox, outbox = inboxes[rank], outboxes[rank]
+    complex_in = kind == "c2c"
+    rng = np.random.default_rng(1234)
+    x = rng.random(world.count())
+    if complex_in:
+        x = x + 1j * rng.random(world.count())
+    rdt, cdt = (np.float32, np.complex64) if prec == 0 else (np.float64, np.complex128)
+    x = x.astype(cdt if complex_in else rdt)
+    tag = {"c2c": hf.backend.b200, "r2c": hf.backend.b200, "cos": hf.backend.b200_cos, "sin": hf.backend.b200_sin, "cos1": hf.backend.b200_cos1}[kind]
+    opts = hf.plan_options(tag, use_reorder=c["reorder"], algorithm=c["alg"], use_pencils=c["pencils"])
+    if kind == "r2c":
+        fft = hf.fft3d_r2c(tag, to_h(inbox), to_h(outbox), r2c_dir, comm, opts)
+    else:
+        fft = hf.fft3d(tag, to_h(inbox), to_h(outbox), comm, opts)
+    assert fft.size_inbox() == inbox.count() and fft.size_outbox() == outbox.count()
+    local = O.get_subbox(world, inbox, x)
+    out_dtype = cdt if kind in ("c2c", "r2c") else rdt
+    tol = TOL[prec] * (4 if kind in ("cos", "sin", "cos1") else 1)
+    worst = 0.0
+    for scaling, sname in ((1, "full"), (0, "none")):
+        ref = O.fft3d_forward(x, n, kind, r2c_dir=r2c_dir, scaling=sname)
+        dx = torch.from_numpy(np.tile(local, batch)).cuda()
+        dy = torch.empty(batch * outbox.count(), dtype=getattr(torch, np.dtype(out_dtype).name), device="cuda")
+        fft.forward(dx, dy, scaling, batch=batch)
+        expect = O.get_subbox(oworld, outbox, ref)
+        got = dy.cpu().numpy()
+        for b in range(batch):
+            seg = got[b * outbox.count():(b + 1) * outbox.count()]
+            err = O.rel_l2(seg, expect) if expect.size else 0.0
+            worst = max(worst, err)
+            assert err <= tol, "forward %s: rel l2 %.3e > %.1e" % (c, err, tol)
+        dz = torch.empty_like(dx)
+        fft.backward(dy, dz, scaling, batch=batch)
+        refb = O.fft3d_backward(ref, n, kind, r2c_dir=r2c_dir, scaling=sname)
+        expect_b = O.get_subbox(world, inbox, refb)
+        got = dz.cpu().numpy()
+        for b in range(batch):
+            seg = got[b * inbox.count():(b + 1) * inbox.count()]
+            err = O.rel_l2(seg, expect_b) if expect_b.size else 0.0
+            worst = max(worst, err)
+            assert err <= 2 * tol, "backward %s: rel l2 %.3e > %.1e" % (c, err, 2 * tol)
+    # in-place with a caller workspace (c2c and r2r only), the way speed3d drives the plan
+    if kind != "r2c" and inbox.count() == outbox.count():
+        work = torch.empty(fft.size_workspace(), dtype=dx.dtype, device="cuda")
+        d = torch.from_numpy(local.copy()).cuda()
+        fft.forward_buffered(d, d, work, 1)
+        fft.backward_buffered(d, d, work, 0)
+        err = O.rel_l2(d.cpu().numpy(), local) if local.size else 0.0
+        assert err <= 2 * tol, "in-place round trip %s: %.3e" % (c, err)
+    return worst
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import heffte_b200 as hf
+    rank, size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = hf.comm_from_torch()
+    else:
+        comm = hf.comm_self()
+    done, worst = 0, 0.0
+    failed = None
+    gin, gout = grids_for(size)[0]
+    todo = [(c, 1) for c in configs(size, args.quick)]
+    # batched transforms across ranks (test/test_fft3d.h:505-572)
+    todo.append((dict(kind="c2c", n=(16, 18, 20), prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 3))
+    flag = torch.zeros(1, device="cuda", dtype=torch.int32)
+    for c, batch in todo:
+        try:
+            worst = max(worst, run_config(hf, torch, comm, rank, c, batch))
+            done += 1
+        except AssertionError as e:
+            failed = str(e)
+        except Exception as e:  # noqa: BLE001
+            failed = repr(e)
+        # every rank learns about a failure before the next collective plan creation (no hangs)
+        flag.fill_(1 if failed else 0)
+        if size > 1:
+            dist.all_reduce(flag)
+        if int(flag.item()):
+            break
+    if failed:
+        print("rank %d FAILED after %d configs: %s" % (rank, done, failed), flush=True)
+    if rank == 0:
+        print("multi_rank_worker: ranks=%d configs=%d worst_rel_l2=%.3e failures=%d" % (size, done, worst, int(flag.item())), flush=True)
+    if size > 1:
+        dist.destroy_process_group()
+    sys.exit(1 if int(flag.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()
