@@ -1,0 +1,139 @@
+"""
+Host planning logic of the b200 backend against the reference -- CPU only (no compute calls).
+  * intermediate boxes / FFT directions of every stage against reference plan_operations() (src/heffte_plan_logic.cpp:424-453):
+    committed dumps of the BASELINE.json configurations (tests/golden/reference_plans.json) and, when oracle/_ref is
+    present, live on a sweep of world sizes, rank counts and option combinations;
+  * processor grids and world splitting against the values asserted in test/test_units_nompi.cpp:12-69;
+  * send/receive lists of the reshape against compute_overlap_map_* (src/heffte_reshape3d.cpp:125-206);
+  * plan sizes (inbox / outbox / workspace) against test/test_c.c:149-151, 225-227 and the reference's fft3d objects.
+"""
+import itertools
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import heffte_oracle as O
+from tests.golden import known_answers as K
+from tests.helpers import bricks, to_h
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _box(nine):
+    return O.Box(nine[0:3], nine[3:6], nine[6:9])
+
+
+def test_procgrid_known_answers(lib):
+    from heffte_b200 import heffte as H
+    for nprocs, grid in K.PROCGRID.items():
+        assert H.make_procgrid(nprocs) == grid
+    # test/test_units_nompi.cpp:48-69: split_world of a 2x3x5-grid keeps every index exactly once
+    world = O.world_box((20, 20, 20))
+    boxes = H.split_world(to_h(world), [2, 3, 5])
+    assert len(boxes) == 30 and sum(b.count() for b in boxes) == world.count()
+    assert H.proc_setup_min_surface(to_h(O.world_box((512, 512, 512))), 8) == [2, 2, 2]
+    assert H.proc_setup_min_surface(to_h(O.world_box((512, 512, 512))), 2) == [1, 1, 2]
+    assert H.proc_setup_min_surface(to_h(O.world_box((512, 512, 512))), 4) == [1, 2, 2]
+
+
+def test_baseline_plans_match_reference_dumps(lib):
+    from heffte_b200 import heffte as H
+    with open(os.path.join(GOLDEN, "reference_plans.json")) as f:
+        plans = json.load(f)
+    assert len(plans) >= 14
+    for name, p in plans.items():
+        inboxes = [to_h(_box(b)) for b in p["inboxes"]]
+        outboxes = [to_h(_box(b)) for b in p["outboxes"]]
+        world = to_h(O.world_box(p["n"]))
+        # our own world splitting reproduces the reference boxes
+        assert [b.nine() for b in H.split_world(world, p["gin"])] == p["inboxes"], name
+        shapes, fdir, count = H.logic_plan(inboxes, outboxes, r2c_direction=p.get("r2c_dir", -1), use_reorder=p.get("reorder", False),
+                                           algorithm=p.get("alg", 0), use_pencils=p.get("pencils", True))
+        assert fdir == p["fft_direction"], name
+        assert count == p["index_count"], name
+        assert shapes == p["shapes"], name
+
+
+def test_plan_sweep_against_live_reference(lib, reference):
+    from heffte_b200 import heffte as H
+    rng = np.random.default_rng(7)
+    checked = 0
+    worlds = [(8, 8, 8), (12, 10, 9), (31, 7, 16), (64, 64, 64), (5, 40, 6)]
+    for n, nranks in itertools.product(worlds, (1, 2, 3, 4, 6, 8, 12)):
+        world = O.world_box(n)
+        gin = reference.proc_setup_min_surface(world, nranks)
+        if min(n[d] // gin[d] for d in range(3)) < 1:
+            continue
+        inboxes = bricks(world, gin)
+        for r2c_dir, reorder, pencils, alg in itertools.product((-1, 0, 2), (False, True), (True, False), (0, 3)):
+            oworld = world.r2c(r2c_dir) if r2c_dir >= 0 else world
+            g2 = reference.make_procgrid(nranks)
+            gout = [(g2[0], g2[1], 1), (1, g2[0], g2[1]), tuple(gin)][int(rng.integers(0, 3))]
+            if min(oworld.size[d] // gout[d] for d in range(3)) < 1:
+                continue
+            outboxes = bricks(oworld, gout, [(0, 1, 2), (2, 0, 1)][int(rng.integers(0, 2))])
+            rank = int(rng.integers(0, nranks))
+            ref = reference.plan_operations(inboxes, outboxes, r2c_dir=r2c_dir, use_reorder=reorder, algorithm=alg, use_pencils=pencils, rank=rank)
+            mine = H.logic_plan([to_h(b) for b in inboxes], [to_h(b) for b in outboxes], r2c_direction=r2c_dir, use_reorder=reorder,
+                                algorithm=alg, use_pencils=pencils, rank=rank)
+            assert mine[1] == ref[1] and mine[2] == ref[2], (n, nranks, r2c_dir, reorder, pencils)
+            assert mine[0] == ref[0], (n, nranks, r2c_dir, reorder, pencils)
+            checked += 1
+    assert checked > 300
+
+
+def test_reshape_pieces_against_oracle(lib):
+    from heffte_b200 import heffte as H
+    world = O.world_box((9, 10, 11))
+    orders = [(0, 1, 2), (1, 0, 2), (2, 1, 0), (0, 2, 1), (1, 2, 0), (2, 0, 1)]
+    for trial in range(12):
+        src = bricks(world, [(1, 2, 3), (3, 2, 1), (2, 3, 1)][trial % 3], orders[trial % 6])
+        dst = bricks(world, [(6, 1, 1), (1, 1, 6), (1, 6, 1)][trial % 3], orders[(trial * 5 + 1) % 6])
+        for me in range(6):
+            sends = H.reshape_pieces([to_h(b) for b in src], [to_h(b) for b in dst], me, receive=False)
+            expect = O.overlap_map(me, 6, src[me], dst, receive=False)
+            assert [(s["peer"], s["offset"], s["count"], s["size0"], s["size1"], s["size2"], s["line"], s["plane"]) for s in sends] == \
+                   [(e["proc"], e["offset"], e["size"]) + tuple(e["plan"]["size"]) + (e["plan"]["line_stride"], e["plan"]["plane_stride"]) for e in expect]
+            recvs = H.reshape_pieces([to_h(b) for b in src], [to_h(b) for b in dst], me, receive=True)
+            expect = O.overlap_map(me, 6, dst[me], src, receive=True)
+            assert [(r["peer"], r["offset"], r["count"], r["buff_line"], r["buff_plane"], (r["map0"], r["map1"], r["map2"])) for r in recvs] == \
+                   [(e["proc"], e["offset"], e["size"], e["plan"]["buff_line_stride"], e["plan"]["buff_plane_stride"], tuple(e["plan"]["map"])) for e in expect]
+            # message slots are dense and ordered like the peers
+            assert [s["buffer_offset"] for s in sends] == list(np.cumsum([0] + [s["count"] for s in sends])[:-1])
+
+
+def test_plan_sizes_of_test_c(lib):
+    # test/test_c.c:149-151 (c2c) and :225-227 (r2c, direction 2): 4x4x4 on two ranks split along dimension 2
+    from heffte_b200 import heffte as H
+    world = O.world_box((4, 4, 4))
+    boxes = [to_h(b) for b in bricks(world, (1, 1, 2))]
+    for rank in range(2):
+        got = H.plan_sizes(0, boxes, boxes, rank, use_reorder=True)
+        assert dict(zip(("inbox", "outbox", "workspace"), got)) == K.C_TEST_SIZES["c2c"][rank]
+    # r2c: rank 0 keeps k = 0..1 of the shortened third dimension (3 entries): rank 0 -> 2 planes, rank 1 -> 1 plane
+    cboxes = [to_h(O.Box((0, 0, 0), (3, 3, 1))), to_h(O.Box((0, 0, 2), (3, 3, 2)))]
+    for rank in range(2):
+        got = H.plan_sizes(1, boxes, cboxes, rank, r2c_direction=2, use_reorder=True)
+        assert dict(zip(("inbox", "outbox", "workspace"), got)) == K.C_TEST_SIZES["r2c"][rank]
+
+
+def test_plan_sizes_against_live_reference(lib, reference):
+    from heffte_b200 import heffte as H
+    kinds = {"c2c": 0, "r2c": 1, "cos": 2}
+    for n, grid in (((12, 10, 8), (1, 2, 2)), ((9, 11, 13), (3, 1, 1)), ((16, 16, 16), (2, 2, 2)), ((7, 6, 20), (1, 1, 5))):
+        world = O.world_box(n)
+        for kind, reorder, pencils in itertools.product(("c2c", "r2c", "cos"), (False, True), (True, False)):
+            oworld = world.r2c(0) if kind == "r2c" else world
+            inboxes, outboxes = bricks(world, grid), bricks(oworld, grid[::-1])
+            eff_reorder = True if kind == "cos" else reorder
+            _, ws = reference.fft3d(kind, 1, inboxes, outboxes, None, r2c_dir=0, use_reorder=eff_reorder, use_pencils=pencils)
+            for rank in range(len(inboxes)):
+                got = H.plan_sizes(kinds[kind], [to_h(b) for b in inboxes], [to_h(b) for b in outboxes], rank,
+                                   r2c_direction=0 if kind == "r2c" else -1, use_reorder=eff_reorder, use_pencils=pencils)
+                assert got[0] == inboxes[rank].count() and got[1] == outboxes[rank].count()
+                # the reference executors may add private scratch (stock r2r: 4n extension); ours never need more than the reference
+                assert got[2] <= ws[rank], (n, grid, kind, reorder, pencils, rank, got, ws[rank])
+                if kind != "cos":
+                    assert got[2] == ws[rank], (n, grid, kind, reorder, pencils, rank)
