@@ -1,6 +1,8 @@
 // TEST INFRASTRUCTURE ONLY -- runs the product's FFT kernel source (heffte_b200/csrc/fft_device.cuh) on the CPU
 // through tests/emul/cuda_emul.h so the CPU-only test-suite can check index arithmetic.  Not part of the product.
+#ifndef B200_HOST_EMULATION
 #define B200_HOST_EMULATION
+#endif
 #include "fft_host_plan.h"
 
 namespace {
@@ -13,7 +15,7 @@ struct emul_launcher {
 };
 }
 
-extern "C" int emul_fft1d(const b200_fft1d_desc *desc, int direction, const void *in, void *out, double scale, int *family){
+extern "C" __attribute__((visibility("default"))) int emul_fft1d(const b200_fft1d_desc *desc, int direction, const void *in, void *out, double scale, int *family){
     b200::host_plan plan;
     const char *why = "";
     int rc = b200::make_host_plan(*desc, plan, &why);

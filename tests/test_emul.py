@@ -26,7 +26,9 @@ def emul():
               [os.path.join(ROOT, "heffte_b200", "csrc", f) for f in ("fft_device.cuh", "fft_dispatch.cuh", "fft_host_plan.h")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in sources):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        cmd = ["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "heffte_b200", "csrc"), "-I", EMUL_DIR,
+        # -Bsymbolic + hidden visibility: the emulated kernels carry the same C++ names as the device stubs inside
+        # libheffte_b200.so (loaded RTLD_GLOBAL by other tests); they must bind to the copies in this library
+        cmd = ["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-fvisibility=hidden", "-Wl,-Bsymbolic", "-I", os.path.join(ROOT, "heffte_b200", "csrc"), "-I", EMUL_DIR,
                os.path.join(EMUL_DIR, "emul_fft.cpp"), "-o", out]
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
