@@ -5,4 +5,4 @@ to a CPU implementation.
 """
 from . import heffte  # noqa: F401
 from .heffte import (backend, scale, reshape_algorithm, box3d, plan_options, fft3d, fft3d_r2c,  # noqa: F401
-                     comm_self, comm_from_torch, comm_from_callbacks, heffte_input_error)
+                     comm_self, comm_threads, comm_from_torch, comm_from_callbacks, heffte_input_error)

@@ -68,6 +68,7 @@ def load():
     sig("heffte_comm_nccl_unique_id", c_int, c_vp)
     sig("heffte_comm_create_nccl", c_int, c_int, c_int, c_vp, ctypes.POINTER(c_vp))
     sig("heffte_comm_create_callbacks", c_int, c_int, c_int, ALLGATHER_FN, EXCHANGE_FN, c_vp, ctypes.POINTER(c_vp))
+    sig("heffte_comm_create_threads", c_int, c_int, ip, ctypes.POINTER(c_vp))
     sig("heffte_comm_rank", c_int, c_vp)
     sig("heffte_comm_size", c_int, c_vp)
     sig("heffte_comm_destroy", c_int, c_vp)
@@ -90,6 +91,10 @@ def load():
         sig("heffte_backward_" + name + "_buffered", None, LP_plan, c_vp, c_vp, c_vp, c_int)
     for name in ("forward_s2s", "forward_d2d", "backward_s2s", "backward_d2d"):
         sig("heffte_" + name + "_buffered", None, LP_plan, c_vp, c_vp, c_vp, c_int)
+    sig("heffte_b200_uses_peer_memory", c_int, LP_plan, c_int)
+    sig("b200_fft1d_execute_scatter", c_int, c_vp, c_int, c_vp, c_vp, c_dbl, c_vp)
+    sig("b200_scatter_copy", c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_vp, c_vp, c_vp)
+    sig("b200_peer_barrier", c_int, c_int, c_int, ctypes.POINTER(c_vp), c_vp, ctypes.c_ulonglong, c_vp)
     sig("heffte_execute", c_int, LP_plan, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int)
     sig("heffte_execute_host", c_int, LP_plan, c_int, c_int, c_int, c_vp, c_vp, c_int)
 

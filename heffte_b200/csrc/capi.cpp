@@ -141,6 +141,14 @@ int heffte_comm_create_callbacks(int rank, int size, heffte_allgather_fn gather,
     *comm = new heffte_comm_s{std::unique_ptr<communicator>(make_callback_communicator(rank, size, gather, exchange, context))};
     return 0;
 }
+int heffte_comm_create_threads(int size, const int *devices, heffte_comm *comms){
+    if (comms == nullptr or size < 1) return fail(B200_ERR_INVALID, "bad arguments");
+    std::string error;
+    std::vector<communicator*> group = make_thread_communicators(size, devices, error);
+    if (static_cast<int>(group.size()) != size) return fail(B200_ERR_INVALID, error);
+    for(int r=0; r<size; r++) comms[r] = new heffte_comm_s{std::unique_ptr<communicator>(group[r])};
+    return 0;
+}
 int heffte_comm_rank(heffte_comm comm){ return (comm and comm->impl) ? comm->impl->rank() : -1; }
 int heffte_comm_size(heffte_comm comm){ return (comm and comm->impl) ? comm->impl->size() : -1; }
 int heffte_comm_destroy(heffte_comm comm){ delete comm; return 0; }
@@ -189,6 +197,12 @@ int heffte_size_workspace(heffte_plan const plan){ return static_cast<int>(hefft
 int heffte_get_backend(heffte_plan const plan){ return plan ? plan->backend_type : -1; }
 int heffte_is_r2c(heffte_plan const plan){ return plan ? plan->using_r2c : -1; }
 double heffte_get_scale_factor(heffte_plan const plan, int scale){ auto *s = state_of(plan); return s ? s->fft->scale_factor(scale) : 0.0; }
+
+int heffte_b200_uses_peer_memory(heffte_plan const plan, int precision){
+    plan_state *s = state_of(plan);
+    if (s == nullptr or precision < 0 or precision > 1) return -1;
+    return s->fft->uses_peer_memory(precision) ? 1 : 0;
+}
 
 int heffte_execute(heffte_plan const plan, int precision, int direction, int batch, void const *input, void *output, void *workspace, int scale){
     plan_state *s = state_of(plan);

@@ -2,8 +2,11 @@
 
 #include <dlfcn.h>
 
+#include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 
 namespace b200 {
@@ -114,7 +117,47 @@ public:
         return 0;
     }
     const char* kind() const override { return "nccl"; }
+    // one process per GPU on one node: CUDA IPC handles travel through the allgather, peers are opened with peer access
+    bool map_peers(void *local, size_t bytes, std::vector<void*> &peers) override {
+        (void) bytes;
+        peers.assign(nranks, nullptr);
+        const char *off = std::getenv("HEFFTE_B200_DISABLE_P2P");
+        struct record { cudaIpcMemHandle_t handle; int ok; int device; char host[64]; };
+        record mine{};
+        mine.ok = (off == nullptr or off[0] == '0') ? 1 : 0;
+        if (mine.ok and cudaIpcGetMemHandle(&mine.handle, local) != cudaSuccess){ mine.ok = 0; cudaGetLastError(); }
+        cudaGetDevice(&mine.device);
+        gethostname_safe(mine.host, sizeof(mine.host));
+        std::vector<record> all(nranks);
+        if (allgather(&mine, all.data(), sizeof(record)) != 0) return false;
+        bool usable = true;
+        for(int r=0; r<nranks; r++) usable = usable and all[r].ok and std::strncmp(all[r].host, mine.host, sizeof(mine.host)) == 0;
+        int opened = usable ? 1 : 0;
+        if (usable){
+            for(int r=0; r<nranks; r++){
+                if (r == my_rank){ peers[r] = local; continue; }
+                if (cudaIpcOpenMemHandle(&peers[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess){
+                    cudaGetLastError(); peers[r] = nullptr; opened = 0; break;
+                }
+            }
+        }
+        // everybody must agree
+        std::vector<int> votes(nranks);
+        if (allgather(&opened, votes.data(), sizeof(int)) != 0) opened = 0;
+        for(int v : votes) if (not v) opened = 0;
+        if (not opened){ unmap_peers(peers); peers.clear(); return false; }
+        return true;
+    }
+    void unmap_peers(std::vector<void*> const &peers) override {
+        for(int r=0; r<static_cast<int>(peers.size()); r++)
+            if (r != my_rank and peers[r] != nullptr) cudaIpcCloseMemHandle(peers[r]);
+    }
 private:
+    static void gethostname_safe(char *out, size_t n){
+        std::memset(out, 0, n);
+        FILE *f = std::fopen("/proc/sys/kernel/random/boot_id", "r");   // same kernel instance == same node (containers share it)
+        if (f){ if (std::fgets(out, static_cast<int>(n), f) == nullptr) out[0] = 0; std::fclose(f); }
+    }
     nccl_comm_t comm = nullptr;
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -139,7 +182,116 @@ private:
     void *context;
 };
 
+// ---- ranks as host threads of one process ------------------------------------------------------------------------------
+struct thread_group {
+    int size = 0;
+    std::mutex guard;
+    std::condition_variable cv;
+    int waiting = 0;
+    long long generation = 0;
+    std::vector<const void*> slot;                 // per rank: pointer published for the current collective
+    struct posted { std::vector<transfer> sends; cudaEvent_t ready = nullptr, done = nullptr; int device = 0; };
+    std::vector<posted> box;
+
+    void sync(){
+        std::unique_lock<std::mutex> lock(guard);
+        long long const mine = generation;
+        if (++waiting == size){ waiting = 0; generation++; cv.notify_all(); }
+        else cv.wait(lock, [&]{ return generation != mine; });
+    }
+};
+
+class thread_communicator : public communicator {
+public:
+    thread_communicator(int rank, std::shared_ptr<thread_group> g, int dev) : group(g), device(dev){ my_rank = rank; nranks = g->size; }
+    ~thread_communicator() override {
+        thread_group::posted &mine = group->box[my_rank];
+        if (mine.ready){ cudaEventDestroy(mine.ready); mine.ready = nullptr; }
+        if (mine.done){ cudaEventDestroy(mine.done); mine.done = nullptr; }
+    }
+    int allgather(const void *mine, void *all, size_t bytes) override {
+        group->slot[my_rank] = mine;
+        group->sync();
+        for(int r=0; r<nranks; r++) std::memcpy(static_cast<char*>(all) + r * bytes, group->slot[r], bytes);
+        group->sync();
+        return 0;
+    }
+    int exchange(std::vector<transfer> const &sends, std::vector<transfer> const &recvs, cudaStream_t stream) override {
+        cudaSetDevice(device);
+        thread_group::posted &mine = group->box[my_rank];
+        if (mine.ready == nullptr){
+            if (cudaEventCreateWithFlags(&mine.ready, cudaEventDisableTiming) != cudaSuccess) return 1;
+            if (cudaEventCreateWithFlags(&mine.done, cudaEventDisableTiming) != cudaSuccess) return 1;
+        }
+        mine.sends = sends;
+        mine.device = device;
+        if (cudaEventRecord(mine.ready, stream) != cudaSuccess) return 1;      // my messages are packed
+        group->sync();
+        int status = 0;
+        for(auto const &r : recvs){
+            thread_group::posted &from = group->box[r.peer];
+            const transfer *match = nullptr;
+            for(auto const &s : from.sends) if (s.peer == my_rank){ match = &s; break; }
+            if (match == nullptr or match->bytes != r.bytes){ status = 1; continue; }
+            if (cudaStreamWaitEvent(stream, from.ready, 0) != cudaSuccess) status = 1;
+            if (r.bytes > 0 and cudaMemcpyPeerAsync(r.data, device, match->data, from.device, r.bytes, stream) != cudaSuccess) status = 1;
+        }
+        if (cudaEventRecord(mine.done, stream) != cudaSuccess) status = 1;     // I have pulled everything addressed to me
+        group->sync();
+        for(auto const &s : sends)                                              // my send buffer is free once the receivers are done
+            if (cudaStreamWaitEvent(stream, group->box[s.peer].done, 0) != cudaSuccess) status = 1;
+        group->sync();
+        return status;
+    }
+    int barrier(cudaStream_t) override { group->sync(); return 0; }
+    const char* kind() const override { return "threads"; }
+    void after_peer_barrier() override { group->sync(); }
+    bool map_peers(void *local, size_t bytes, std::vector<void*> &peers) override {
+        (void) bytes;
+        const char *off = std::getenv("HEFFTE_B200_DISABLE_P2P");
+        struct record { void *ptr; int device; int ok; };
+        record mine{local, device, (off == nullptr or off[0] == '0') ? 1 : 0};
+        std::vector<record> all(nranks);
+        allgather(&mine, all.data(), sizeof(record));
+        int usable = 1;
+        cudaSetDevice(device);
+        for(int r=0; r<nranks and usable; r++){
+            if (not all[r].ok) usable = 0;
+            if (all[r].device != device){
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, device, all[r].device) != cudaSuccess or not can) usable = 0;
+                else{
+                    cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+                    if (e != cudaSuccess and e != cudaErrorPeerAccessAlreadyEnabled) usable = 0;
+                    cudaGetLastError();
+                }
+            }
+        }
+        std::vector<int> votes(nranks);
+        allgather(&usable, votes.data(), sizeof(int));
+        for(int v : votes) if (not v) usable = 0;
+        peers.clear();
+        if (not usable) return false;
+        for(int r=0; r<nranks; r++) peers.push_back(all[r].ptr);
+        return true;
+    }
+private:
+    std::shared_ptr<thread_group> group;
+    int device;
+};
+
 } // namespace
+
+std::vector<communicator*> make_thread_communicators(int size, const int *devices, std::string &error){
+    std::vector<communicator*> out;
+    if (size < 1){ error = "bad group size"; return out; }
+    auto group = std::make_shared<thread_group>();
+    group->size = size;
+    group->slot.assign(size, nullptr);
+    group->box.resize(size);
+    for(int r=0; r<size; r++) out.push_back(new thread_communicator(r, group, devices ? devices[r] : 0));
+    return out;
+}
 
 communicator* make_self_communicator(){ return new self_communicator(); }
 

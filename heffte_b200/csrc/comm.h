@@ -6,7 +6,7 @@
 // copy already loaded by PyTorch is shared when the backend is used from Python.
 #pragma once
 
-#include <cuda_runtime.h>
+#include "cuda_compat.h"
 
 #include <cstddef>
 #include <string>
@@ -31,6 +31,15 @@ public:
     virtual int exchange(std::vector<transfer> const &sends, std::vector<transfer> const &recvs, cudaStream_t stream) = 0;
     virtual int barrier(cudaStream_t stream) = 0;
     virtual const char* kind() const = 0;
+    // Peer memory (NVLink): COLLECTIVE.  Every rank passes one device allocation of `bytes`; on success peers[r] is an
+    // address valid on THIS rank's device for rank r's allocation (peers[rank()] == local) and every rank returns true.
+    // Returns false on every rank when peer mapping is not available (the plan then uses exchange()).
+    virtual bool map_peers(void *local, size_t bytes, std::vector<void*> &peers){ (void) local; (void) bytes; peers.clear(); return false; }
+    virtual void unmap_peers(std::vector<void*> const &peers){ (void) peers; }
+    // Called right after a peer barrier kernel has been enqueued.  Ranks that are host threads sharing one GPU rendezvous here:
+    // kernels of different streams can share a hardware queue, and a spinning barrier kernel followed by dependent work of the
+    // same stream would otherwise block the barrier kernel of another rank queued behind it.  One process per GPU: nothing to do.
+    virtual void after_peer_barrier(){}
 protected:
     int my_rank = 0, nranks = 1;
 };
@@ -41,6 +50,12 @@ communicator* make_self_communicator();
 communicator* make_nccl_communicator(int rank, int size, const void *unique_id, std::string &error);
 // fills 128 bytes; returns 0 on success
 int nccl_unique_id(void *out128, std::string &error);
+
+// N ranks inside ONE process, one host thread per rank (the single-process multi-GPU mode, and the way the test-suite runs
+// multi-rank plans on a single GPU): rank r drives device devices[r] (repeats allowed).  Peer memory is direct (unified
+// addressing + cudaDeviceEnablePeerAccess), exchange() is a stream-ordered device copy.  Returns `size` communicators that
+// share one group; each must be used from its own host thread, collectively.
+std::vector<communicator*> make_thread_communicators(int size, const int *devices, std::string &error);
 
 // host-only communicator driven by callbacks (used by the CPU-side multi-process tests of the planning logic
 // and by callers that own a different transport); exchange() is the caller's callback

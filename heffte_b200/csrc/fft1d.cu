@@ -27,6 +27,26 @@ void allow_smem(const void *kernel, size_t){
     done.insert(kernel);
 }
 
+
+#define B200_DECLARE_SLICE(name) int name(int n, fft_args const &a, cuda_launcher &L)
+B200_DECLARE_SLICE(run_strided_f32_direct); B200_DECLARE_SLICE(run_strided_f32_scatter);
+B200_DECLARE_SLICE(run_strided_f64_direct); B200_DECLARE_SLICE(run_strided_f64_scatter);
+B200_DECLARE_SLICE(run_contig_f32_direct);  B200_DECLARE_SLICE(run_contig_f32_scatter);
+B200_DECLARE_SLICE(run_contig_f64_direct);  B200_DECLARE_SLICE(run_contig_f64_scatter);
+
+int cuda_launcher::run_pow2(bool strided, bool is_float, bool scatter, int n, fft_args const &a){
+    if (strided){
+        if (is_float) return scatter ? run_strided_f32_scatter(n, a, *this) : run_strided_f32_direct(n, a, *this);
+        return scatter ? run_strided_f64_scatter(n, a, *this) : run_strided_f64_direct(n, a, *this);
+    }
+    if (is_float) return scatter ? run_contig_f32_scatter(n, a, *this) : run_contig_f32_direct(n, a, *this);
+    return scatter ? run_contig_f64_scatter(n, a, *this) : run_contig_f64_direct(n, a, *this);
+}
+int cuda_launcher::run_generic(bool is_float, long long blocks, int threads, size_t smem, generic_args const &g){
+    if (is_float) return launch(fft_generic_kernel<float>, blocks, threads, smem, g);
+    return launch(fft_generic_kernel<double>, blocks, threads, smem, g);
+}
+
 } // namespace b200
 
 using namespace b200;
@@ -90,6 +110,14 @@ int b200_fft1d_execute(b200_fft1d_plan plan, int direction, const void *in, void
     if (plan == nullptr) return fail(B200_ERR_INVALID, "null plan");
     cuda_launcher L{static_cast<cudaStream_t>(stream)};
     int rc = run_host_plan(plan->host, plan->twiddle, direction, in, out, scale, L);
+    if (rc == -1) return fail(B200_ERR_UNSUPPORTED, "no kernel for this length");
+    return rc;
+}
+
+int b200_fft1d_execute_scatter(b200_fft1d_plan plan, int direction, const void *in, const void *device_scatter_map, double scale, void *stream){
+    if (plan == nullptr or device_scatter_map == nullptr) return fail(B200_ERR_INVALID, "null plan or scatter map");
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    int rc = run_host_plan(plan->host, plan->twiddle, direction, in, nullptr, scale, L, device_scatter_map);
     if (rc == -1) return fail(B200_ERR_UNSUPPORTED, "no kernel for this length");
     return rc;
 }

@@ -17,6 +17,7 @@
 #pragma once
 
 #include "cuda_compat.h"
+#include "scatter_map.h"
 #include <stdint.h>
 
 namespace b200 {
@@ -140,7 +141,39 @@ struct fft_args {
     int count_a;
     int backward;          // 0 forward, 1 backward
     double scale;          // applied on the final store
+    const scatter_map *smap;   // device pointer; non-null selects the scatter variants (og is ignored)
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// scatter map: where the output of a batched transform goes when the following reshape is fused into the store.
+// The local box is cut into cells (<= 8 per axis) such that every cell lands in ONE destination box; a cell knows the
+// address of its destination (local memory or a peer GPU's memory mapped over NVLink) and the strides of that box.
+// Coordinates are local: k = index along the transform, (a, b) = line index split as a = line % count_a, b = line / count_a.
+// Replaces, fused: direct_packer::pack + MPI_Alltoallv + direct/transpose_packer::unpack of the reference
+// (src/heffte_reshape3d.cpp:365-443, include/heffte_pack3d.h:89-197).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int scatter_find(const int *cut, int n, int x){
+    int c = 0;
+    for(int i=1; i<n; i++) c += (x >= cut[i]) ? 1 : 0;
+    return c;
+}
+// cell row of a line: constant for a thread that owns one line
+__device__ __forceinline__ int scatter_row(const scatter_map *m, int a, int b){
+    return scatter_find(m->cut_a, m->na, a) * m->nb + scatter_find(m->cut_b, m->nb, b);
+}
+template<typename V>
+__device__ __forceinline__ V* scatter_address(const scatter_map *m, int row, int k, int a, int b){
+    const int ck = scatter_find(m->cut_k, m->nk, k);
+    const scatter_cell &c = m->cell[ck * (m->na * m->nb) + row];
+    return reinterpret_cast<V*>(c.base) + (k * c.sk + a * c.sa + b * c.sb);
+}
+// every thread of the CTA takes part; the caller synchronises before the map is used
+__device__ __forceinline__ void scatter_stage(scatter_map *dst, const scatter_map *src){
+    const int words = (scatter_header_bytes + static_cast<int>(sizeof(scatter_cell)) * src->ncells) / 16;
+    const int4 *g = reinterpret_cast<const int4*>(src);
+    int4 *s = reinterpret_cast<int4*>(dst);
+    for(int i = threadIdx.x; i < words; i += blockDim.x) s[i] = g[i];
+}
 
 __device__ __forceinline__ long long line_offset(line_geom const &g, int count_a, long long line){
     long long b = line / count_a;
@@ -223,9 +256,11 @@ __device__ __forceinline__ long long tile_line_offset(line_geom const &g, int co
 // brought in with asynchronous copies (LDGSTS, all of it in flight at once, no registers held across the load), the
 // passes are in-place decimation-in-frequency, and the digit reversal is absorbed into the row index of the store.
 // ---------------------------------------------------------------------------------------------------------
-template<typename T, typename RL, int S, int TPL, int LPB, bool BWD>
+struct scatter_ctx { const scatter_map *map; int row, a, b; };   // per-thread view of the map (one line per thread)
+
+template<typename T, typename RL, int S, int TPL, int LPB, bool BWD, bool SCATTER>
 __device__ __forceinline__ void strided_pass(cplx<T> *sm, unsigned t, unsigned j, bool valid, cplx<T> *gout, long long ostride,
-                                             const cplx<T> *tw, T scale, bool do_scale){
+                                             const cplx<T> *tw, T scale, bool do_scale, scatter_ctx const &sc){
     constexpr unsigned R = RL::radix(S);
     constexpr unsigned ST = RL::stride(S);         // distance between butterfly legs
     constexpr unsigned NB = RL::N / R;             // butterflies per line
@@ -251,21 +286,31 @@ __device__ __forceinline__ void strided_pass(cplx<T> *sm, unsigned t, unsigned j
         }else{
             if (valid){
                 // last pass: ST == 1, p = q*R + r, so the natural index is k(q*R) + r * N/R
-                cplx<T> *dst = gout + static_cast<long long>(dif_output_index<RL>(p0)) * ostride;
-                const long long hop = static_cast<long long>(RL::N / R) * ostride;
-                #pragma unroll
-                for(unsigned r=0; r<R; r++){
-                    cplx<T> x = BWD ? cswap(v[r]) : v[r];
-                    if (do_scale){ x.x *= scale; x.y *= scale; }
-                    *dst = x;
-                    dst += hop;
+                const unsigned k0 = dif_output_index<RL>(p0);
+                if constexpr (SCATTER){
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++){
+                        cplx<T> x = BWD ? cswap(v[r]) : v[r];
+                        if (do_scale){ x.x *= scale; x.y *= scale; }
+                        *scatter_address<cplx<T>>(sc.map, sc.row, static_cast<int>(k0 + r * (RL::N / R)), sc.a, sc.b) = x;
+                    }
+                }else{
+                    cplx<T> *dst = gout + static_cast<long long>(k0) * ostride;
+                    const long long hop = static_cast<long long>(RL::N / R) * ostride;
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++){
+                        cplx<T> x = BWD ? cswap(v[r]) : v[r];
+                        if (do_scale){ x.x *= scale; x.y *= scale; }
+                        *dst = x;
+                        dst += hop;
+                    }
                 }
             }
         }
     }
 }
 
-template<typename T, typename RL, int TPL, int LPB, int MINB, bool BWD>
+template<typename T, typename RL, int TPL, int LPB, int MINB, bool BWD, bool SCATTER>
 __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a){
     B200_DYN_SMEM(smem_raw);
     cplx<T> *sm = reinterpret_cast<cplx<T>*>(smem_raw);
@@ -288,22 +333,33 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a
             dst += TPL * LPB;
         }
     }
-    cplx<T> *gout = reinterpret_cast<cplx<T>*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, line) : 0);
+    cplx<T> *gout = nullptr;
+    scatter_ctx sc{nullptr, 0, 0, 0};
+    if constexpr (SCATTER){
+        scatter_map *smap = reinterpret_cast<scatter_map*>(sm + static_cast<size_t>(RL::N) * LPB);   // behind the tile
+        scatter_stage(smap, a.smap);
+        sc.map = smap;
+        sc.b = static_cast<int>(line / static_cast<unsigned>(a.count_a));
+        sc.a = static_cast<int>(line - static_cast<unsigned>(sc.b) * static_cast<unsigned>(a.count_a));
+    }else{
+        gout = reinterpret_cast<cplx<T>*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, line) : 0);
+    }
     async_wait_all();
     __syncthreads();
+    if constexpr (SCATTER) sc.row = valid ? scatter_row(sc.map, sc.a, sc.b) : 0;
 
-    strided_pass<T, RL, 0, TPL, LPB, BWD>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale);
+    strided_pass<T, RL, 0, TPL, LPB, BWD, SCATTER>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale, sc);
     if constexpr (P > 1){
         __syncthreads();
-        strided_pass<T, RL, 1, TPL, LPB, BWD>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale);
+        strided_pass<T, RL, 1, TPL, LPB, BWD, SCATTER>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale, sc);
     }
     if constexpr (P > 2){
         __syncthreads();
-        strided_pass<T, RL, 2, TPL, LPB, BWD>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale);
+        strided_pass<T, RL, 2, TPL, LPB, BWD, SCATTER>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale, sc);
     }
     if constexpr (P > 3){
         __syncthreads();
-        strided_pass<T, RL, 3, TPL, LPB, BWD>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale);
+        strided_pass<T, RL, 3, TPL, LPB, BWD, SCATTER>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale, sc);
     }
 }
 
@@ -314,9 +370,10 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a
 // ---------------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr unsigned pad_index(unsigned i){ return i + (i >> 3); }
 
-template<typename T, typename RL, int S, int NS, int TPL, bool BWD>
+template<typename T, typename RL, int S, int NS, int TPL, bool BWD, bool SCATTER>
 __device__ __forceinline__ void contig_pass(cplx<T> *row, unsigned j, bool valid, const cplx<T> *gin, cplx<T> *gout,
-                                            long long istride, long long ostride, const cplx<T> *tw, T scale, bool do_scale){
+                                            long long istride, long long ostride, const cplx<T> *tw, T scale, bool do_scale,
+                                            scatter_ctx const &sc){
     constexpr unsigned R = RL::radix(S);
     constexpr unsigned NB = RL::N / R;
     constexpr unsigned BPT = NB / TPL;              // butterflies per thread in this pass
@@ -357,21 +414,30 @@ __device__ __forceinline__ void contig_pass(cplx<T> *row, unsigned j, bool valid
             for(unsigned r=0; r<R; r++) row[pad_index(o + r * NS)] = v[u][r];
         }else{
             if (valid){
-                cplx<T> *dst = gout + static_cast<long long>(o) * ostride;
-                const long long hop = static_cast<long long>(NS) * ostride;
-                #pragma unroll
-                for(unsigned r=0; r<R; r++){
-                    cplx<T> x = BWD ? cswap(v[u][r]) : v[u][r];
-                    if (do_scale){ x.x *= scale; x.y *= scale; }
-                    *dst = x;
-                    dst += hop;
+                if constexpr (SCATTER){
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++){
+                        cplx<T> x = BWD ? cswap(v[u][r]) : v[u][r];
+                        if (do_scale){ x.x *= scale; x.y *= scale; }
+                        *scatter_address<cplx<T>>(sc.map, sc.row, static_cast<int>(o + r * NS), sc.a, sc.b) = x;
+                    }
+                }else{
+                    cplx<T> *dst = gout + static_cast<long long>(o) * ostride;
+                    const long long hop = static_cast<long long>(NS) * ostride;
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++){
+                        cplx<T> x = BWD ? cswap(v[u][r]) : v[u][r];
+                        if (do_scale){ x.x *= scale; x.y *= scale; }
+                        *dst = x;
+                        dst += hop;
+                    }
                 }
             }
         }
     }
 }
 
-template<typename T, typename RL, int LPB, int MINB, bool BWD>
+template<typename T, typename RL, int LPB, int MINB, bool BWD, bool SCATTER>
 __global__ void __launch_bounds__((RL::N / RL::rmax) * LPB, MINB) fft_contig_kernel(fft_args a){
     B200_DYN_SMEM(smem_raw);
     constexpr int TPL = RL::N / RL::rmax;
@@ -381,25 +447,37 @@ __global__ void __launch_bounds__((RL::N / RL::rmax) * LPB, MINB) fft_contig_ker
     const unsigned line = blockIdx.x * LPB + t;
     const bool valid = line < a.nlines;
     const cplx<T> *gin = reinterpret_cast<const cplx<T>*>(a.in) + (valid ? tile_line_offset(a.ig, a.count_a, line) : 0);
-    cplx<T> *gout = reinterpret_cast<cplx<T>*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, line) : 0);
+    cplx<T> *gout = nullptr;
+    scatter_ctx sc{nullptr, 0, 0, 0};
+    if constexpr (SCATTER){
+        scatter_map *smap = reinterpret_cast<scatter_map*>(smem_raw + ((sizeof(cplx<T>) * PITCH * LPB + 15) / 16) * 16);
+        scatter_stage(smap, a.smap);
+        __syncthreads();
+        sc.map = smap;
+        sc.b = static_cast<int>(line / static_cast<unsigned>(a.count_a));
+        sc.a = static_cast<int>(line - static_cast<unsigned>(sc.b) * static_cast<unsigned>(a.count_a));
+        sc.row = valid ? scatter_row(smap, sc.a, sc.b) : 0;
+    }else{
+        gout = reinterpret_cast<cplx<T>*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, line) : 0);
+    }
     const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
     const T scale = static_cast<T>(a.scale);
     const bool do_scale = a.scale != 1.0;
     constexpr int P = RL::passes;
     constexpr int N1 = RL::radix(0), N2 = N1 * RL::radix(1), N3 = N2 * RL::radix(2);
 
-    contig_pass<T, RL, 0, 1, TPL, BWD>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale);
+    contig_pass<T, RL, 0, 1, TPL, BWD, SCATTER>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale, sc);
     if constexpr (P > 1){
         __syncthreads();
-        contig_pass<T, RL, 1, N1, TPL, BWD>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale);
+        contig_pass<T, RL, 1, N1, TPL, BWD, SCATTER>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale, sc);
     }
     if constexpr (P > 2){
         __syncthreads();
-        contig_pass<T, RL, 2, N2, TPL, BWD>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale);
+        contig_pass<T, RL, 2, N2, TPL, BWD, SCATTER>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale, sc);
     }
     if constexpr (P > 3){
         __syncthreads();
-        contig_pass<T, RL, 3, N3, TPL, BWD>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale);
+        contig_pass<T, RL, 3, N3, TPL, BWD, SCATTER>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale, sc);
     }
 }
 
@@ -435,6 +513,7 @@ struct generic_args {
     int lines_fast;          // 1: thread index runs across lines first (neighbour lines adjacent in memory)
     int nfactors;
     int factors[24];
+    const scatter_map *smap;   // device pointer or null: fused reshape on the store side (read from global memory, L1-resident)
 };
 
 template<typename T>
@@ -568,46 +647,59 @@ __global__ void fft_generic_kernel(generic_args a){
         if (a.lines_fast){ t = idx % lpb; i = idx / lpb; } else { i = idx % nout; t = idx / nout; }
         long long line = line0 + t;
         if (line >= a.nlines) continue;
-        long long off = line_offset(a.og, a.count_a, line);
         const cplx<T> *res = src + t * m;
+        // destination of element i of this line: plain strided output, or the fused reshape
+        void *where;
+        {
+            const bool complex_out = (a.mode == mode_c2c || a.mode == mode_r2c);
+            if (a.smap != nullptr){
+                const int lb = static_cast<int>(line / a.count_a), la = static_cast<int>(line - static_cast<long long>(lb) * a.count_a);
+                const int row = scatter_row(a.smap, la, lb);
+                where = complex_out ? static_cast<void*>(scatter_address<cplx<T>>(a.smap, row, i, la, lb))
+                                    : static_cast<void*>(scatter_address<T>(a.smap, row, i, la, lb));
+            }else{
+                const long long pos = line_offset(a.og, a.count_a, line) + (long long)i * a.og.stride;
+                where = complex_out ? static_cast<void*>(reinterpret_cast<cplx<T>*>(a.out) + pos) : static_cast<void*>(reinterpret_cast<T*>(a.out) + pos);
+            }
+        }
         switch(a.mode){
             case mode_c2c: {
                 cplx<T> x = res[i];
                 if (a.backward) x = cswap(x);
                 x.x *= scale; x.y *= scale;
-                reinterpret_cast<cplx<T>*>(a.out)[off + (long long)i * a.og.stride] = x;
+                *static_cast<cplx<T>*>(where) = x;
             } break;
             case mode_r2c: {
                 cplx<T> x = res[i];
                 x.x *= scale; x.y *= scale;
-                reinterpret_cast<cplx<T>*>(a.out)[off + (long long)i * a.og.stride] = x;
+                *static_cast<cplx<T>*>(where) = x;
             } break;
             case mode_c2r: {
                 // engine ran forward on swapped input: result = swap(ifft); real part sits in .y
-                reinterpret_cast<T*>(a.out)[off + (long long)i * a.og.stride] = res[i].y * scale;
+                *static_cast<T*>(where) = res[i].y * scale;
             } break;
             case mode_dct2: {
                 // y_k = 2 Re( e^{-i pi k / 2n} V_k ),  e^{-i pi k/2n} = W_{4n}^k
                 cplx<T> w = ldg_c<T>(tw + m + i);
                 cplx<T> z = cmul(res[i], w);
-                reinterpret_cast<T*>(a.out)[off + (long long)i * a.og.stride] = T(2) * z.x * scale;
+                *static_cast<T*>(where) = T(2) * z.x * scale;
             } break;
             case mode_dst2: {
                 cplx<T> w = ldg_c<T>(tw + m + (n - 1 - i));
                 cplx<T> z = cmul(res[n - 1 - i], w);
-                reinterpret_cast<T*>(a.out)[off + (long long)i * a.og.stride] = T(2) * z.x * scale;
+                *static_cast<T*>(where) = T(2) * z.x * scale;
             } break;
             case mode_dct3: case mode_dst3: {
                 // v = ifft(V) * n is in res (swapped: real part in .y); x_{2i} = v_i, x_{2i+1} = v_{n-1-i}
                 int srcpos = (i & 1) ? (n - 1 - (i >> 1)) : (i >> 1);
                 T v = res[srcpos].y * T(2);
                 if (a.mode == mode_dst3 && (i & 1)) v = -v;
-                reinterpret_cast<T*>(a.out)[off + (long long)i * a.og.stride] = v * scale;
+                *static_cast<T*>(where) = v * scale;
             } break;
             case mode_dct1: {
                 T v = res[i].x;
                 if (a.backward) v *= T(2);
-                reinterpret_cast<T*>(a.out)[off + (long long)i * a.og.stride] = v * scale;
+                *static_cast<T*>(where) = v * scale;
             } break;
         }
     }

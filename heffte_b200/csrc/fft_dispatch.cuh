@@ -16,53 +16,53 @@ constexpr bool is_pow2(long long n){ return n > 0 && (n & (n - 1)) == 0; }
 constexpr int pow2_max = 4096;
 constexpr int pow2_min = 16;
 
-template<typename T, typename RL, int TPL, int LPB, int MINB, typename Launcher>
+template<typename T, typename RL, int TPL, int LPB, int MINB, bool SCATTER, typename Launcher>
 int launch_strided(fft_args const &a, Launcher &L){
     long long blocks = (a.nlines + LPB - 1) / LPB;
-    size_t smem = sizeof(cplx<T>) * (size_t)RL::N * LPB;
-    if (a.backward) return L.launch(fft_strided_kernel<T, RL, TPL, LPB, MINB, true>, blocks, TPL * LPB, smem, a);
-    return L.launch(fft_strided_kernel<T, RL, TPL, LPB, MINB, false>, blocks, TPL * LPB, smem, a);
+    size_t smem = sizeof(cplx<T>) * (size_t)RL::N * LPB + (SCATTER ? sizeof(scatter_map) : 0);
+    if (a.backward) return L.launch(fft_strided_kernel<T, RL, TPL, LPB, MINB, true, SCATTER>, blocks, TPL * LPB, smem, a);
+    return L.launch(fft_strided_kernel<T, RL, TPL, LPB, MINB, false, SCATTER>, blocks, TPL * LPB, smem, a);
 }
-template<typename T, typename RL, int LPB, int MINB, typename Launcher>
+template<typename T, typename RL, int LPB, int MINB, bool SCATTER, typename Launcher>
 int launch_contig(fft_args const &a, Launcher &L){
     long long blocks = (a.nlines + LPB - 1) / LPB;
     constexpr int PITCH = pad_index(RL::N) + 1;
-    size_t smem = sizeof(cplx<T>) * (size_t)PITCH * LPB;
-    if (a.backward) return L.launch(fft_contig_kernel<T, RL, LPB, MINB, true>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
-    return L.launch(fft_contig_kernel<T, RL, LPB, MINB, false>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
+    size_t smem = ((sizeof(cplx<T>) * (size_t)PITCH * LPB + 15) / 16) * 16 + (SCATTER ? sizeof(scatter_map) : 0);
+    if (a.backward) return L.launch(fft_contig_kernel<T, RL, LPB, MINB, true, SCATTER>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
+    return L.launch(fft_contig_kernel<T, RL, LPB, MINB, false, SCATTER>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
 }
 
 // M = lines-per-row multiplier: 1 for double (8 lines = 128 B), 2 for float (16 lines = 128 B)
-template<typename T, typename Launcher>
+template<typename T, bool SCATTER, typename Launcher>
 int dispatch_strided(int n, fft_args const &a, Launcher &L){
     constexpr int M = row_lines<T>::value / 8;
     switch(n){
-        case 16:   return launch_strided<T, radix_list<4, 4, 1, 1>,   4 / M, 32 * M, 2>(a, L);
-        case 32:   return launch_strided<T, radix_list<8, 4, 1, 1>,   4 / M, 32 * M, 2>(a, L);
-        case 64:   return launch_strided<T, radix_list<8, 8, 1, 1>,   8 / M, 16 * M, 2>(a, L);
-        case 128:  return launch_strided<T, radix_list<8, 4, 4, 1>,  16 / M,  8 * M, 2>(a, L);
-        case 256:  return launch_strided<T, radix_list<8, 8, 4, 1>,  32 / M,  8 * M, 2>(a, L);
-        case 512:  return launch_strided<T, radix_list<8, 8, 8, 1>,  32 / M,  8 * M, 3>(a, L);
-        case 1024: return launch_strided<T, radix_list<16, 8, 8, 1>, 32 / M,  8 * M, 1>(a, L);
-        case 2048: return launch_strided<T, radix_list<8, 8, 8, 4>, 128 / M,  4 * M, 1>(a, L);
-        case 4096: return launch_strided<T, radix_list<8, 8, 8, 8>, 256 / M,  2 * M, 1>(a, L);
+        case 16:   return launch_strided<T, radix_list<4, 4, 1, 1>,   4 / M, 32 * M, 2, SCATTER>(a, L);
+        case 32:   return launch_strided<T, radix_list<8, 4, 1, 1>,   4 / M, 32 * M, 2, SCATTER>(a, L);
+        case 64:   return launch_strided<T, radix_list<8, 8, 1, 1>,   8 / M, 16 * M, 2, SCATTER>(a, L);
+        case 128:  return launch_strided<T, radix_list<8, 4, 4, 1>,  16 / M,  8 * M, 2, SCATTER>(a, L);
+        case 256:  return launch_strided<T, radix_list<8, 8, 4, 1>,  32 / M,  8 * M, 2, SCATTER>(a, L);
+        case 512:  return launch_strided<T, radix_list<8, 8, 8, 1>,  32 / M,  8 * M, 3, SCATTER>(a, L);
+        case 1024: return launch_strided<T, radix_list<16, 8, 8, 1>, 32 / M,  8 * M, 1, SCATTER>(a, L);
+        case 2048: return launch_strided<T, radix_list<8, 8, 8, 4>, 128 / M,  4 * M, 1, SCATTER>(a, L);
+        case 4096: return launch_strided<T, radix_list<8, 8, 8, 8>, 256 / M,  2 * M, 1, SCATTER>(a, L);
         default: return -1;
     }
 }
 
-template<typename T, typename Launcher>
+template<typename T, bool SCATTER, typename Launcher>
 int dispatch_contig(int n, fft_args const &a, Launcher &L){
     // small CTAs (64-128 threads), many per SM: measured best on B200 (tools/kbench.cu, profiles/)
     switch(n){
-        case 16:   return launch_contig<T, radix_list<4, 4, 1, 1>,   32, 8>(a, L);
-        case 32:   return launch_contig<T, radix_list<8, 4, 1, 1>,   32, 6>(a, L);
-        case 64:   return launch_contig<T, radix_list<8, 8, 1, 1>,   16, 6>(a, L);
-        case 128:  return launch_contig<T, radix_list<8, 4, 4, 1>,    8, 6>(a, L);
-        case 256:  return launch_contig<T, radix_list<8, 8, 4, 1>,    4, 6>(a, L);
-        case 512:  return launch_contig<T, radix_list<8, 8, 8, 1>,    1, 12>(a, L);
-        case 1024: return launch_contig<T, radix_list<16, 8, 8, 1>,   1, 4>(a, L);
-        case 2048: return launch_contig<T, radix_list<8, 8, 8, 4>,    1, 2>(a, L);
-        case 4096: return launch_contig<T, radix_list<8, 8, 8, 8>,    1, 1>(a, L);
+        case 16:   return launch_contig<T, radix_list<4, 4, 1, 1>,   32, 8, SCATTER>(a, L);
+        case 32:   return launch_contig<T, radix_list<8, 4, 1, 1>,   32, 6, SCATTER>(a, L);
+        case 64:   return launch_contig<T, radix_list<8, 8, 1, 1>,   16, 6, SCATTER>(a, L);
+        case 128:  return launch_contig<T, radix_list<8, 4, 4, 1>,    8, 6, SCATTER>(a, L);
+        case 256:  return launch_contig<T, radix_list<8, 8, 4, 1>,    4, 6, SCATTER>(a, L);
+        case 512:  return launch_contig<T, radix_list<8, 8, 8, 1>,    1, 12, SCATTER>(a, L);
+        case 1024: return launch_contig<T, radix_list<16, 8, 8, 1>,   1, 4, SCATTER>(a, L);
+        case 2048: return launch_contig<T, radix_list<8, 8, 8, 4>,    1, 2, SCATTER>(a, L);
+        case 4096: return launch_contig<T, radix_list<8, 8, 8, 8>,    1, 1, SCATTER>(a, L);
         default: return -1;
     }
 }

@@ -102,8 +102,10 @@ inline int make_host_plan(b200_fft1d_desc const &desc, host_plan &plan, const ch
 inline line_geom to_geom(b200_line_geom const &g){ return line_geom{g.stride, g.stride_a, g.stride_b}; }
 
 // runs the plan through a Launcher (CUDA stream launcher in the product, thread emulation in tests/emul)
+// `scatter` (device pointer to a scatter_map, or null) fuses the following reshape into the store of the transform
 template<typename Launcher>
-int run_host_plan(host_plan const &plan, const void *twiddle, int direction, const void *in, void *out, double scale, Launcher &L){
+int run_host_plan(host_plan const &plan, const void *twiddle, int direction, const void *in, void *out, double scale, Launcher &L,
+                  const void *scatter = nullptr){
     b200_fft1d_desc const &d = plan.desc;
     long long const nlines = d.count_a * d.count_b;
     if (nlines == 0) return B200_SUCCESS;
@@ -119,9 +121,8 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
         a.count_a = static_cast<int>(d.count_a);
         a.backward = backward ? 1 : 0;
         a.scale = scale;
-        if (plan.family == family_strided)
-            return is_float ? dispatch_strided<float>(static_cast<int>(d.n), a, L) : dispatch_strided<double>(static_cast<int>(d.n), a, L);
-        return is_float ? dispatch_contig<float>(static_cast<int>(d.n), a, L) : dispatch_contig<double>(static_cast<int>(d.n), a, L);
+        a.smap = static_cast<const scatter_map*>(scatter);
+        return L.run_pow2(plan.family == family_strided, is_float, scatter != nullptr, static_cast<int>(d.n), a);
     }
 
     generic_args g;
@@ -137,6 +138,7 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
     g.lpb = plan.lpb;
     g.lines_fast = plan.lines_fast;
     g.nfactors = plan.nfactors;
+    g.smap = static_cast<const scatter_map*>(scatter);
     for(int i=0; i<24; i++) g.factors[i] = (i < plan.nfactors) ? plan.factors[i] : 1;
     switch(d.kind){
         case B200_C2C:  g.mode = mode_c2c; break;
@@ -146,8 +148,7 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
         default:        g.mode = mode_dct1; break;
     }
     long long const blocks = (nlines + plan.lpb - 1) / plan.lpb;
-    if (is_float) return L.launch(fft_generic_kernel<float>, blocks, plan.threads, plan.smem, g);
-    return L.launch(fft_generic_kernel<double>, blocks, plan.threads, plan.smem, g);
+    return L.run_generic(is_float, blocks, plan.threads, plan.smem, g);
 }
 
 } // namespace b200

@@ -42,6 +42,30 @@ int b200_transpose_unpack(int elem_bytes, long long nfast, long long nmid, long 
     return rc;
 }
 
+int b200_scatter_copy(int elem_bytes, long long nfast, long long nmid, long long nslow, long long line_stride, long long plane_stride,
+                      const void *src, const void *device_scatter_map, void *stream){
+    if (device_scatter_map == nullptr) return fail(B200_ERR_INVALID, "null scatter map");
+    if (nfast > 2147483647LL or nmid > 2147483647LL or nslow > 2147483647LL) return fail(B200_ERR_UNSUPPORTED, "box too large");
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    scatter_copy_args a{src, static_cast<const scatter_map*>(device_scatter_map), (int) nfast, (int) nmid, (int) nslow, line_stride, plane_stride, 1};
+    int rc = launch_scatter_copy(elem_bytes, a, L);
+    return (rc == B200_ERR_INVALID) ? fail(rc, "element size must be 4, 8 or 16 bytes") : rc;
+}
+
+int b200_peer_barrier(int nranks, int me, void *const *remote_slots, void *local_flags, unsigned long long epoch, void *stream){
+    if (nranks < 1 or nranks > barrier_max_ranks or me < 0 or me >= nranks) return fail(B200_ERR_INVALID, "bad rank count for the peer barrier");
+    peer_barrier_args a{};
+    for(int p=0; p<nranks; p++) a.remote[p] = static_cast<unsigned long long*>(remote_slots[p]);
+    a.local = static_cast<unsigned long long*>(local_flags);
+    a.epoch = epoch; a.nranks = nranks; a.me = me;
+#ifdef B200_HOST_EMULATION
+    return B200_SUCCESS;   // tests/emul: streams are synchronous and the thread-ranks rendezvous in after_peer_barrier()
+#else
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    return L.launch(peer_barrier_kernel, 1, barrier_max_ranks, 0, a);
+#endif
+}
+
 int b200_scale(int precision, long long count, void *data, double factor, void *stream){
     cuda_launcher L{static_cast<cudaStream_t>(stream)};
     return launch_scale(precision, count, data, factor, L);

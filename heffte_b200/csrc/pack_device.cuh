@@ -6,8 +6,79 @@
 #pragma once
 
 #include "cuda_compat.h"
+#include "fft_device.cuh"
 
 namespace b200 {
+
+// ---------------------------------------------------------------------------------------------------------
+// scatter copy: the first reshape of a transform (user box -> the boxes of the first FFT stage) written straight into
+// the destination boxes, local or on a peer GPU over NVLink.  One pass: no send buffer, no receive buffer, no unpack.
+// Coordinates of the map: k = fast index of my box, a = mid, b = slow.
+// ---------------------------------------------------------------------------------------------------------
+struct scatter_copy_args {
+    const void *src;
+    const scatter_map *smap;     // device pointer
+    int nfast, nmid, nslow;
+    long long line, plane;       // strides of my box
+    int tf;                      // threads along the fast axis (power of two <= 256)
+};
+
+template<typename V>
+__global__ void __launch_bounds__(256) scatter_copy_kernel(scatter_copy_args a){
+    B200_DYN_SMEM(map_raw);
+    scatter_map *smap = reinterpret_cast<scatter_map*>(map_raw);
+    scatter_stage(smap, a.smap);
+    __syncthreads();
+    const V *src = reinterpret_cast<const V*>(a.src);
+    const int tx = threadIdx.x & (a.tf - 1), ty = threadIdx.x / a.tf;
+    const int rows = blockDim.x / a.tf;                         // lines handled side by side by one CTA
+    const long long nlines = static_cast<long long>(a.nmid) * a.nslow;
+    for(long long line = static_cast<long long>(blockIdx.x) * rows + ty; line < nlines; line += static_cast<long long>(gridDim.x) * rows){
+        const int s = static_cast<int>(line / a.nmid), m = static_cast<int>(line - static_cast<long long>(s) * a.nmid);
+        const int row = scatter_row(smap, m, s);
+        const V *from = src + s * a.plane + m * a.line;
+        int f = tx;
+        // four independent loads in flight per thread
+        for(; f + 3 * a.tf < a.nfast; f += 4 * a.tf){
+            V v0 = from[f], v1 = from[f + a.tf], v2 = from[f + 2 * a.tf], v3 = from[f + 3 * a.tf];
+            *scatter_address<V>(smap, row, f, m, s) = v0;
+            *scatter_address<V>(smap, row, f + a.tf, m, s) = v1;
+            *scatter_address<V>(smap, row, f + 2 * a.tf, m, s) = v2;
+            *scatter_address<V>(smap, row, f + 3 * a.tf, m, s) = v3;
+        }
+        for(; f < a.nfast; f += a.tf) *scatter_address<V>(smap, row, f, m, s) = from[f];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// barrier between the GPUs of a plan, stream ordered: rank r publishes `epoch` into slot r of every peer's flag array
+// (peer memory, NVLink) and waits until every peer has published it into this rank's array.  All data written by the
+// kernels enqueued before the barrier is visible to the peers once they pass it.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int barrier_max_ranks = 64;
+struct peer_barrier_args {
+    unsigned long long *remote[barrier_max_ranks];   // remote[p]: address of slot `me` in the flag array of rank p
+    unsigned long long *local;                       // my flag array (slot p is written by rank p)
+    unsigned long long epoch;
+    int nranks, me;
+};
+
+#ifndef B200_HOST_EMULATION
+__global__ void __launch_bounds__(barrier_max_ranks) peer_barrier_kernel(peer_barrier_args a){
+    const int p = threadIdx.x;
+    if (p >= a.nranks || p == a.me) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(a.remote[p]), "l"(a.epoch) : "memory");
+    unsigned long long seen = 0, start, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
+    for(;;){
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.local + p) : "memory");
+        if (seen >= a.epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - start > 20000000000ULL) __trap();     // 20 s: a peer died; fail instead of hanging the GPU
+    }
+}
+#endif
 
 struct copy3d_args {
     const void *src;

@@ -29,6 +29,24 @@ int launch_copy3d(int elem_bytes, copy3d_args const &a, Launcher &L){
     }
 }
 
+template<typename Launcher>
+int launch_scatter_copy(int elem_bytes, scatter_copy_args a, Launcher &L){
+    long long const nlines = static_cast<long long>(a.nmid) * a.nslow;
+    if (nlines <= 0 or a.nfast <= 0) return B200_SUCCESS;
+    int tf = 1;
+    while(tf < a.nfast and tf < 256) tf *= 2;
+    a.tf = tf;
+    long long const rows = 256 / tf;
+    long long const blocks = std::max<long long>(1, std::min<long long>((nlines + rows - 1) / rows, (long long)num_sms * 16));
+    size_t const smem = sizeof(scatter_map);
+    switch(elem_bytes){
+        case 4:  return L.launch(scatter_copy_kernel<float>,   blocks, 256, smem, a);
+        case 8:  return L.launch(scatter_copy_kernel<double>,  blocks, 256, smem, a);
+        case 16: return L.launch(scatter_copy_kernel<double2>, blocks, 256, smem, a);
+        default: return B200_ERR_INVALID;
+    }
+}
+
 // general permuting copy: dst[f + m*dl + s*dp] = src[f*ss0 + m*ss1 + s*ss2]
 template<typename Launcher>
 int launch_permute(int elem_bytes, permute_args a, Launcher &L){

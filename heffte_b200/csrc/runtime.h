@@ -2,7 +2,7 @@
 // error reporting for the C ABI, the launch counter and the CUDA launcher policy.
 #pragma once
 
-#include <cuda_runtime.h>
+#include "cuda_compat.h"
 
 #include <atomic>
 #include <mutex>
@@ -10,6 +10,7 @@
 #include <unordered_set>
 
 #include "../../include/heffte_b200_kernels.h"
+#include "fft_device.cuh"
 
 namespace b200 {
 
@@ -27,16 +28,27 @@ struct cuda_launcher {
     int launch(kernel_t kernel, long long blocks, int threads, size_t smem, args_t const &args){
         if (blocks <= 0) return B200_SUCCESS;
         if (blocks > 2147483647LL) return fail(B200_ERR_UNSUPPORTED, "grid too large");
+#ifdef B200_HOST_EMULATION
+        emul::launch(kernel, dim3(static_cast<unsigned>(blocks)), dim3(static_cast<unsigned>(threads)), smem, args);   // tests/emul only
+#else
         if (smem > 48 * 1024) allow_smem(reinterpret_cast<const void*>(kernel), smem);
         kernel<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(args);
+#endif
         launch_counter.fetch_add(1, std::memory_order_relaxed);
         return check_cuda(cudaPeekAtLastError(), "kernel launch");
     }
+    // kernel selection of the batched FFT (fft_host_plan.h): the instantiations live in the fft_inst_*.cu slices
+    int run_pow2(bool strided, bool is_float, bool scatter, int n, fft_args const &a);
+    int run_generic(bool is_float, long long blocks, int threads, size_t smem, generic_args const &g);
     template<typename kernel_t, typename args_t>
     int launch3(kernel_t kernel, long long gx, long long gy, long long gz, int threads, size_t smem, args_t const &args){
         if (gx <= 0 or gy <= 0 or gz <= 0) return B200_SUCCESS;
         if (gx > 2147483647LL or gy > 65535 or gz > 65535) return fail(B200_ERR_UNSUPPORTED, "grid too large");
+#ifdef B200_HOST_EMULATION
+        emul::launch(kernel, dim3((unsigned) gx, (unsigned) gy, (unsigned) gz), dim3(static_cast<unsigned>(threads)), smem, args);
+#else
         kernel<<<dim3((unsigned) gx, (unsigned) gy, (unsigned) gz), threads, smem, stream>>>(args);
+#endif
         launch_counter.fetch_add(1, std::memory_order_relaxed);
         return check_cuda(cudaPeekAtLastError(), "kernel launch");
     }

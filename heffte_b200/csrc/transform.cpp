@@ -1,7 +1,11 @@
 #include "transform.h"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+
+#include "scatter_build.h"
 
 namespace b200 {
 
@@ -14,18 +18,18 @@ namespace {
 inline char* advance(void *p, idx elements, int elem_bytes){ return static_cast<char*>(p) + elements * elem_bytes; }
 inline const char* advance(const void *p, idx elements, int elem_bytes){ return static_cast<const char*>(p) + elements * elem_bytes; }
 
-// geometry of the batch of lines of `box` that run along `dim`
+// geometry of the batch of lines of `box` that run along `dim`.  The two other axes are kept apart
+// (a = the faster one, b = the slower one) so that a line knows its box coordinates: the fused reshape needs them.
 void line_layout(box3 const &box, int dim, b200_line_geom &g, long long &count_a, long long &count_b){
-    if (dim == box.order[0]){
-        g.stride = 1; g.stride_a = box.osize(0); g.stride_b = 0;
-        count_a = box.osize(1) * box.osize(2); count_b = 1;
-    }else if (dim == box.order[1]){
-        g.stride = box.osize(0); g.stride_a = 1; g.stride_b = box.osize(0) * box.osize(1);
-        count_a = box.osize(0); count_b = box.osize(2);
-    }else{
-        g.stride = box.osize(0) * box.osize(1); g.stride_a = 1; g.stride_b = 0;
-        count_a = box.osize(0) * box.osize(1); count_b = 1;
-    }
+    idx const strides[3] = {1, box.osize(0), box.osize(0) * box.osize(1)};
+    int const pos = box.position_of(dim);
+    int const a_pos = (pos == 0) ? 1 : 0, b_pos = (pos == 2) ? 1 : 2;
+    g.stride = strides[pos]; g.stride_a = strides[a_pos]; g.stride_b = strides[b_pos];
+    count_a = box.osize(a_pos); count_b = box.osize(b_pos);
+}
+
+bool shapes_differ(shape const &a, shape const &b){
+    return not (extents_match(a, b) and a[0].same_order(b[0]));
 }
 
 } // namespace
@@ -124,7 +128,7 @@ int reshape_op::apply(int elem_bytes, const void *src, void *dst, void *workspac
     for(auto const &p : recvs)
         if (p.peer != me) incoming.push_back({p.peer, recv_buffer + p.buffer_offset * elem_bytes, static_cast<size_t>(p.count) * elem_bytes});
 
-    if (not outgoing.empty() or not incoming.empty()){
+    {   // collective over the ranks of the plan, also with nothing to send or receive
         int rc = comm->exchange(outgoing, incoming, stream);
         if (rc) return fail(B200_ERR_NCCL, "exchange failed in reshape");
     }
@@ -204,8 +208,199 @@ transform3d::transform3d(transform_kind kind, box3 const &inbox, box3 const &out
 }
 
 transform3d::~transform3d(){
+    for(int p=0; p<2; p++){
+        peer_state &P = peer[p];
+        if (P.arena){
+            cudaStreamSynchronize(cstream);
+            if (not P.arenas.empty()) ccomm->unmap_peers(P.arenas);
+            cudaFree(P.arena);
+        }
+        if (P.maps) cudaFree(P.maps);
+    }
     for(int p=0; p<2; p++) for(int i=0; i<3; i++) if (exec[p][i]) b200_fft1d_destroy(exec[p][i]);
     if (own_workspace) cudaFree(own_workspace);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// peer-memory mode
+// ------------------------------------------------------------------------------------------------------------
+// Collective over the ranks of the plan (first transform of each precision): allocate and peer-map the arena, build the
+// scatter maps of every stage.  Any rank failing any step makes every rank fall back to the exchange() path.
+bool transform3d::ensure_peer(int precision){
+    peer_state &P = peer[precision];
+    if (P.tried) return P.active;
+    P.tried = true;
+    int const n = ccomm->size();
+    if (n < 2 or n > 64) return false;
+    int const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
+    int const cplx_bytes = 2 * real_bytes;
+    bool const complex_data = (tkind == kind_c2c or tkind == kind_r2c);
+    bool any = false;
+    for(int s=0; s<4; s++){
+        P.fused[0][s] = shapes_differ(lp.in_shape[s], lp.out_shape[s]);
+        P.fused[1][s] = shapes_differ(lp.out_shape[3-s], lp.in_shape[3-s]);
+        any = any or P.fused[0][s];
+    }
+    if (not any) return false;
+
+    // a buffer holds the largest box this rank ever owns, in the widest element type of the plan
+    // (the same size on every rank: buffer 1 of a peer sits at a known offset inside its arena)
+    idx largest = 1;
+    for(int s=0; s<4; s++)
+        for(int r=0; r<n; r++) largest = std::max(largest, std::max(lp.in_shape[s][r].count(), lp.out_shape[s][r].count()));
+    P.buffer_bytes = ((static_cast<size_t>(largest) * (complex_data ? cplx_bytes : real_bytes) + 255) / 256) * 256;
+    size_t const arena_bytes = 4096 + 2 * P.buffer_bytes;
+    int ok = 1;
+    if (cudaMalloc(&P.arena, arena_bytes) != cudaSuccess){ P.arena = nullptr; cudaGetLastError(); ok = 0; }
+    if (ok and (cudaMemset(P.arena, 0, 4096) != cudaSuccess or cudaDeviceSynchronize() != cudaSuccess)) ok = 0;
+    // map_peers is collective: it is called by every rank even after a local failure (with a harmless null allocation vote)
+    std::vector<void*> arenas;
+    bool mapped = false;
+    {
+        std::vector<int> votes(n);
+        if (ccomm->allgather(&ok, votes.data(), sizeof(int)) != 0) ok = 0;
+        for(int v : votes) if (not v) ok = 0;
+        if (ok) mapped = ccomm->map_peers(P.arena, arena_bytes, arenas);
+    }
+    if (not mapped){
+        if (P.arena){ cudaFree(P.arena); P.arena = nullptr; }
+        return false;
+    }
+    P.arenas = arenas;
+    P.remote_slots.resize(n);
+    for(int r=0; r<n; r++) P.remote_slots[r] = static_cast<char*>(arenas[r]) + sizeof(unsigned long long) * me;
+
+    // scatter maps: ((direction * 4 + stage) * 2 + buffer)
+    std::vector<scatter_map> maps(16);
+    std::string why;
+    int built = 1;
+    for(int dir=0; dir<2 and built; dir++){
+        for(int st=0; st<4 and built; st++){
+            if (not P.fused[dir][st]) continue;
+            shape const &dest = (dir == 0) ? lp.out_shape[st] : lp.in_shape[3-st];
+            // the box this rank writes in that stage, the axis of the transform in front of the reshape, the element size
+            box3 written;
+            int k_pos = 0, bytes = complex_data ? cplx_bytes : real_bytes;
+            if (st == 0){
+                written = (dir == 0) ? lp.in_shape[0][me] : lp.out_shape[3][me];
+                if (tkind == kind_r2c and dir == 0) bytes = real_bytes;
+            }else{
+                int const e = (dir == 0) ? st - 1 : 3 - st;                 // executor in front of this reshape
+                written = (dir == 0) ? lp.in_shape[st][me] : lp.out_shape[3-st][me];
+                if (not written.empty()) k_pos = written.position_of(lp.fft_direction[e]);
+                if (tkind == kind_r2c and dir == 1 and e == 0) bytes = real_bytes;   // c2r output
+            }
+            for(int w=0; w<2; w++){
+                std::vector<void*> bases(n);
+                for(int r=0; r<n; r++) bases[r] = static_cast<char*>(arenas[r]) + 4096 + static_cast<size_t>(w) * P.buffer_bytes;
+                if (not build_scatter_map(written, k_pos, dest, bases, bytes, maps[(dir * 4 + st) * 2 + w], why)){ built = 0; break; }
+            }
+        }
+    }
+    if (built and cudaMalloc(&P.maps, maps.size() * sizeof(scatter_map)) != cudaSuccess){ P.maps = nullptr; cudaGetLastError(); built = 0; }
+    if (built and cudaMemcpy(P.maps, maps.data(), maps.size() * sizeof(scatter_map), cudaMemcpyHostToDevice) != cudaSuccess) built = 0;
+    {
+        std::vector<int> votes(n);
+        if (ccomm->allgather(&built, votes.data(), sizeof(int)) != 0) built = 0;
+        for(int v : votes) if (not v) built = 0;
+    }
+    if (not built){
+        ccomm->unmap_peers(P.arenas);
+        P.arenas.clear();
+        cudaFree(P.arena); P.arena = nullptr;
+        if (P.maps){ cudaFree(P.maps); P.maps = nullptr; }
+        return false;
+    }
+    P.active = true;
+    return true;
+}
+
+int transform3d::peer_fence(int precision){
+    peer_state &P = peer[precision];
+    P.epoch++;
+    if (std::getenv("HEFFTE_B200_TRACE")) std::fprintf(stderr, "[b200 rank %d] fence %llu\n", me, P.epoch);
+    int rc = b200_peer_barrier(ccomm->size(), me, P.remote_slots.data(), P.arena, P.epoch, cstream);
+    ccomm->after_peer_barrier();
+    return rc;
+}
+
+// One transform with every reshape fused into the store of the kernel in front of it.  Data alternates between the two
+// peer-mapped buffers; a fence follows every stage that writes into other ranks' memory.
+int transform3d::run_peer(int precision, bool is_backward, const void *in, void *out, double scale){
+    peer_state &P = peer[precision];
+    int const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
+    int const cplx_bytes = 2 * real_bytes;
+    bool const complex_data = (tkind == kind_c2c or tkind == kind_r2c);
+    int const dir = is_backward ? 1 : 0;
+    int const direction = is_backward ? B200_BACKWARD : B200_FORWARD;
+    b200_fft1d_plan const *X = exec[precision];
+    auto map_of = [&](int st, int w){ return static_cast<const char*>(P.maps) + sizeof(scatter_map) * static_cast<size_t>((dir * 4 + st) * 2 + w); };
+
+    int last_fft = -1;
+    for(int st=1; st<4; st++) if (X[is_backward ? 3 - st : st - 1]) last_fft = st;
+
+    // every peer has finished reading its buffers of the previous transform before anybody writes into them again
+    int rc = peer_fence(precision);
+    if (rc) return rc;
+    unsigned touched = 0;            // buffers read or written locally since the last fence
+
+    const void *cur = in;
+    int cur_buffer = -1;             // -1: caller memory
+    if (P.fused[dir][0]){
+        box3 const &box = is_backward ? lp.out_shape[3][me] : lp.in_shape[0][me];
+        int bytes = complex_data ? cplx_bytes : real_bytes;
+        if (tkind == kind_r2c and not is_backward) bytes = real_bytes;
+        if (not box.empty()){
+            rc = b200_scatter_copy(bytes, box.osize(0), box.osize(1), box.osize(2), box.osize(0), box.osize(0) * box.osize(1), cur, map_of(0, 0), cstream);
+            if (rc) return rc;
+        }
+        rc = peer_fence(precision);
+        if (rc) return rc;
+        cur_buffer = 0; cur = P.buffer(0);
+    }
+    for(int st=1; st<4; st++){
+        int const e = is_backward ? 3 - st : st - 1;
+        double const stage_scale = (st == last_fft) ? scale : 1.0;
+        bool const type_changes = (tkind == kind_r2c and e == 0);          // r2c / c2r cannot run in place
+        if (P.fused[dir][st]){
+            int const w = (cur_buffer < 0) ? 0 : (cur_buffer ^ 1);
+            if (touched & (1u << w)){ rc = peer_fence(precision); if (rc) return rc; touched = 0; }
+            if (X[e]){
+                rc = b200_fft1d_execute_scatter(X[e], direction, cur, map_of(st, w), stage_scale, cstream);
+                if (rc) return rc;
+            }
+            rc = peer_fence(precision);
+            if (rc) return rc;
+            touched = 0;
+            cur_buffer = w; cur = P.buffer(w);
+        }else{
+            bool later_fused = false;
+            for(int t=st+1; t<4; t++) later_fused = later_fused or P.fused[dir][t];
+            void *dst;
+            int dst_buffer;
+            // the caller's output can take the result once nothing moves any more -- except the complex intermediates of a
+            // complex-to-real transform, which do not fit the real output array
+            bool const fits_output = not (tkind == kind_r2c and is_backward and st < 3);
+            if (not later_fused and fits_output){ dst = out; dst_buffer = -1; }
+            else if (cur_buffer >= 0 and not type_changes){ dst = const_cast<void*>(cur); dst_buffer = cur_buffer; }
+            else{ dst_buffer = (cur_buffer < 0) ? 0 : (cur_buffer ^ 1); dst = P.buffer(dst_buffer); }
+            if (cur_buffer >= 0) touched |= 1u << cur_buffer;
+            if (dst_buffer >= 0) touched |= 1u << dst_buffer;
+            if (X[e]){
+                rc = b200_fft1d_execute(X[e], direction, cur, dst, stage_scale, cstream);
+                if (rc) return rc;
+            }
+            cur = dst; cur_buffer = dst_buffer;     // also without a transform (empty box): every rank follows the same buffers
+        }
+    }
+    if (cur != out){
+        idx const count = is_backward ? inbox_count : outbox_count;
+        bool const real_out = (tkind == kind_r2c and is_backward) or not complex_data;
+        size_t const bytes = static_cast<size_t>(count) * (real_out ? real_bytes : cplx_bytes);
+        if (count > 0 and cudaMemcpyAsync(out, cur, bytes, cudaMemcpyDeviceToDevice, cstream) != cudaSuccess)
+            return fail(B200_ERR_CUDA, "cudaMemcpyAsync failed");
+    }
+    return B200_SUCCESS;
 }
 
 double transform3d::scale_factor(int scaling) const {
@@ -253,7 +448,8 @@ int transform3d::forward(int precision, int batch, const void *in, void *out, vo
     if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
     int rc = ensure_executors(precision);
     if (rc) return rc;
-    if (workspace == nullptr){
+    bool const through_peers = ensure_peer(precision);
+    if (workspace == nullptr and not through_peers){
         workspace = ensure_workspace(precision, 1);
         if (workspace == nullptr) return fail(B200_ERR_CUDA, "cannot allocate the workspace");
     }
@@ -261,8 +457,9 @@ int transform3d::forward(int precision, int batch, const void *in, void *out, vo
     size_t const in_unit = (tkind == kind_c2c) ? 2 * real_bytes : real_bytes;
     size_t const out_unit = (tkind == kind_c2c or tkind == kind_r2c) ? 2 * real_bytes : real_bytes;
     for(int b=0; b<std::max(batch, 1); b++){
-        rc = run(precision, false, static_cast<const char*>(in) + b * inbox_count * in_unit,
-                 static_cast<char*>(out) + b * outbox_count * out_unit, workspace, scale_factor(scaling));
+        const char *src = static_cast<const char*>(in) + b * inbox_count * in_unit;
+        char *dst = static_cast<char*>(out) + b * outbox_count * out_unit;
+        rc = through_peers ? run_peer(precision, false, src, dst, scale_factor(scaling)) : run(precision, false, src, dst, workspace, scale_factor(scaling));
         if (rc) return rc;
     }
     return B200_SUCCESS;
@@ -272,7 +469,8 @@ int transform3d::backward(int precision, int batch, const void *in, void *out, v
     if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
     int rc = ensure_executors(precision);
     if (rc) return rc;
-    if (workspace == nullptr){
+    bool const through_peers = ensure_peer(precision);
+    if (workspace == nullptr and not through_peers){
         workspace = ensure_workspace(precision, 1);
         if (workspace == nullptr) return fail(B200_ERR_CUDA, "cannot allocate the workspace");
     }
@@ -280,8 +478,9 @@ int transform3d::backward(int precision, int batch, const void *in, void *out, v
     size_t const in_unit = (tkind == kind_c2c or tkind == kind_r2c) ? 2 * real_bytes : real_bytes;
     size_t const out_unit = (tkind == kind_c2c) ? 2 * real_bytes : real_bytes;
     for(int b=0; b<std::max(batch, 1); b++){
-        rc = run(precision, true, static_cast<const char*>(in) + b * outbox_count * in_unit,
-                 static_cast<char*>(out) + b * inbox_count * out_unit, workspace, scale_factor(scaling));
+        const char *src = static_cast<const char*>(in) + b * outbox_count * in_unit;
+        char *dst = static_cast<char*>(out) + b * inbox_count * out_unit;
+        rc = through_peers ? run_peer(precision, true, src, dst, scale_factor(scaling)) : run(precision, true, src, dst, workspace, scale_factor(scaling));
         if (rc) return rc;
     }
     return B200_SUCCESS;

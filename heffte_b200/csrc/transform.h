@@ -8,6 +8,7 @@
 
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "../../include/heffte_b200_kernels.h"
 #include "comm.h"
@@ -74,10 +75,31 @@ public:
     int forward(int precision, int batch, const void *in, void *out, void *workspace, int scaling);
     int backward(int precision, int batch, const void *in, void *out, void *workspace, int scaling);
 
+    // true once the plan runs its reshapes through peer memory (NVLink stores fused into the FFT kernels)
+    bool uses_peer_memory(int precision) const { return peer[precision].active; }
+
 private:
     int run(int precision, bool is_backward, const void *in, void *out, void *workspace, double scale);
+    int run_peer(int precision, bool is_backward, const void *in, void *out, double scale);
     int ensure_executors(int precision);
     void* ensure_workspace(int precision, int batch);
+    bool ensure_peer(int precision);
+    int peer_fence(int precision);
+
+    // ---- peer-memory mode: every reshape is fused into the store of the transform in front of it --------------------------
+    // (stage 0 = the first reshape, a scatter copy; stage s = 1..3: transform s-1 followed by reshape s)
+    struct peer_state {
+        bool tried = false, active = false;
+        void *arena = nullptr;                 // [flags | buffer 0 | buffer 1], peer-mapped on every rank of the plan
+        size_t buffer_bytes = 0;
+        std::vector<void*> arenas;             // address of every rank's arena as seen from this device
+        std::vector<void*> remote_slots;       // my slot in every rank's flag array
+        unsigned long long epoch = 0;
+        void *maps = nullptr;                  // device array of scatter maps, index ((direction * 4 + stage) * 2 + buffer)
+        bool fused[2][4] = {{false, false, false, false}, {false, false, false, false}};   // reshape of that stage moves data (global fact)
+        char* buffer(int index) const { return static_cast<char*>(arena) + 4096 + static_cast<size_t>(index) * buffer_bytes; }
+    };
+    peer_state peer[2];
 
     transform_kind tkind;
     int r2c_dir;

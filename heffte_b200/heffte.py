@@ -121,6 +121,18 @@ def comm_self():
     return communicator(handle)
 
 
+def comm_threads(size, devices=None):
+    """`size` ranks in this process, one host thread per rank (rank r on CUDA device devices[r], default all on device 0)."""
+    lib = _lib.load()
+    handles = (ctypes.c_void_p * size)()
+    dev = None
+    if devices is not None:
+        dev = (ctypes.c_int * size)(*[int(d) for d in devices])
+    if lib.heffte_comm_create_threads(size, dev, handles) != 0:
+        raise heffte_input_error(_lib.last_error())
+    return [communicator(ctypes.c_void_p(h)) for h in handles]
+
+
 def comm_from_torch(group=None, device=None):
     """One rank per GPU: share an NCCL unique id through torch.distributed, then build the NCCL communicator."""
     import torch
@@ -247,6 +259,9 @@ class heffte_fft_plan:
 
     def size_workspace(self):
         return _lib.load().heffte_size_workspace64(self.plan)
+
+    def uses_peer_memory(self, precision=1):
+        return _lib.load().heffte_b200_uses_peer_memory(self.plan, precision) == 1
 
     def get_scale_factor(self, scaling):
         return _lib.load().heffte_get_scale_factor(self.plan, scaling)

@@ -73,6 +73,10 @@ typedef int (*heffte_allgather_fn)(void *context, const void *mine, void *all, s
 typedef int (*heffte_exchange_fn)(void *context, int nsend, const int *send_peer, void *const *send_ptr, const size_t *send_bytes,
                                   int nrecv, const int *recv_peer, void *const *recv_ptr, const size_t *recv_bytes, void *stream);
 int heffte_comm_create_callbacks(int rank, int size, heffte_allgather_fn gather, heffte_exchange_fn exchange, void *context, heffte_comm *comm);
+/* `size` ranks inside ONE process, one host thread per rank, rank r on CUDA device devices[r] (NULL: all on device 0; the
+ * same device may repeat -- this is how the test-suite runs multi-rank plans on one GPU).  Writes `size` handles; each must
+ * be used from its own host thread and all plan calls are collective over the group. */
+int heffte_comm_create_threads(int size, const int *devices, heffte_comm *comms);
 int heffte_comm_rank(heffte_comm comm);
 int heffte_comm_size(heffte_comm comm);
 int heffte_comm_destroy(heffte_comm comm);
@@ -131,6 +135,9 @@ void heffte_backward_d2d_buffered(heffte_plan const plan, double const *input, d
 int heffte_execute(heffte_plan const plan, int precision, int direction, int batch, void const *input, void *output, void *workspace, int scale);
 /* same through pinned host staging: copies input host->device, transforms, copies the result device->host, synchronises */
 int heffte_execute_host(heffte_plan const plan, int precision, int direction, int batch, void const *host_input, void *host_output, int scale);
+/* 1 when the plan moves data between ranks through peer memory (NVLink stores fused into the FFT kernels), 0 when it uses
+ * the communicator's send/receive path, -1 on a bad handle; meaningful after the first transform of that precision */
+int heffte_b200_uses_peer_memory(heffte_plan const plan, int precision);
 /* error text of the last failing call on this thread */
 const char* heffte_last_error(void);
 

@@ -76,6 +76,14 @@ int b200_fft1d_destroy(b200_fft1d_plan plan);
  * the separate scaling kernel (src/heffte_backend_cuda.cu:138-145, 471-478).  in == out is allowed for C2C/r2r
  * when the two geometries coincide. */
 int b200_fft1d_execute(b200_fft1d_plan plan, int direction, const void *in, void *out, double scale, void *stream);
+/*
+ * Same transform with the FOLLOWING RESHAPE FUSED INTO THE STORE: every output element is written straight into the box
+ * of the rank that owns it after the reshape -- in local memory or in a peer GPU's memory mapped over NVLink.
+ * `device_scatter_map` points to a b200 scatter map in device memory (built by the plan, csrc/scatter_build.h).
+ * Replaces, in one kernel: cufftExec* + direct_packer::pack + MPI_Alltoallv + direct/transpose_packer::unpack
+ * (reference src/heffte_reshape3d.cpp:365-443, include/heffte_backend_cuda.h:494-524, 800-829).
+ */
+int b200_fft1d_execute_scatter(b200_fft1d_plan plan, int direction, const void *in, const void *device_scatter_map, double scale, void *stream);
 /* name of the kernel family the plan resolved to ("strided", "contig", "generic"), for tests and profiling */
 const char* b200_fft1d_kernel_name(b200_fft1d_plan plan);
 
@@ -99,6 +107,18 @@ int b200_transpose_unpack(int elem_bytes, long long nfast, long long nmid, long 
                           long long line_stride, long long plane_stride,
                           long long buff_line_stride, long long buff_plane_stride,
                           int map0, int map1, int map2, const void *src, void *dst, void *stream);
+/*
+ * Reshape of a box without a transform in front of it (the first reshape of a plan), written straight into the destination
+ * boxes through a scatter map: pack + transfer + unpack of the reference in one pass (src/heffte_reshape3d.cpp:365-443).
+ */
+int b200_scatter_copy(int elem_bytes, long long nfast, long long nmid, long long nslow, long long line_stride, long long plane_stride,
+                      const void *src, const void *device_scatter_map, void *stream);
+/*
+ * Stream-ordered barrier between the GPUs of a plan over peer memory (stands where the reference blocks the host in
+ * MPI_Alltoallv / MPI_Waitany, src/heffte_reshape3d.cpp:388-402, 662): remote_slots[p] is the address, in rank p's flag
+ * array, of the slot that belongs to rank `me`; local_flags is this rank's array; epoch increases by one per barrier.
+ */
+int b200_peer_barrier(int nranks, int me, void *const *remote_slots, void *local_flags, unsigned long long epoch, void *stream);
 /* Replaces heffte::cuda::scale_data (src/heffte_backend_cuda.cu:138-145, 471-478): data[i] *= factor over `count` reals. */
 int b200_scale(int precision, long long count, void *data, double factor, void *stream);
 /* Replaces heffte::cuda::convert (src/heffte_backend_cuda.cu:44-56, 352-361): real -> complex (zero imaginary) and complex -> real. */

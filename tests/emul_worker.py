@@ -1,0 +1,66 @@
+"""
+TEST INFRASTRUCTURE.  Whole multi-rank plans on the CPU: loads the EMULATED build of the product library
+(tests/emul/build_emul_library.py: same sources and C ABI, kernels executed thread-by-thread on the host, synchronous
+stand-in for the CUDA runtime) and runs the reference-style distributed test matrix with the ranks as host threads, in the
+peer-memory mode (fused FFT + reshape, scatter maps into the other ranks' buffers) and in the pack / exchange / unpack mode.
+Run by tests/test_emul_distributed.py in a subprocess:   python tests/emul_worker.py <nranks> <peer|exchange> [stride]
+"""
+import os
+import sys
+import threading
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    nranks, mode = int(sys.argv[1]), sys.argv[2]
+    stride = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    if mode == "exchange":
+        os.environ["HEFFTE_B200_DISABLE_P2P"] = "1"
+    else:
+        os.environ.pop("HEFFTE_B200_DISABLE_P2P", None)
+    from tests.emul.build_emul_library import build
+    from heffte_b200 import _lib
+    _lib.LIB_PATH = build()          # the emulated library stands in for libheffte_b200.so in THIS process only
+    import heffte_b200 as hf
+    from tests.multi_rank_worker import HostArrays, configs, grids_for, run_config
+
+    todo = [(c, 1) for c in configs(nranks, quick=True) if max(c["n"]) <= 32][::stride]
+    gin, gout = grids_for(nranks)[0]
+    todo.append((dict(kind="c2c", n=(8, 9, 10), prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 2))
+    comms = hf.comm_threads(nranks)
+    gate = threading.Barrier(nranks)
+    failures = [None] * nranks
+    done = [0] * nranks
+    stop = threading.Event()
+
+    def body(rank):
+        for index, (c, batch) in enumerate(todo):
+            try:
+                run_config(hf, None, comms[rank], rank, c, batch, expect_peer=(mode == "peer"), arrays=HostArrays())
+                done[rank] += 1
+            except Exception as e:  # noqa: BLE001
+                failures[rank] = "config %d: %r" % (index, e)
+                stop.set()
+            gate.wait()
+            if stop.is_set():
+                break
+            gate.wait()
+
+    threads = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(nranks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=1500)
+    if any(t.is_alive() for t in threads):
+        print("emul_worker: hung; failures:", [f for f in failures if f], "done:", done, flush=True)
+        os._exit(3)
+    if any(failures):
+        print("emul_worker: FAILED", [f for f in failures if f], flush=True)
+        sys.exit(1)
+    print("emul_worker: ranks=%d mode=%s configs=%d ok" % (nranks, mode, min(done)), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,7 +23,8 @@ def emul():
     from heffte_b200 import _lib
     out = os.path.join(EMUL_DIR, "_build", "libemul.so")
     sources = [os.path.join(EMUL_DIR, "emul_fft.cpp"), os.path.join(EMUL_DIR, "cuda_emul.h")] + \
-              [os.path.join(ROOT, "heffte_b200", "csrc", f) for f in ("fft_device.cuh", "fft_dispatch.cuh", "fft_host_plan.h")]
+              [os.path.join(ROOT, "heffte_b200", "csrc", f) for f in ("fft_device.cuh", "fft_dispatch.cuh", "fft_host_plan.h", "scatter_build.h",
+                                                                      "pack_device.cuh", "pack_host.h")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in sources):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         # -Bsymbolic + hidden visibility: the emulated kernels carry the same C++ names as the device stubs inside
@@ -36,6 +37,11 @@ def emul():
     lib.emul_fft1d.restype = ctypes.c_int
     lib.emul_fft1d.argtypes = [ctypes.POINTER(_lib.b200_fft1d_desc), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
                                ctypes.POINTER(ctypes.c_int)]
+    lib.emul_fft1d_reshape.restype = ctypes.c_int
+    lib.emul_fft1d_reshape.argtypes = [ctypes.POINTER(_lib.b200_fft1d_desc), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
+    lib.emul_scatter_copy.restype = ctypes.c_int
+    lib.emul_scatter_copy.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     return lib
 
 
