@@ -329,6 +329,31 @@ def b200_arm(args):
                "d2h_bytes_per_step": in_bytes + mid_bytes, "steps": e2e_steps,
                "note": "per rank bytes; step = forward(host in -> host out) + backward(host out -> host in), pinned buffers"}
 
+    # ---- multi-GPU: device time of every stage of one forward and one backward transform (CUDA events on the plan's stream) ----
+    multi = None
+    if distributed:
+        peer_mode = bool(fft.uses_peer_memory(prec))
+        per_dir = []
+        if peer_mode:
+            fft.stage_timing(True)
+            for direction in ("forward", "backward"):
+                barrier()
+                if direction == "forward":
+                    fft.forward_buffered(data_in, data_out, work, hf.scale.full)
+                else:
+                    fft.backward_buffered(data_out, data_in, work, hf.scale.none)
+                torch.cuda.synchronize()
+                per_dir.append([dict(direction=direction, stage=nm, ms=ms, local_bytes=lb, sent_bytes=sb) for nm, ms, lb, sb in fft.stage_times()])
+            fft.stage_timing(False)
+        # max over ranks of every stage time (same stage list on every rank)
+        flat = [e for d in per_dir for e in d]
+        if flat:
+            t = torch.tensor([e["ms"] for e in flat], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            for e, v in zip(flat, t.tolist()):
+                e["ms"] = v
+        multi = {"peer_memory": peer_mode, "stages": flat}
+
     # ---- roofline of the dominant kernel: the batched 1-D FFT pass, timed alone with CUDA events -----------------------
     roofline, stages = None, []
     if rank == 0:
@@ -383,6 +408,37 @@ def b200_arm(args):
                                                 "measured_ms": sec_per_transform * 1e3,
                                                 "frac_of_hbm_roofline": (3 * 2.0 * elems * csize / (peaks["hbm_gbs"] * 1e9)) / sec_per_transform}}
 
+    if rank == 0 and multi is not None and multi["stages"]:
+        peaks, peak_kind = measured_peaks()
+        nvlink_peak = 770.0   # GB/s per direction per GPU: measured peer copy on this pool (B200_PROFILING.md; tools/ipc_probe.py saw 760)
+        for e in multi["stages"]:
+            if e["ms"] > 0:
+                e["hbm_GB/s"] = e["local_bytes"] / e["ms"] * 1e-6
+                e["nvlink_GB/s"] = e["sent_bytes"] / e["ms"] * 1e-6
+        fwd = [e for e in multi["stages"] if e["direction"] == "forward"]
+        work_stages = [e for e in fwd if e["stage"] != "fence" and e["stage"] != "start"]
+        dominant = max(work_stages, key=lambda e: e["ms"]) if work_stages else None
+        elem = (8 if prec == 0 else 16)
+        d_bytes = float(max(nin, nout)) * elem                               # D: bytes of one rank's box
+        hbm_bytes = 6.0 * d_bytes                                            # three passes, read + write
+        nvl_bytes = float(sum(e["sent_bytes"] for e in fwd))
+        t_hbm = hbm_bytes / (peaks["hbm_gbs"] * 1e9)
+        t_nvl = nvl_bytes / (nvlink_peak * 1e9)
+        if dominant is not None:
+            sent_bound = dominant["sent_bytes"] / (nvlink_peak * 1e9) >= dominant["local_bytes"] / (peaks["hbm_gbs"] * 1e9)
+            roofline = {"bound": "nvlink" if sent_bound else "hbm",
+                        "achieved": dominant["nvlink_GB/s"] if sent_bound else dominant["hbm_GB/s"],
+                        "peak": nvlink_peak if sent_bound else peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": (dominant["nvlink_GB/s"] / nvlink_peak) if sent_bound else (dominant["hbm_GB/s"] / peaks["hbm_gbs"]),
+                        "traffic": None, "kernel": dominant["stage"],
+                        "peak_source": "measured peer copy 770 GB/s per direction (B200_PROFILING.md)" if sent_bound else peak_kind + " hbm_gbs",
+                        "algorithmic_bytes_per_launch": dominant["sent_bytes"] if sent_bound else dominant["local_bytes"],
+                        "whole_transform": {"hbm_algorithmic_GB": hbm_bytes * 1e-9, "nvlink_GB_sent_per_gpu": nvl_bytes * 1e-9,
+                                            "t_hbm_ms": t_hbm * 1e3, "t_nvlink_ms": t_nvl * 1e3, "measured_ms": sec_per_transform * 1e3,
+                                            "frac_of_overlap_roofline": max(t_hbm, t_nvl) / sec_per_transform,
+                                            "frac_of_serial_roofline": (t_hbm + t_nvl) / sec_per_transform}}
+        stages = multi["stages"]
+
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample ------------------------------
     cpu = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
@@ -404,7 +460,7 @@ def b200_arm(args):
                            args.kind, args.precision, n[0], n[1], n[2], grid, "reorder" if args.reorder else "no-reorder",
                            "slabs" if args.slabs else "pencils"),
                        "l2": "working set %.0f MB per GPU exceeds the 126 MB L2" % (max(nin, nout) * (8 if prec == 0 else 16) / 1e6),
-                       "comm": "nccl send/recv" if distributed else "none"},
+                       "comm": ("peer memory: NVLink stores fused into the FFT kernels" if (multi and multi["peer_memory"]) else "nccl send/recv") if distributed else "none"},
             "max_roundtrip_error": err,
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -92,6 +92,8 @@ def load():
     for name in ("forward_s2s", "forward_d2d", "backward_s2s", "backward_d2d"):
         sig("heffte_" + name + "_buffered", None, LP_plan, c_vp, c_vp, c_vp, c_int)
     sig("heffte_b200_uses_peer_memory", c_int, LP_plan, c_int)
+    sig("heffte_b200_stage_timing", c_int, LP_plan, c_int)
+    sig("heffte_b200_stage_times", c_int, LP_plan, c_int, ctypes.c_char_p, ctypes.POINTER(c_dbl), ctypes.POINTER(c_ll), ctypes.POINTER(c_ll))
     sig("b200_fft1d_execute_scatter", c_int, c_vp, c_int, c_vp, c_vp, c_dbl, c_vp)
     sig("b200_scatter_copy", c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_vp, c_vp, c_vp)
     sig("b200_peer_barrier", c_int, c_int, c_int, ctypes.POINTER(c_vp), c_vp, ctypes.c_ulonglong, c_vp)

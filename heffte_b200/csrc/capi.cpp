@@ -204,6 +204,27 @@ int heffte_b200_uses_peer_memory(heffte_plan const plan, int precision){
     return s->fft->uses_peer_memory(precision) ? 1 : 0;
 }
 
+int heffte_b200_stage_timing(heffte_plan const plan, int enable){
+    plan_state *s = state_of(plan);
+    if (s == nullptr) return -1;
+    s->fft->enable_stage_timing(enable != 0);
+    return 0;
+}
+int heffte_b200_stage_times(heffte_plan const plan, int max_entries, char *names, double *ms, long long *local_bytes, long long *sent_bytes){
+    plan_state *s = state_of(plan);
+    if (s == nullptr) return -1;
+    if (cudaStreamSynchronize(s->fft->stream()) != cudaSuccess) return -1;
+    auto records = s->fft->collect_stage_times();
+    int n = 0;
+    for(auto const &r : records){
+        if (n >= max_entries) break;
+        std::memcpy(names + 40 * n, r.name, 40);
+        ms[n] = r.ms; local_bytes[n] = r.local_bytes; sent_bytes[n] = r.sent_bytes;
+        n++;
+    }
+    return n;
+}
+
 int heffte_execute(heffte_plan const plan, int precision, int direction, int batch, void const *input, void *output, void *workspace, int scale){
     plan_state *s = state_of(plan);
     if (s == nullptr) return fail(B200_ERR_INVALID, "invalid plan handle");

@@ -219,6 +219,7 @@ transform3d::~transform3d(){
     }
     for(int p=0; p<2; p++) for(int i=0; i<3; i++) if (exec[p][i]) b200_fft1d_destroy(exec[p][i]);
     if (own_workspace) cudaFree(own_workspace);
+    for(cudaEvent_t e : marks) cudaEventDestroy(e);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -290,6 +291,9 @@ bool transform3d::ensure_peer(int precision){
                 if (not written.empty()) k_pos = written.position_of(lp.fft_direction[e]);
                 if (tkind == kind_r2c and dir == 1 and e == 0) bytes = real_bytes;   // c2r output
             }
+            stage_elems[dir][st] = written.count();
+            sent_elems[dir][st] = 0;
+            for(int r=0; r<n; r++) if (r != me) sent_elems[dir][st] += written.overlap(dest[r]).count();
             for(int w=0; w<2; w++){
                 std::vector<void*> bases(n);
                 for(int r=0; r<n; r++) bases[r] = static_cast<char*>(arenas[r]) + 4096 + static_cast<size_t>(w) * P.buffer_bytes;
@@ -315,6 +319,34 @@ bool transform3d::ensure_peer(int precision){
     return true;
 }
 
+void transform3d::mark(const char *name, long long local_bytes, long long sent_bytes){
+    if (not timing) return;
+    size_t const k = pending.size();
+    if (marks.size() <= k){
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        marks.push_back(e);
+    }
+    stage_record r{};
+    std::snprintf(r.name, sizeof(r.name), "%s", name);
+    r.ms = 0; r.local_bytes = local_bytes; r.sent_bytes = sent_bytes;
+    pending.push_back(r);
+    cudaEventRecord(marks[k], cstream);
+}
+
+// call after the stream has been synchronised; entry i covers the time between mark i-1 and mark i
+std::vector<transform3d::stage_record> transform3d::collect_stage_times(){
+    std::vector<stage_record> out;
+    for(size_t i=1; i<pending.size(); i++){
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, marks[i-1], marks[i]) != cudaSuccess) ms = -1;
+        stage_record r = pending[i];
+        r.ms = ms;
+        out.push_back(r);
+    }
+    return out;
+}
+
 int transform3d::peer_fence(int precision){
     peer_state &P = peer[precision];
     P.epoch++;
@@ -336,13 +368,23 @@ int transform3d::run_peer(int precision, bool is_backward, const void *in, void 
     b200_fft1d_plan const *X = exec[precision];
     auto map_of = [&](int st, int w){ return static_cast<const char*>(P.maps) + sizeof(scatter_map) * static_cast<size_t>((dir * 4 + st) * 2 + w); };
 
-    int last_fft = -1;
-    for(int st=1; st<4; st++) if (X[is_backward ? 3 - st : st - 1]) last_fft = st;
+    // the scaling rides on the LAST transform stage of the plan -- a global choice: a rank whose box is empty in that stage
+    // must not scale earlier, its data would be scaled again by the ranks that receive it
+    int const last_fft = 3;
 
+    pending.clear();
+    mark("start", 0, 0);
     // every peer has finished reading its buffers of the previous transform before anybody writes into them again
     int rc = peer_fence(precision);
     if (rc) return rc;
+    mark("fence", 0, 0);
     unsigned touched = 0;            // buffers read or written locally since the last fence
+    auto bytes_of = [&](int e, bool output){     // element size on the input / output side of executor e in this direction
+        if (tkind == kind_c2c) return cplx_bytes;
+        if (tkind != kind_r2c) return real_bytes;
+        if (e != 0) return cplx_bytes;
+        return (output != is_backward) ? cplx_bytes : real_bytes;   // r2c forward writes complex, c2r backward writes real
+    };
 
     const void *cur = in;
     int cur_buffer = -1;             // -1: caller memory
@@ -354,8 +396,10 @@ int transform3d::run_peer(int precision, bool is_backward, const void *in, void 
             rc = b200_scatter_copy(bytes, box.osize(0), box.osize(1), box.osize(2), box.osize(0), box.osize(0) * box.osize(1), cur, map_of(0, 0), cstream);
             if (rc) return rc;
         }
+        mark("reshape0 (scatter copy)", (2 * stage_elems[dir][0] - sent_elems[dir][0]) * bytes, sent_elems[dir][0] * bytes);
         rc = peer_fence(precision);
         if (rc) return rc;
+        mark("fence", 0, 0);
         cur_buffer = 0; cur = P.buffer(0);
     }
     for(int st=1; st<4; st++){
@@ -369,8 +413,16 @@ int transform3d::run_peer(int precision, bool is_backward, const void *in, void 
                 rc = b200_fft1d_execute_scatter(X[e], direction, cur, map_of(st, w), stage_scale, cstream);
                 if (rc) return rc;
             }
+            {
+                char label[40];
+                std::snprintf(label, sizeof(label), "fft%d + reshape%d (fused)", e, is_backward ? st : st);
+                long long const read_bytes = X[e] ? static_cast<long long>(is_backward ? lp.out_shape[e][me].count() : lp.out_shape[e][me].count()) * bytes_of(e, false) : 0;
+                long long const wrote = stage_elems[dir][st] * bytes_of(e, true), sent = sent_elems[dir][st] * bytes_of(e, true);
+                mark(label, read_bytes + wrote - sent, sent);
+            }
             rc = peer_fence(precision);
             if (rc) return rc;
+            mark("fence", 0, 0);
             touched = 0;
             cur_buffer = w; cur = P.buffer(w);
         }else{
@@ -389,6 +441,12 @@ int transform3d::run_peer(int precision, bool is_backward, const void *in, void 
             if (X[e]){
                 rc = b200_fft1d_execute(X[e], direction, cur, dst, stage_scale, cstream);
                 if (rc) return rc;
+                char label[40];
+                std::snprintf(label, sizeof(label), "fft%d (local)", e);
+                long long const count = lp.out_shape[e][me].count();
+                long long const out_count = (tkind == kind_r2c and e == 0) ? (is_backward ? count : lp.in_shape[1][me].count()) : count;
+                long long const in_count = (tkind == kind_r2c and e == 0 and is_backward) ? lp.in_shape[1][me].count() : count;
+                mark(label, in_count * bytes_of(e, false) + out_count * bytes_of(e, true), 0);
             }
             cur = dst; cur_buffer = dst_buffer;     // also without a transform (empty box): every rank follows the same buffers
         }
@@ -399,6 +457,7 @@ int transform3d::run_peer(int precision, bool is_backward, const void *in, void 
         size_t const bytes = static_cast<size_t>(count) * (real_out ? real_bytes : cplx_bytes);
         if (count > 0 and cudaMemcpyAsync(out, cur, bytes, cudaMemcpyDeviceToDevice, cstream) != cudaSuccess)
             return fail(B200_ERR_CUDA, "cudaMemcpyAsync failed");
+        mark("copy to the caller's array", 2 * static_cast<long long>(bytes), 0);
     }
     return B200_SUCCESS;
 }
@@ -494,9 +553,8 @@ int transform3d::run(int precision, bool is_backward, const void *in, void *out,
     int const direction = is_backward ? B200_BACKWARD : B200_FORWARD;
     b200_fft1d_plan const *X = exec[precision];
 
-    int last_fft = -1;
-    for(int s=0; s<3; s++) if (X[E[s]]) last_fft = s;
-    auto stage_scale = [&](int s){ return (s == last_fft) ? scale : 1.0; };
+    // the scaling rides on the last transform stage, on every rank (see run_peer)
+    auto stage_scale = [&](int s){ return (s == 2) ? scale : 1.0; };
 
     // ---- complex-to-complex and real-to-real: one element type from end to end ---------------------------------
     if (tkind != kind_r2c){

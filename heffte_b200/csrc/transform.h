@@ -75,6 +75,11 @@ public:
     int forward(int precision, int batch, const void *in, void *out, void *workspace, int scaling);
     int backward(int precision, int batch, const void *in, void *out, void *workspace, int scaling);
 
+    // per-stage device timing of the most recent transform (peer-memory mode): enable, run, synchronise, collect
+    struct stage_record { char name[40]; double ms; long long local_bytes; long long sent_bytes; };
+    void enable_stage_timing(bool on){ timing = on; }
+    std::vector<stage_record> collect_stage_times();
+
     // true once the plan runs its reshapes through peer memory (NVLink stores fused into the FFT kernels)
     bool uses_peer_memory(int precision) const { return peer[precision].active; }
 
@@ -100,6 +105,12 @@ private:
         char* buffer(int index) const { return static_cast<char*>(arena) + 4096 + static_cast<size_t>(index) * buffer_bytes; }
     };
     peer_state peer[2];
+    long long sent_elems[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};     // elements that leave this GPU in stage (direction, st)
+    long long stage_elems[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};    // elements this rank writes in that stage
+    bool timing = false;
+    std::vector<cudaEvent_t> marks;
+    std::vector<stage_record> pending;
+    void mark(const char *name, long long local_bytes, long long sent_bytes);
 
     transform_kind tkind;
     int r2c_dir;

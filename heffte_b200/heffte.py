@@ -263,6 +263,19 @@ class heffte_fft_plan:
     def uses_peer_memory(self, precision=1):
         return _lib.load().heffte_b200_uses_peer_memory(self.plan, precision) == 1
 
+    def stage_timing(self, enable=True):
+        _lib.load().heffte_b200_stage_timing(self.plan, int(enable))
+
+    def stage_times(self):
+        """[(name, ms, local HBM bytes, bytes sent over NVLink)] of the most recent transform (peer-memory mode)"""
+        n = 32
+        names = ctypes.create_string_buffer(40 * n)
+        ms = (ctypes.c_double * n)()
+        loc = (ctypes.c_longlong * n)()
+        sent = (ctypes.c_longlong * n)()
+        k = _lib.load().heffte_b200_stage_times(self.plan, n, names, ms, loc, sent)
+        return [(names.raw[40 * i:40 * i + 40].split(b"\0")[0].decode(), ms[i], loc[i], sent[i]) for i in range(max(k, 0))]
+
     def get_scale_factor(self, scaling):
         return _lib.load().heffte_get_scale_factor(self.plan, scaling)
 

@@ -138,6 +138,11 @@ int heffte_execute_host(heffte_plan const plan, int precision, int direction, in
 /* 1 when the plan moves data between ranks through peer memory (NVLink stores fused into the FFT kernels), 0 when it uses
  * the communicator's send/receive path, -1 on a bad handle; meaningful after the first transform of that precision */
 int heffte_b200_uses_peer_memory(heffte_plan const plan, int precision);
+/* Device timing of the stages of the most recent transform in peer-memory mode (CUDA events on the plan's stream): enable,
+ * run one transform, then collect (synchronises the stream).  Entry i: name (40 chars), milliseconds, bytes read + written in
+ * local HBM and bytes stored into other GPUs over NVLink by that stage.  Returns the number of entries. */
+int heffte_b200_stage_timing(heffte_plan const plan, int enable);
+int heffte_b200_stage_times(heffte_plan const plan, int max_entries, char *names, double *ms, long long *local_bytes, long long *sent_bytes);
 /* error text of the last failing call on this thread */
 const char* heffte_last_error(void);
 

