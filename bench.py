@@ -201,12 +201,17 @@ def b200_arm(args):
     import torch
     import heffte_b200 as hf
     from heffte_b200 import _lib, build
-    build.build_library()
-    lib = _lib.load()
-
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # the library is built in-tree ahead of time (python -m heffte_b200.build / __graft_entry__.build()); build here only if it is
+    # missing, and never from several ranks at once
+    if not os.path.exists(build.library_path()):
+        if world_size > 1:
+            raise SystemExit("bench.py: %s is missing; run `python -m heffte_b200.build` before a multi-rank launch" % build.library_path())
+        build.build_library()
+    lib = _lib.load()
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the b200 backend has no CPU fallback")
     torch.cuda.set_device(local_rank)

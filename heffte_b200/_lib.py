@@ -53,6 +53,13 @@ def load():
     sig("heffte_last_error", ctypes.c_char_p)
     sig("b200_launch_count", c_ll)
     sig("b200_device_count", c_int)
+    sig("b200_device_alloc", c_int, ctypes.c_size_t, ctypes.POINTER(c_vp))
+    sig("b200_device_free", c_int, c_vp)
+    sig("b200_copy_to_device", c_int, c_vp, c_vp, ctypes.c_size_t, c_vp)
+    sig("b200_copy_to_host", c_int, c_vp, c_vp, ctypes.c_size_t, c_vp)
+    sig("b200_copy_on_device", c_int, c_vp, c_vp, ctypes.c_size_t, c_vp)
+    sig("b200_stream_synchronize", c_int, c_vp)
+    sig("b200_device_set", c_int, c_int)
     sig("b200_fft1d_create", c_int, ctypes.POINTER(b200_fft1d_desc), ctypes.POINTER(c_vp))
     sig("b200_fft1d_destroy", c_int, c_vp)
     sig("b200_fft1d_execute", c_int, c_vp, c_int, c_vp, c_vp, c_dbl, c_vp)

@@ -29,7 +29,7 @@ def _fingerprint():
     h = hashlib.sha256()
     for path in _sources():
         with open(path, "rb") as f:
-            h.update(path.encode())
+            h.update(os.path.basename(path).encode())   # not the absolute path: the tree is copied to the GPU box
             h.update(f.read())
     h.update(" ".join(ARCH + COMMON).encode())
     return h.hexdigest()

@@ -66,6 +66,28 @@ int b200_device_count(void){
     return count;
 }
 
+int b200_device_alloc(size_t bytes, void **device_pointer){
+    if (device_pointer == nullptr) return fail(B200_ERR_INVALID, "null argument");
+    *device_pointer = nullptr;
+    if (bytes == 0) return B200_SUCCESS;
+    return check_cuda(cudaMalloc(device_pointer, bytes), "cudaMalloc");
+}
+int b200_device_free(void *device_pointer){ return (device_pointer == nullptr) ? B200_SUCCESS : check_cuda(cudaFree(device_pointer), "cudaFree"); }
+int b200_copy_to_device(const void *host, void *device, size_t bytes, void *stream){
+    if (bytes == 0) return B200_SUCCESS;
+    return check_cuda(cudaMemcpyAsync(device, host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)), "copy to device");
+}
+int b200_copy_to_host(const void *device, void *host, size_t bytes, void *stream){
+    if (bytes == 0) return B200_SUCCESS;
+    return check_cuda(cudaMemcpyAsync(host, device, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)), "copy to host");
+}
+int b200_copy_on_device(const void *source, void *destination, size_t bytes, void *stream){
+    if (bytes == 0) return B200_SUCCESS;
+    return check_cuda(cudaMemcpyAsync(destination, source, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)), "copy on device");
+}
+int b200_stream_synchronize(void *stream){ return check_cuda(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "stream synchronize"); }
+int b200_device_set(int device){ return check_cuda(cudaSetDevice(device), "cudaSetDevice"); }
+
 int b200_fft1d_create(const b200_fft1d_desc *desc, b200_fft1d_plan *out){
     if (desc == nullptr or out == nullptr) return fail(B200_ERR_INVALID, "null argument");
     auto *plan = new b200_fft1d_plan_s();

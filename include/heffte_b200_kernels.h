@@ -45,6 +45,20 @@ long long b200_launch_count(void);
 int b200_device_count(void);
 
 /*
+ * Device memory and transfers for callers that do not include the CUDA headers (the C++ front-end include/heffte_b200.hpp).
+ * Replace heffte::backend::data_manipulator<tag::gpu> (include/heffte_backend_cuda.h:230-284) and heffte::gpu::transfer
+ * (include/heffte_backend_data_transfer.h:29-183).  `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ * the copies are asynchronous with respect to the host unless the host memory is pageable.
+ */
+int b200_device_alloc(size_t bytes, void **device_pointer);
+int b200_device_free(void *device_pointer);
+int b200_copy_to_device(const void *host, void *device, size_t bytes, void *stream);
+int b200_copy_to_host(const void *device, void *host, size_t bytes, void *stream);
+int b200_copy_on_device(const void *source, void *destination, size_t bytes, void *stream);
+int b200_stream_synchronize(void *stream);
+int b200_device_set(int device);
+
+/*
  * Batched strided 1-D FFT plan.
  * Replaces: heffte::plan_cufft / plan_cufft_r2c (include/heffte_backend_cuda.h:346-422, 580-621), i.e.
  * cufftMakePlanMany(size, howmany, stride, dist) -- but with TWO batch dimensions so the "blocks" loop the
