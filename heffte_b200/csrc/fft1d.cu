@@ -42,6 +42,14 @@ int cuda_launcher::run_pow2(bool strided, bool is_float, bool scatter, int n, ff
     if (is_float) return scatter ? run_contig_f32_scatter(n, a, *this) : run_contig_f32_direct(n, a, *this);
     return scatter ? run_contig_f64_scatter(n, a, *this) : run_contig_f64_direct(n, a, *this);
 }
+int run_real_f32_direct(int kind, int m, fft_args const &a, cuda_launcher &L);
+int run_real_f32_scatter(int kind, int m, fft_args const &a, cuda_launcher &L);
+int run_real_f64_direct(int kind, int m, fft_args const &a, cuda_launcher &L);
+int run_real_f64_scatter(int kind, int m, fft_args const &a, cuda_launcher &L);
+int cuda_launcher::run_real(bool is_float, bool scatter, int kind, int m, fft_args const &a){
+    if (is_float) return scatter ? run_real_f32_scatter(kind, m, a, *this) : run_real_f32_direct(kind, m, a, *this);
+    return scatter ? run_real_f64_scatter(kind, m, a, *this) : run_real_f64_direct(kind, m, a, *this);
+}
 int cuda_launcher::run_generic(bool is_float, long long blocks, int threads, size_t smem, generic_args const &g){
     if (is_float) return launch(fft_generic_kernel<float>, blocks, threads, smem, g);
     return launch(fft_generic_kernel<double>, blocks, threads, smem, g);
@@ -124,6 +132,7 @@ const char* b200_fft1d_kernel_name(b200_fft1d_plan plan){
     switch(plan->host.family){
         case family_strided: return "strided";
         case family_contig: return "contig";
+        case family_contig_real: return "contig_real";
         default: return "generic";
     }
 }

@@ -136,6 +136,7 @@ struct fft_args {
     const void *in;
     void *out;
     const void *twiddle;   // W_N^k, k = 0..N-1, forward sign, complex of the working precision
+    const void *twiddle2;  // real-data kernels only: W_{4n}^j, j = 0..n (n = real length = 2N)
     line_geom ig, og;
     long long nlines;
     int count_a;
@@ -370,14 +371,16 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a
 // ---------------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr unsigned pad_index(unsigned i){ return i + (i >> 3); }
 
-template<typename T, typename RL, int S, int NS, int TPL, bool BWD, bool SCATTER>
+// IN_SMEM: the first pass finds its input in the row (a prologue put it there); OUT_SMEM: the last pass leaves its output
+// in the row, natural order (an epilogue takes it from there).  Used by the real-data kernels below.
+template<typename T, typename RL, int S, int NS, int TPL, bool BWD, bool SCATTER, bool IN_SMEM = false, bool OUT_SMEM = false>
 __device__ __forceinline__ void contig_pass(cplx<T> *row, unsigned j, bool valid, const cplx<T> *gin, cplx<T> *gout,
                                             long long istride, long long ostride, const cplx<T> *tw, T scale, bool do_scale,
                                             scatter_ctx const &sc){
     constexpr unsigned R = RL::radix(S);
     constexpr unsigned NB = RL::N / R;
     constexpr unsigned BPT = NB / TPL;              // butterflies per thread in this pass
-    constexpr bool FIRST = (S == 0), LAST = (S == RL::passes - 1);
+    constexpr bool FIRST = (S == 0) && !IN_SMEM, LAST = (S == RL::passes - 1) && !OUT_SMEM;
     cplx<T> v[BPT][R];
     #pragma unroll
     for(unsigned u=0; u<BPT; u++){
@@ -478,6 +481,177 @@ __global__ void __launch_bounds__((RL::N / RL::rmax) * LPB, MINB) fft_contig_ker
     if constexpr (P > 3){
         __syncthreads();
         contig_pass<T, RL, 3, N3, TPL, BWD, SCATTER>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale, sc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// real-data variants of the contiguous kernel (power-of-two real length n = 2M, lines contiguous on both sides):
+//   real_r2c : forward  real n -> complex n/2+1 ;  backward complex n/2+1 -> real n          (cufftExecD2Z / Z2D)
+//   real_cos : forward  REDFT10 (DCT-II)        ;  backward 2*REDFT01 (DCT-III)               (reference cufft_cos)
+//   real_sin : forward  RODFT10 (DST-II)        ;  backward 2*RODFT01 (DST-III)               (reference cufft_sin)
+// All of them run ONE complex FFT of length M = n/2 per line (the even/odd packing z_j = x_2j + i x_2j+1) between a
+// prologue and an epilogue that stay in shared memory:
+//   rfft:   E = (Z_k + conj Z_{M-k})/2,  O = -i (Z_k - conj Z_{M-k})/2,  X_k = E + W_n^k O,  X_{M-k} = conj(E - W_n^k O)
+//   irfft:  A = X_k + conj X_{M-k},  B = X_k - conj X_{M-k},  Z_k = A + i W_n^{-k} B,  Z_{M-k} = conj(A - i W_n^{-k} B)
+//   DCT-II (Makhoul): v = (x_0, x_2, ..., x_3, x_1), V = rfft(v), y_k = 2 Re(w_k V_k), y_{n-k} = -2 Im(w_k V_k), w_k = W_{4n}^k
+//   DCT-III: V_k = conj(w_k) (y_k - i y_{n-k}), v = irfft(V), x_{2i} = 2 v_i, x_{2i+1} = 2 v_{n-1-i}
+//   DST-II(x)_k = DCT-II((-1)^i x_i)_{n-1-k};  DST-III(x)_i = (-1)^i DCT-III(reversed x)_i
+// The reference reaches the r2r transforms through a length-4n r2c FFT and pre/post-processing kernels launched line
+// by line (include/heffte_r2r_executor.h:43-180, 191-278; src/heffte_backend_cuda.cu:149-327): 16x the FFT work and
+// 2 x 32768 launches per stage at 512^3 / 8 ranks; here a stage is one launch that moves every real number once.
+// ---------------------------------------------------------------------------------------------------------
+enum real_kind : int { real_r2c = 0, real_cos = 1, real_sin = 2 };
+
+// position of real number p of a line inside a padded complex row (re/im interleaved)
+__host__ __device__ constexpr unsigned real_pos(unsigned p){ return 2 * pad_index(p >> 1) + (p & 1); }
+
+template<typename T, typename RL, int LPB, int MINB, int KIND, bool BWD, bool SCATTER>
+__global__ void __launch_bounds__((RL::N / RL::rmax) * LPB, MINB) fft_contig_real_kernel(fft_args a){
+    B200_DYN_SMEM(smem_raw);
+    constexpr unsigned M = RL::N, NR = 2 * RL::N;
+    constexpr int TPL = RL::N / RL::rmax;
+    constexpr unsigned PITCH = pad_index(RL::N) + 1;
+    constexpr bool R2C = (KIND == real_r2c);
+    constexpr bool PROLOGUE = !(R2C && !BWD);               // everything but the real-to-complex forward load
+    constexpr bool EPILOGUE = !(R2C && BWD) || SCATTER;     // everything but the plain complex-to-real store
+    constexpr bool REAL_IN = !R2C || !BWD, REAL_OUT = !R2C || BWD;
+    const unsigned j = threadIdx.x % TPL, t = threadIdx.x / TPL;
+    cplx<T> *row = reinterpret_cast<cplx<T>*>(smem_raw) + t * PITCH;
+    T *rrow = reinterpret_cast<T*>(row);
+    const unsigned line = blockIdx.x * LPB + t;
+    const bool valid = line < a.nlines;
+    const long long ioff = valid ? tile_line_offset(a.ig, a.count_a, line) : 0;
+    const T *rin = reinterpret_cast<const T*>(a.in) + (REAL_IN ? ioff : 2 * ioff);          // both views of the input line
+    const cplx<T> *cin = reinterpret_cast<const cplx<T>*>(rin);
+    T *rout = nullptr;
+    scatter_ctx sc{nullptr, 0, 0, 0};
+    if constexpr (SCATTER){
+        scatter_map *smap = reinterpret_cast<scatter_map*>(smem_raw + ((sizeof(cplx<T>) * PITCH * LPB + 15) / 16) * 16);
+        scatter_stage(smap, a.smap);
+        __syncthreads();
+        sc.map = smap;
+        sc.b = static_cast<int>(line / static_cast<unsigned>(a.count_a));
+        sc.a = static_cast<int>(line - static_cast<unsigned>(sc.b) * static_cast<unsigned>(a.count_a));
+        sc.row = valid ? scatter_row(smap, sc.a, sc.b) : 0;
+    }else{
+        const long long ooff = valid ? tile_line_offset(a.og, a.count_a, line) : 0;
+        rout = reinterpret_cast<T*>(a.out) + (REAL_OUT ? ooff : 2 * ooff);
+    }
+    cplx<T> *cout = reinterpret_cast<cplx<T>*>(rout);
+    const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
+    const cplx<T> *tx = reinterpret_cast<const cplx<T>*>(a.twiddle2);
+    const T scale = static_cast<T>(a.scale);
+    const bool do_scale = a.scale != 1.0;
+
+    // ---- prologue: build the (swapped, for the backward engine) complex input of the M-point transform in the row -------
+    if constexpr (PROLOGUE){
+        if (valid){
+            if constexpr (!BWD){
+                // DCT-II / DST-II: Makhoul permutation of the real line, coalesced read, two interleaved write streams
+                for(unsigned i = j; i < NR; i += TPL){
+                    T x = rin[i];
+                    if (KIND == real_sin && (i & 1)) x = -x;
+                    const unsigned p = (i & 1) ? NR - 1 - (i >> 1) : (i >> 1);
+                    rrow[real_pos(p)] = x;
+                }
+            }else{
+                for(unsigned k = j; k <= M / 2; k += TPL){
+                    cplx<T> vk, vm;     // spectrum of the real sequence at k and M-k
+                    if constexpr (R2C){
+                        vk = cin[k]; vm = cin[M - k];
+                        if (k == 0){ vk.y = 0; vm.y = 0; }      // c2r ignores the imaginary part of the self-conjugate entries
+                    }else{
+                        T yk, ynk, ymk, ypk;   // y_k, y_{n-k}, y_{M-k}, y_{M+k} of the (reversed, for the sine) input
+                        if constexpr (KIND == real_cos){
+                            yk = rin[k]; ynk = (k == 0) ? T(0) : rin[NR - k]; ymk = rin[M - k]; ypk = rin[M + k];
+                        }else{
+                            yk = rin[NR - 1 - k]; ynk = (k == 0) ? T(0) : rin[k - 1]; ymk = rin[M - 1 + k]; ypk = rin[M - 1 - k];
+                        }
+                        const cplx<T> wk = ldg_c<T>(tx + k), wm = ldg_c<T>(tx + (M - k));
+                        vk = cmul(mk<T>(yk, -ynk), mk<T>(wk.x, -wk.y));
+                        vm = cmul(mk<T>(ymk, -ypk), mk<T>(wm.x, -wm.y));
+                    }
+                    const cplx<T> A = mk<T>(vk.x + vm.x, vk.y - vm.y), B = mk<T>(vk.x - vm.x, vk.y + vm.y);
+                    const cplx<T> w = ldg_c<T>(tx + 4 * k);
+                    const cplx<T> wb = cmul(mk<T>(w.x, -w.y), B);         // W_n^{-k} B
+                    const cplx<T> C = mk<T>(-wb.y, wb.x);                 // i W_n^{-k} B
+                    row[pad_index(k)] = mk<T>(A.y + C.y, A.x + C.x);                      // swap(A + C)
+                    if (k > 0) row[pad_index(M - k)] = mk<T>(-(A.y - C.y), A.x - C.x);    // swap(conj(A - C))
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- the M-point complex transform ---------------------------------------------------------------------------
+    constexpr int P = RL::passes;
+    constexpr int N1 = RL::radix(0), N2 = N1 * RL::radix(1), N3 = N2 * RL::radix(2);
+    // swaps of the backward engine live in the prologue / epilogue when those exist
+    contig_pass<T, RL, 0, 1, TPL, BWD, false, PROLOGUE, (EPILOGUE && P == 1)>(row, j, valid, cin, cout, 1, 1, tw, scale, do_scale, sc);
+    if constexpr (P > 1){
+        __syncthreads();
+        contig_pass<T, RL, 1, N1, TPL, BWD, false, false, (EPILOGUE && P == 2)>(row, j, valid, cin, cout, 1, 1, tw, scale, do_scale, sc);
+    }
+    if constexpr (P > 2){
+        __syncthreads();
+        contig_pass<T, RL, 2, N2, TPL, BWD, false, false, (EPILOGUE && P == 3)>(row, j, valid, cin, cout, 1, 1, tw, scale, do_scale, sc);
+    }
+    if constexpr (P > 3){
+        __syncthreads();
+        contig_pass<T, RL, 3, N3, TPL, BWD, false, false, (EPILOGUE && P == 4)>(row, j, valid, cin, cout, 1, 1, tw, scale, do_scale, sc);
+    }
+
+    // ---- epilogue ------------------------------------------------------------------------------------------------
+    if constexpr (EPILOGUE){
+        __syncthreads();
+        if (!valid) return;
+        auto put_real = [&](unsigned i, T value){
+            if (do_scale) value *= scale;
+            if constexpr (SCATTER) *scatter_address<T>(sc.map, sc.row, static_cast<int>(i), sc.a, sc.b) = value;
+            else rout[i] = value;
+        };
+        if constexpr (BWD){
+            // the engine ran forward on swapped data: row[e] = (Im z_e, Re z_e) with z_e = v_2e + i v_2e+1
+            for(unsigned i = j; i < NR; i += TPL){
+                if constexpr (R2C){
+                    put_real(i, (i & 1) ? row[pad_index(i >> 1)].x : row[pad_index(i >> 1)].y);
+                }else{
+                    const unsigned p = (i & 1) ? NR - 1 - (i >> 1) : (i >> 1);
+                    T v = (p & 1) ? row[pad_index(p >> 1)].x : row[pad_index(p >> 1)].y;
+                    v *= T(2);
+                    if (KIND == real_sin && (i & 1)) v = -v;
+                    put_real(i, v);
+                }
+            }
+        }else{
+            const T half = static_cast<T>(0.5);
+            for(unsigned k = j; k <= M / 2; k += TPL){
+                const cplx<T> zk = row[pad_index(k)], zm = row[pad_index((M - k) % M)];
+                const cplx<T> E = mk<T>((zk.x + zm.x) * half, (zk.y - zm.y) * half);
+                const cplx<T> O = mk<T>((zk.y + zm.y) * half, (zm.x - zk.x) * half);      // -i (Z_k - conj Z_{M-k}) / 2
+                const cplx<T> Pk = cmul(ldg_c<T>(tx + 4 * k), O);
+                const cplx<T> vk = mk<T>(E.x + Pk.x, E.y + Pk.y), vm = mk<T>(E.x - Pk.x, -(E.y - Pk.y));
+                if constexpr (R2C){
+                    cplx<T> xk = vk, xm = vm;
+                    if (do_scale){ xk.x *= scale; xk.y *= scale; xm.x *= scale; xm.y *= scale; }
+                    if constexpr (SCATTER){
+                        *scatter_address<cplx<T>>(sc.map, sc.row, static_cast<int>(k), sc.a, sc.b) = xk;
+                        *scatter_address<cplx<T>>(sc.map, sc.row, static_cast<int>(M - k), sc.a, sc.b) = xm;
+                    }else{
+                        cout[k] = xk;
+                        cout[M - k] = xm;
+                    }
+                }else{
+                    const cplx<T> a1 = cmul(ldg_c<T>(tx + k), vk), a2 = cmul(ldg_c<T>(tx + (M - k)), vm);
+                    // y_k, y_{n-k}, y_{M-k}, y_{M+k}; the sine transform stores y_p at n-1-p
+                    auto put_y = [&](unsigned p, T value){ put_real((KIND == real_sin) ? NR - 1 - p : p, value); };
+                    put_y(k, T(2) * a1.x);
+                    if (k > 0) put_y(NR - k, T(-2) * a1.y);
+                    put_y(M - k, T(2) * a2.x);
+                    if (k > 0) put_y(M + k, T(-2) * a2.y);
+                }
+            }
+        }
     }
 }
 

@@ -67,4 +67,41 @@ int dispatch_contig(int n, fft_args const &a, Launcher &L){
     }
 }
 
+// real-data variants (fft_contig_real_kernel): m = n/2 is the length of the complex engine
+template<typename T, typename RL, int LPB, int MINB, int KIND, bool SCATTER, typename Launcher>
+int launch_contig_real(fft_args const &a, Launcher &L){
+    long long blocks = (a.nlines + LPB - 1) / LPB;
+    constexpr int PITCH = pad_index(RL::N) + 1;
+    size_t smem = ((sizeof(cplx<T>) * (size_t)PITCH * LPB + 15) / 16) * 16 + (SCATTER ? sizeof(scatter_map) : 0);
+    if (a.backward) return L.launch(fft_contig_real_kernel<T, RL, LPB, MINB, KIND, true, SCATTER>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
+    return L.launch(fft_contig_real_kernel<T, RL, LPB, MINB, KIND, false, SCATTER>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
+}
+
+constexpr int real_pow2_min = 2 * pow2_min;   // real lengths served by the fast real kernels
+constexpr int real_pow2_max = 4096;
+
+template<typename T, int KIND, bool SCATTER, typename Launcher>
+int dispatch_contig_real_kind(int m, fft_args const &a, Launcher &L){
+    switch(m){
+        case 16:   return launch_contig_real<T, radix_list<4, 4, 1, 1>,   32, 6, KIND, SCATTER>(a, L);
+        case 32:   return launch_contig_real<T, radix_list<8, 4, 1, 1>,   32, 4, KIND, SCATTER>(a, L);
+        case 64:   return launch_contig_real<T, radix_list<8, 8, 1, 1>,   16, 4, KIND, SCATTER>(a, L);
+        case 128:  return launch_contig_real<T, radix_list<8, 4, 4, 1>,    8, 4, KIND, SCATTER>(a, L);
+        case 256:  return launch_contig_real<T, radix_list<8, 8, 4, 1>,    4, 6, KIND, SCATTER>(a, L);
+        case 512:  return launch_contig_real<T, radix_list<8, 8, 8, 1>,    1, 12, KIND, SCATTER>(a, L);
+        case 1024: return launch_contig_real<T, radix_list<16, 8, 8, 1>,   1, 4, KIND, SCATTER>(a, L);
+        case 2048: return launch_contig_real<T, radix_list<8, 8, 8, 4>,    1, 2, KIND, SCATTER>(a, L);
+        default: return -1;
+    }
+}
+template<typename T, bool SCATTER, typename Launcher>
+int dispatch_contig_real(int kind, int m, fft_args const &a, Launcher &L){
+    switch(kind){
+        case real_r2c: return dispatch_contig_real_kind<T, real_r2c, SCATTER>(m, a, L);
+        case real_cos: return dispatch_contig_real_kind<T, real_cos, SCATTER>(m, a, L);
+        case real_sin: return dispatch_contig_real_kind<T, real_sin, SCATTER>(m, a, L);
+        default: return -1;
+    }
+}
+
 } // namespace b200

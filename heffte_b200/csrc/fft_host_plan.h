@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <vector>
 
 #include "../../include/heffte_b200_kernels.h"
@@ -11,7 +12,7 @@
 
 namespace b200 {
 
-enum kernel_family { family_strided = 0, family_contig = 1, family_generic = 2 };
+enum kernel_family { family_strided = 0, family_contig = 1, family_generic = 2, family_contig_real = 3 };
 
 struct host_plan {
     b200_fft1d_desc desc;
@@ -24,6 +25,8 @@ struct host_plan {
     size_t smem = 0;        // generic: dynamic shared memory
     int threads = 256;      // generic: block size
     long long table_main = 0, table_extra_mod = 1, table_extra = 0;  // twiddle table layout
+    long long table_third = 0;   // family_contig_real: W_{n/2}^k for the complex engine, behind the two other segments
+    int real_kind = 0;           // family_contig_real: real_r2c / real_cos / real_sin
 };
 
 inline std::vector<int> factorize(int m){
@@ -48,9 +51,10 @@ void fill_twiddles(std::vector<T> &table, size_t offset, long long m, long long 
 }
 template<typename T>
 std::vector<T> make_twiddle_table(host_plan const &plan){
-    std::vector<T> table(2 * (plan.table_main + plan.table_extra));
+    std::vector<T> table(2 * (plan.table_main + plan.table_extra + plan.table_third));
     fill_twiddles<T>(table, 0, plan.table_main, plan.table_main);
     if (plan.table_extra > 0) fill_twiddles<T>(table, plan.table_main, plan.table_extra_mod, plan.table_extra);
+    if (plan.table_third > 0) fill_twiddles<T>(table, plan.table_main + plan.table_extra, plan.table_third, plan.table_third);
     return table;
 }
 
@@ -96,6 +100,15 @@ inline int make_host_plan(b200_fft1d_desc const &desc, host_plan &plan, const ch
     plan.threads = (work >= 256) ? 256 : ((work >= 128) ? 128 : ((work >= 64) ? 64 : 32));
     plan.table_main = plan.m;
     if (desc.kind == B200_COS or desc.kind == B200_SIN){ plan.table_extra_mod = 4LL * n; plan.table_extra = n; }
+    // power-of-two real transforms along contiguous lines: the half-length complex engine (fft_contig_real_kernel); the
+    // generic plan above stays as the path for pointers that are not aligned to a complex number
+    bool const real_kind_ok = (desc.kind == B200_R2C or desc.kind == B200_COS or desc.kind == B200_SIN);
+    if (real_kind_ok and is_pow2(n) and n >= real_pow2_min and n <= real_pow2_max and desc.in.stride == 1 and desc.out.stride == 1){
+        plan.family = family_contig_real;
+        plan.real_kind = (desc.kind == B200_R2C) ? real_r2c : ((desc.kind == B200_COS) ? real_cos : real_sin);
+        plan.table_extra_mod = 4LL * n; plan.table_extra = n + 1;      // W_{4n}^j, j = 0..n (the generic path reads j < n)
+        plan.table_third = n / 2;
+    }
     return B200_SUCCESS;
 }
 
@@ -112,9 +125,33 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
     bool const backward = (direction == B200_BACKWARD);
     bool const is_float = (d.precision == B200_PREC_FLOAT);
 
-    if (plan.family != family_generic){
+    if (plan.family == family_contig_real){
+        // the real line doubles as a line of complex numbers on the r2c load and the c2r store: pairs must be aligned
+        size_t const csize = is_float ? 8 : 16;
+        b200_line_geom const &rg = d.in;           // geometry of the real side of an r2c plan
+        bool aligned = true;
+        if (d.kind == B200_R2C){
+            const void *real_side = backward ? static_cast<const void*>(out) : in;
+            if (backward and scatter != nullptr) real_side = nullptr;      // scattered reals are stored one by one
+            aligned = (reinterpret_cast<uintptr_t>(real_side) % csize == 0) and (rg.stride_a % 2 == 0) and (rg.stride_b % 2 == 0);
+        }
+        if (aligned){
+            fft_args a;
+            a.in = in; a.out = out;
+            a.twiddle = static_cast<const char*>(twiddle) + csize * static_cast<size_t>(plan.table_main + plan.table_extra);
+            a.twiddle2 = static_cast<const char*>(twiddle) + csize * static_cast<size_t>(plan.table_main);
+            a.ig = to_geom(backward ? d.out : d.in);
+            a.og = to_geom(backward ? d.in : d.out);
+            a.nlines = nlines;
+            a.count_a = static_cast<int>(d.count_a);
+            a.backward = backward ? 1 : 0;
+            a.scale = scale;
+            a.smap = static_cast<const scatter_map*>(scatter);
+            return L.run_real(is_float, scatter != nullptr, plan.real_kind, static_cast<int>(d.n / 2), a);
+        }
+    }else if (plan.family != family_generic){
         fft_args a;
-        a.in = in; a.out = out; a.twiddle = twiddle;
+        a.in = in; a.out = out; a.twiddle = twiddle; a.twiddle2 = nullptr;
         a.ig = to_geom(backward ? d.out : d.in);   // backward swaps the roles of the two geometries
         a.og = to_geom(backward ? d.in : d.out);
         a.nlines = nlines;

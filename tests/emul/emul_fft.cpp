@@ -21,6 +21,11 @@ struct emul_launcher {
         if (is_float) return scatter ? dispatch_contig<float, true>(n, a, *this) : dispatch_contig<float, false>(n, a, *this);
         return scatter ? dispatch_contig<double, true>(n, a, *this) : dispatch_contig<double, false>(n, a, *this);
     }
+    int run_real(bool is_float, bool scatter, int kind, int m, b200::fft_args const &a){
+        using namespace b200;
+        if (is_float) return scatter ? dispatch_contig_real<float, true>(kind, m, a, *this) : dispatch_contig_real<float, false>(kind, m, a, *this);
+        return scatter ? dispatch_contig_real<double, true>(kind, m, a, *this) : dispatch_contig_real<double, false>(kind, m, a, *this);
+    }
     int run_generic(bool is_float, long long blocks, int threads, size_t smem, b200::generic_args const &g){
         if (is_float) return launch(b200::fft_generic_kernel<float>, blocks, threads, smem, g);
         return launch(b200::fft_generic_kernel<double>, blocks, threads, smem, g);
