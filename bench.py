@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, nargs=3, default=[512, 512, 512])
     ap.add_argument("--precision", default="double", choices=["float", "double"])
-    ap.add_argument("--kind", default="c2c", choices=["c2c", "r2c"])
+    ap.add_argument("--kind", default="c2c", choices=["c2c", "r2c", "r2r"], help="r2r = DCT-II / DCT-III (speed3d_r2r ... cos)")
     ap.add_argument("--reorder", action="store_true")
     ap.add_argument("--slabs", action="store_true")
     ap.add_argument("--io-pencils", action="store_true", help="pencil-shaped in/out boxes (speed3d -io_pencils)")
@@ -151,7 +151,7 @@ def run_reference_speed3d(kind, precision, size, nruns, options=()):
     while ranks * 2 <= min(cores, 64):
         ranks *= 2
     env = dict(os.environ, SHIM_NP=str(ranks))
-    cmd = [binary, "stock", precision, str(size[0]), str(size[1]), str(size[2]), "-n%d" % nruns] + list(options)
+    cmd = [binary, "stock-cos" if kind == "r2r" else "stock", precision, str(size[0]), str(size[1]), str(size[2]), "-n%d" % nruns] + list(options)
     t0 = time.time()
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=3000)
     wall = time.time() - t0
@@ -244,8 +244,10 @@ def b200_arm(args):
     else:
         outbox = hf.heffte.split_world(world, out_grid)[rank]
 
-    options = hf.plan_options(hf.backend.b200, use_reorder=args.reorder, use_pencils=not args.slabs)
-    fft = hf.fft3d_r2c(hf.backend.b200, inbox, outbox, 0, comm, options) if r2c else hf.fft3d(hf.backend.b200, inbox, outbox, comm, options)
+    r2r = args.kind == "r2r"
+    tag = hf.backend.b200_cos if r2r else hf.backend.b200
+    options = hf.plan_options(tag, use_reorder=args.reorder, use_pencils=not args.slabs)
+    fft = hf.fft3d_r2c(tag, inbox, outbox, 0, comm, options) if r2c else hf.fft3d(tag, inbox, outbox, comm, options)
 
     gen = torch.Generator(device="cuda")
     gen.manual_seed(4242 + rank)
@@ -253,13 +255,16 @@ def b200_arm(args):
     if r2c:
         data_in = torch.rand(nin, dtype=rdtype, device="cuda", generator=gen)
         data_out = torch.empty(nout, dtype=cdtype, device="cuda")
+    elif r2r:
+        data_in = torch.rand(max(nin, nout), dtype=rdtype, device="cuda", generator=gen)
+        data_out = data_in
     else:
         # speed3d: complex data with zero imaginary part, transformed in place
         data_in = torch.complex(torch.rand(max(nin, nout), dtype=rdtype, device="cuda", generator=gen),
                                 torch.zeros(max(nin, nout), dtype=rdtype, device="cuda"))
         data_out = data_in
     reference_copy = data_in.clone()
-    work = torch.empty(fft.size_workspace(), dtype=cdtype, device="cuda")
+    work = torch.empty(fft.size_workspace(), dtype=rdtype if r2r else cdtype, device="cuda")
 
     def step():
         fft.forward_buffered(data_in, data_out, work, hf.scale.full)
@@ -306,8 +311,8 @@ def b200_arm(args):
     e2e = None
     if not args.no_e2e:
         real_bytes = 4 if prec == 0 else 8
-        host_in = torch.empty(nin if r2c else max(nin, nout), dtype=rdtype if r2c else cdtype).pin_memory()
-        host_mid = torch.empty(nout if r2c else max(nin, nout), dtype=cdtype).pin_memory()
+        host_in = torch.empty(nin if r2c else max(nin, nout), dtype=rdtype if (r2c or r2r) else cdtype).pin_memory()
+        host_mid = torch.empty(nout if r2c else max(nin, nout), dtype=rdtype if r2r else cdtype).pin_memory()
         host_in.copy_(reference_copy.cpu())
         np_in, np_mid = host_in.numpy(), host_mid.numpy()
         np_back = torch.empty_like(host_in).pin_memory().numpy()
@@ -357,6 +362,11 @@ def b200_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             for e, v in zip(flat, t.tolist()):
                 e["ms"] = v
+            # bytes of the busiest rank of every stage (the plan may be uneven: tools/plan_traffic.py)
+            t = torch.tensor([[e["local_bytes"], e["sent_bytes"]] for e in flat], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            for e, (lb, sb) in zip(flat, t.tolist()):
+                e["local_bytes"], e["sent_bytes"] = int(lb), int(sb)
         multi = {"peer_memory": peer_mode, "stages": flat}
 
     # ---- roofline of the dominant kernel: the batched 1-D FFT pass, timed alone with CUDA events -----------------------
@@ -368,32 +378,41 @@ def b200_arm(args):
         stage_box = [int(v) for v in inbox.size]
         if world_size > 1:
             stage_box = None  # stage boxes differ per stage; report per-stage numbers only on one GPU
-        if stage_box is not None and not r2c:
+        if stage_box is not None:
             n0, n1, n2 = stage_box
-            elems = n0 * n1 * n2
-            csize = 8 if prec == 0 else 16
-            geoms = [((1, n0, 0), n1 * n2, 1, n0), ((n0, 1, n0 * n1), n0, n2, n1), ((n0 * n1, 1, 0), n0 * n1, 1, n2)]
-            for dim, (g, ca, cb, length) in enumerate(geoms):
-                d = b200_fft1d_desc(prec, 0, length, ca, cb, b200_line_geom(*g), b200_line_geom(*g))
+            rsize = 4 if prec == 0 else 8
+            csize = 2 * rsize
+            # (kind, length, count_a, count_b, geometry in, geometry out, in buffer, out buffer, algorithmic bytes: one read + one write)
+            if r2c:
+                h = n0 // 2 + 1
+                plans = [(1, n0, n1 * n2, 1, (1, n0, 0), (1, h, 0), data_in, data_out, n0 * n1 * n2 * rsize + h * n1 * n2 * csize),
+                         (0, n1, h, n2, (h, 1, h * n1), (h, 1, h * n1), data_out, data_out, 2 * h * n1 * n2 * csize),
+                         (0, n2, h * n1, 1, (h * n1, 1, 0), (h * n1, 1, 0), data_out, data_out, 2 * h * n1 * n2 * csize)]
+            else:
+                k, esize = (2, rsize) if r2r else (0, csize)
+                plans = [(k, n0, n1 * n2, 1, (1, n0, 0), (1, n0, 0), data_in, data_in, 2 * n0 * n1 * n2 * esize),
+                         (k, n1, n0, n2, (n0, 1, n0 * n1), (n0, 1, n0 * n1), data_in, data_in, 2 * n0 * n1 * n2 * esize),
+                         (k, n2, n0 * n1, 1, (n0 * n1, 1, 0), (n0 * n1, 1, 0), data_in, data_in, 2 * n0 * n1 * n2 * esize)]
+            for dim, (k, length, ca, cb, gi, go, src, dst, algo_bytes) in enumerate(plans):
+                d = b200_fft1d_desc(prec, k, length, ca, cb, b200_line_geom(*gi), b200_line_geom(*go))
                 plan = ctypes.c_void_p()
                 if lib.b200_fft1d_create(ctypes.byref(d), ctypes.byref(plan)) != 0:
                     continue
-                ptr = ctypes.c_void_p(data_in.data_ptr())
+                pin, pout = ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr())
                 for _ in range(3):
-                    lib.b200_fft1d_execute(plan, 0, ptr, ptr, ctypes.c_double(1.0), None)
+                    lib.b200_fft1d_execute(plan, 0, pin, pout, ctypes.c_double(1.0), None)
                 torch.cuda.synchronize()
                 reps = 10
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 for _ in range(reps):
-                    lib.b200_fft1d_execute(plan, 0, ptr, ptr, ctypes.c_double(1.0), None)
+                    lib.b200_fft1d_execute(plan, 0, pin, pout, ctypes.c_double(1.0), None)
                 b.record()
                 torch.cuda.synchronize()
                 ms = a.elapsed_time(b) / reps
                 name = lib.b200_fft1d_kernel_name(plan).decode()
                 lib.b200_fft1d_destroy(plan)
-                algo_bytes = 2.0 * elems * csize    # one read + one write of the local box per pass
-                stages.append({"dim": dim, "kernel": name, "n": length, "ms": ms, "GB/s": algo_bytes / ms * 1e-6,
+                stages.append({"dim": dim, "kernel": name, "n": length, "ms": ms, "GB/s": algo_bytes / ms * 1e-6, "algorithmic_bytes": algo_bytes,
                                "frac_of_%s_hbm" % peak_kind: algo_bytes / ms * 1e-6 / peaks["hbm_gbs"]})
             if stages:
                 dominant = max(stages, key=lambda s: s["ms"])
@@ -408,10 +427,10 @@ def b200_arm(args):
                             "frac": dominant["GB/s"] / peaks["hbm_gbs"], "traffic": traffic,
                             "kernel": "fft_%s_kernel (dim %d)" % (dominant["kernel"], dominant["dim"]),
                             "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650 GB/s",
-                            "algorithmic_bytes_per_launch": 2.0 * elems * csize,
-                            "whole_transform": {"algorithmic_GB": 3 * 2.0 * elems * csize * 1e-9, "sum_of_passes_ms": total_ms,
+                            "algorithmic_bytes_per_launch": dominant["algorithmic_bytes"],
+                            "whole_transform": {"algorithmic_GB": sum(s["algorithmic_bytes"] for s in stages) * 1e-9, "sum_of_passes_ms": total_ms,
                                                 "measured_ms": sec_per_transform * 1e3,
-                                                "frac_of_hbm_roofline": (3 * 2.0 * elems * csize / (peaks["hbm_gbs"] * 1e9)) / sec_per_transform}}
+                                                "frac_of_hbm_roofline": (sum(s["algorithmic_bytes"] for s in stages) / (peaks["hbm_gbs"] * 1e9)) / sec_per_transform}}
 
     if rank == 0 and multi is not None and multi["stages"]:
         peaks, peak_kind = measured_peaks()

@@ -111,6 +111,7 @@ def load():
     sig("heffte_b200_make_procgrid", None, c_int, ip)
     sig("heffte_b200_proc_setup_min_surface", None, ip, c_int, ip)
     sig("heffte_b200_split_world", None, ip, ip, ip)
+    sig("heffte_b200_execution_plan", c_int, c_int, ip, ip, c_int, c_int, c_int, c_int, c_int, c_int, ip, ip, ip)
     sig("heffte_b200_reshape_pieces", c_int, c_int, ip, ip, c_int, c_int, ctypes.POINTER(c_ll), c_int)
     sig("heffte_b200_plan_sizes", c_int, c_int, c_int, ip, ip, c_int, c_int, c_int, c_int, c_int, c_int,
         ctypes.POINTER(c_ll), ctypes.POINTER(c_ll), ctypes.POINTER(c_ll))

@@ -316,6 +316,27 @@ int heffte_b200_logic_plan(int nranks, int const *inboxes, int const *outboxes, 
     return 0;
 }
 
+int heffte_b200_execution_plan(int nranks, int const *inboxes, int const *outboxes, int r2c_direction,
+                               int use_reorder, int algorithm, int use_pencils, int subranks, int rank,
+                               int *shapes_out, int *fft_direction, int *swaps){
+    try{
+        shape ins, outs;
+        for(int r=0; r<nranks; r++){ ins.push_back(box_from9(inboxes + 9 * r)); outs.push_back(box_from9(outboxes + 9 * r)); }
+        plan_options o;
+        o.use_reorder = use_reorder != 0; o.algorithm = algorithm; o.use_pencils = use_pencils != 0; o.subranks = subranks;
+        logic_plan lp = make_execution_plan(ins, outs, r2c_direction, o, rank, swaps);
+        for(int s=0; s<4; s++)
+            for(int r=0; r<nranks; r++){
+                box_to9(lp.in_shape[s][r], shapes_out + (s * nranks + r) * 9);
+                box_to9(lp.out_shape[s][r], shapes_out + ((4 + s) * nranks + r) * 9);
+            }
+        for(int d=0; d<3; d++) fft_direction[d] = lp.fft_direction[d];
+    }catch(std::exception &e){
+        return fail(B200_ERR_INVALID, e.what());
+    }
+    return 0;
+}
+
 void heffte_b200_make_procgrid(int nprocs, int *grid2){ auto g = grid2d(nprocs); grid2[0] = g[0]; grid2[1] = g[1]; }
 void heffte_b200_proc_setup_min_surface(int const *world_box, int nprocs, int *grid3){
     auto g = grid_min_surface(box_from9(world_box), nprocs);

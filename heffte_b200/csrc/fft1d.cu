@@ -46,7 +46,15 @@ int run_real_f32_direct(int kind, int m, fft_args const &a, cuda_launcher &L);
 int run_real_f32_scatter(int kind, int m, fft_args const &a, cuda_launcher &L);
 int run_real_f64_direct(int kind, int m, fft_args const &a, cuda_launcher &L);
 int run_real_f64_scatter(int kind, int m, fft_args const &a, cuda_launcher &L);
-int cuda_launcher::run_real(bool is_float, bool scatter, int kind, int m, fft_args const &a){
+int run_sreal_f32_direct(int kind, int m, fft_args const &a, cuda_launcher &L);
+int run_sreal_f32_scatter(int kind, int m, fft_args const &a, cuda_launcher &L);
+int run_sreal_f64_direct(int kind, int m, fft_args const &a, cuda_launcher &L);
+int run_sreal_f64_scatter(int kind, int m, fft_args const &a, cuda_launcher &L);
+int cuda_launcher::run_real(bool strided, bool is_float, bool scatter, int kind, int m, fft_args const &a){
+    if (strided){
+        if (is_float) return scatter ? run_sreal_f32_scatter(kind, m, a, *this) : run_sreal_f32_direct(kind, m, a, *this);
+        return scatter ? run_sreal_f64_scatter(kind, m, a, *this) : run_sreal_f64_direct(kind, m, a, *this);
+    }
     if (is_float) return scatter ? run_real_f32_scatter(kind, m, a, *this) : run_real_f32_direct(kind, m, a, *this);
     return scatter ? run_real_f64_scatter(kind, m, a, *this) : run_real_f64_direct(kind, m, a, *this);
 }
@@ -133,6 +141,7 @@ const char* b200_fft1d_kernel_name(b200_fft1d_plan plan){
         case family_strided: return "strided";
         case family_contig: return "contig";
         case family_contig_real: return "contig_real";
+        case family_strided_real: return "strided_real";
         default: return "generic";
     }
 }

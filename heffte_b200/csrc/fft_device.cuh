@@ -189,7 +189,8 @@ template<typename T> __device__ __forceinline__ cplx<T> ldg_c(const cplx<T> *p){
 template<int BYTES> __device__ __forceinline__ void async_copy(void *smem_dst, const void *gsrc){
     unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(gsrc));
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(s), "l"(gsrc));
+    else if constexpr (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(s), "l"(gsrc));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(s), "l"(gsrc));
 }
 __device__ __forceinline__ void async_wait_all(){ asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 #else
@@ -650,6 +651,220 @@ __global__ void __launch_bounds__((RL::N / RL::rmax) * LPB, MINB) fft_contig_rea
                     put_y(M - k, T(2) * a2.x);
                     if (k > 0) put_y(M + k, T(-2) * a2.y);
                 }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// real-data variants of the strided kernel: same transforms and same algebra as fft_contig_real_kernel, for lines whose
+// neighbours are adjacent in memory (a real transform along the middle / slow axis of a box, i.e. every r2r stage but
+// the first of a plan that does not reorder, and r2c along dimensions 1 / 2).  The tile is [M][LPB] complex numbers;
+// a row of LPB adjacent reals is one 128-byte access.  Forward: the real rows land (asynchronously) in the re/im slots
+// the even/odd packing wants, decimation-in-frequency passes in place, and the rfft / DCT post-processing reads the
+// pair (k, M-k) at its digit-reversed positions.  Backward: the pair-wise pre-processing writes the tile, and the last
+// pass stores real rows straight from registers.
+// ---------------------------------------------------------------------------------------------------------
+// in-place position of natural index k after all DIF passes (inverse of dif_output_index)
+template<typename RL>
+__device__ __forceinline__ unsigned dif_position_of(unsigned k){
+    constexpr unsigned r0 = RL::radix(0);
+    unsigned p = (k % r0) * RL::stride(0);
+    k /= r0;
+    if constexpr (RL::passes > 1){ constexpr unsigned r1 = RL::radix(1); p += (k % r1) * RL::stride(1); k /= r1; }
+    if constexpr (RL::passes > 2){ constexpr unsigned r2 = RL::radix(2); p += (k % r2) * RL::stride(2); k /= r2; }
+    if constexpr (RL::passes > 3){ p += k; }
+    return p;
+}
+
+// where real number p of the engine output goes, and what it is multiplied by, on the backward store
+template<typename T, int KIND>
+__device__ __forceinline__ void real_backward_target(unsigned p, unsigned M, unsigned &row, T &factor){
+    if constexpr (KIND == real_r2c){ row = p; factor = T(1); }
+    else{
+        row = (p < M) ? 2 * p : 2 * (2 * M - 1 - p) + 1;
+        factor = (KIND == real_sin && (row & 1)) ? T(-2) : T(2);
+    }
+}
+
+template<typename T, typename RL, int S, int TPL, int LPB, int KIND, bool BWD, bool SCATTER>
+__device__ __forceinline__ void strided_real_pass(cplx<T> *sm, unsigned t, unsigned j, bool valid, T *rout, long long ostride,
+                                                  const cplx<T> *tw, T scale, bool do_scale, scatter_ctx const &sc){
+    constexpr unsigned R = RL::radix(S);
+    constexpr unsigned ST = RL::stride(S);
+    constexpr unsigned NB = RL::N / R;
+    constexpr unsigned M = RL::N;
+    constexpr bool FIRST = (S == 0), LAST = (S == RL::passes - 1);
+    #pragma unroll
+    for(unsigned u=0; u<NB/TPL; u++){
+        const unsigned q = j + u * TPL;
+        const unsigned o = q % ST;
+        const unsigned p0 = (q / ST) * (ST * R) + o;
+        cplx<T> *cell = sm + p0 * LPB + t;
+        cplx<T> v[R];
+        #pragma unroll
+        for(unsigned r=0; r<R; r++){
+            cplx<T> x = cell[r * ST * LPB];
+            // DST-II: the odd samples sit in the second half of the permuted sequence and carry a minus sign
+            if (FIRST && !BWD && KIND == real_sin && r >= R / 2){ x.x = -x.x; x.y = -x.y; }
+            v[r] = x;
+        }
+        butterfly<T, R>::run(v);
+        if constexpr (!LAST || !BWD){
+            if constexpr (!LAST) apply_twiddles<T, R, true>(v, tw, o * (RL::N / (ST * R)));
+            #pragma unroll
+            for(unsigned r=0; r<R; r++) cell[r * ST * LPB] = v[r];
+        }else{
+            if (valid){
+                const unsigned k0 = dif_output_index<RL>(p0);
+                #pragma unroll
+                for(unsigned r=0; r<R; r++){
+                    const unsigned e = k0 + r * (M / R);        // engine output index: z_e = v_2e + i v_2e+1, stored swapped
+                    #pragma unroll
+                    for(unsigned h=0; h<2; h++){
+                        unsigned row; T factor;
+                        real_backward_target<T, KIND>(2 * e + h, M, row, factor);
+                        T value = (h == 0 ? v[r].y : v[r].x) * factor;
+                        if (do_scale) value *= scale;
+                        if constexpr (SCATTER) *scatter_address<T>(sc.map, sc.row, static_cast<int>(row), sc.a, sc.b) = value;
+                        else rout[static_cast<long long>(row) * ostride] = value;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template<typename T, typename RL, int TPL, int LPB, int MINB, int KIND, bool BWD, bool SCATTER>
+__global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_real_kernel(fft_args a){
+    B200_DYN_SMEM(smem_raw);
+    constexpr unsigned M = RL::N, NR = 2 * RL::N;
+    constexpr bool R2C = (KIND == real_r2c);
+    cplx<T> *sm = reinterpret_cast<cplx<T>*>(smem_raw);
+    T *rsm = reinterpret_cast<T*>(smem_raw);
+    const unsigned t = threadIdx.x % LPB, j = threadIdx.x / LPB;
+    const unsigned line = blockIdx.x * LPB + t;
+    const bool valid = line < a.nlines;
+    const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
+    const cplx<T> *tx = reinterpret_cast<const cplx<T>*>(a.twiddle2);
+    const T scale = static_cast<T>(a.scale);
+    const bool do_scale = a.scale != 1.0;
+    constexpr int P = RL::passes;
+    const long long ioff = valid ? tile_line_offset(a.ig, a.count_a, line) : 0;
+    const long long istride = a.ig.stride;
+
+    scatter_ctx sc{nullptr, 0, 0, 0};
+    long long ooff = 0;
+    if constexpr (SCATTER){
+        scatter_map *smap = reinterpret_cast<scatter_map*>(sm + static_cast<size_t>(RL::N) * LPB);   // behind the tile
+        scatter_stage(smap, a.smap);
+        sc.map = smap;
+        sc.b = static_cast<int>(line / static_cast<unsigned>(a.count_a));
+        sc.a = static_cast<int>(line - static_cast<unsigned>(sc.b) * static_cast<unsigned>(a.count_a));
+    }else{
+        ooff = valid ? tile_line_offset(a.og, a.count_a, line) : 0;
+    }
+    const long long ostride = a.og.stride;
+
+    if constexpr (!BWD){
+        // ---- forward: real rows -> re/im slots of the packed sequence (asynchronous, nothing held in registers) ----------
+        if (valid){
+            const T *src = reinterpret_cast<const T*>(a.in) + ioff + static_cast<long long>(j) * istride;
+            const long long hop = static_cast<long long>(TPL) * istride;
+            #pragma unroll 4
+            for(unsigned i = j; i < NR; i += TPL){
+                const unsigned p = R2C ? i : ((i & 1) ? NR - 1 - (i >> 1) : (i >> 1));
+                async_copy<sizeof(T)>(rsm + (2 * ((p >> 1) * LPB + t) + (p & 1)), src);
+                src += hop;
+            }
+        }
+        async_wait_all();
+        __syncthreads();
+        if constexpr (SCATTER) sc.row = valid ? scatter_row(sc.map, sc.a, sc.b) : 0;
+    }else{
+        // ---- backward: Z_k and Z_{M-k} from the pair (k, M-k) of the input, written swapped for the forward engine ---------
+        if constexpr (SCATTER){ __syncthreads(); sc.row = valid ? scatter_row(sc.map, sc.a, sc.b) : 0; }
+        if (valid){
+            const T *rin = reinterpret_cast<const T*>(a.in) + (R2C ? 2 * ioff : ioff);
+            const cplx<T> *cin = reinterpret_cast<const cplx<T>*>(rin);
+            for(unsigned k = j; k <= M / 2; k += TPL){
+                cplx<T> vk, vm;
+                if constexpr (R2C){
+                    vk = cin[static_cast<long long>(k) * istride]; vm = cin[static_cast<long long>(M - k) * istride];
+                    if (k == 0){ vk.y = 0; vm.y = 0; }
+                }else{
+                    T yk, ynk, ymk, ypk;
+                    if constexpr (KIND == real_cos){
+                        yk = rin[k * istride]; ynk = (k == 0) ? T(0) : rin[(NR - k) * istride];
+                        ymk = rin[(M - k) * istride]; ypk = rin[(M + k) * istride];
+                    }else{
+                        yk = rin[(NR - 1 - k) * istride]; ynk = (k == 0) ? T(0) : rin[(k - 1) * istride];
+                        ymk = rin[(M - 1 + k) * istride]; ypk = rin[(M - 1 - k) * istride];
+                    }
+                    const cplx<T> wk = ldg_c<T>(tx + k), wm = ldg_c<T>(tx + (M - k));
+                    vk = cmul(mk<T>(yk, -ynk), mk<T>(wk.x, -wk.y));
+                    vm = cmul(mk<T>(ymk, -ypk), mk<T>(wm.x, -wm.y));
+                }
+                const cplx<T> A = mk<T>(vk.x + vm.x, vk.y - vm.y), B = mk<T>(vk.x - vm.x, vk.y + vm.y);
+                const cplx<T> w = ldg_c<T>(tx + 4 * k);
+                const cplx<T> wb = cmul(mk<T>(w.x, -w.y), B);
+                const cplx<T> C = mk<T>(-wb.y, wb.x);
+                sm[k * LPB + t] = mk<T>(A.y + C.y, A.x + C.x);
+                if (k > 0) sm[(M - k) * LPB + t] = mk<T>(-(A.y - C.y), A.x - C.x);
+            }
+        }
+        __syncthreads();
+    }
+
+    T *rout = SCATTER ? nullptr : reinterpret_cast<T*>(a.out) + ((R2C && !BWD) ? 2 * ooff : ooff);
+    strided_real_pass<T, RL, 0, TPL, LPB, KIND, BWD, SCATTER>(sm, t, j, valid, rout, ostride, tw, scale, do_scale, sc);
+    if constexpr (P > 1){
+        __syncthreads();
+        strided_real_pass<T, RL, 1, TPL, LPB, KIND, BWD, SCATTER>(sm, t, j, valid, rout, ostride, tw, scale, do_scale, sc);
+    }
+    if constexpr (P > 2){
+        __syncthreads();
+        strided_real_pass<T, RL, 2, TPL, LPB, KIND, BWD, SCATTER>(sm, t, j, valid, rout, ostride, tw, scale, do_scale, sc);
+    }
+    if constexpr (P > 3){
+        __syncthreads();
+        strided_real_pass<T, RL, 3, TPL, LPB, KIND, BWD, SCATTER>(sm, t, j, valid, rout, ostride, tw, scale, do_scale, sc);
+    }
+
+    if constexpr (!BWD){
+        // ---- forward epilogue: spectrum of the real sequence from the pair (k, M-k), then r2c store or DCT / DST twiddle ------
+        __syncthreads();
+        if (!valid) return;
+        cplx<T> *cout = reinterpret_cast<cplx<T>*>(rout);
+        auto put_real = [&](unsigned i, T value){
+            if (do_scale) value *= scale;
+            if constexpr (SCATTER) *scatter_address<T>(sc.map, sc.row, static_cast<int>(i), sc.a, sc.b) = value;
+            else rout[static_cast<long long>(i) * ostride] = value;
+        };
+        const T half = static_cast<T>(0.5);
+        for(unsigned k = j; k <= M / 2; k += TPL){
+            const cplx<T> zk = sm[dif_position_of<RL>(k) * LPB + t], zm = sm[dif_position_of<RL>((M - k) % M) * LPB + t];
+            const cplx<T> E = mk<T>((zk.x + zm.x) * half, (zk.y - zm.y) * half);
+            const cplx<T> O = mk<T>((zk.y + zm.y) * half, (zm.x - zk.x) * half);
+            const cplx<T> Pk = cmul(ldg_c<T>(tx + 4 * k), O);
+            const cplx<T> vk = mk<T>(E.x + Pk.x, E.y + Pk.y), vm = mk<T>(E.x - Pk.x, -(E.y - Pk.y));
+            if constexpr (R2C){
+                cplx<T> xk = vk, xm = vm;
+                if (do_scale){ xk.x *= scale; xk.y *= scale; xm.x *= scale; xm.y *= scale; }
+                if constexpr (SCATTER){
+                    *scatter_address<cplx<T>>(sc.map, sc.row, static_cast<int>(k), sc.a, sc.b) = xk;
+                    *scatter_address<cplx<T>>(sc.map, sc.row, static_cast<int>(M - k), sc.a, sc.b) = xm;
+                }else{
+                    cout[static_cast<long long>(k) * ostride] = xk;
+                    cout[static_cast<long long>(M - k) * ostride] = xm;
+                }
+            }else{
+                const cplx<T> a1 = cmul(ldg_c<T>(tx + k), vk), a2 = cmul(ldg_c<T>(tx + (M - k)), vm);
+                auto put_y = [&](unsigned p, T value){ put_real((KIND == real_sin) ? NR - 1 - p : p, value); };
+                put_y(k, T(2) * a1.x);
+                if (k > 0) put_y(NR - k, T(-2) * a1.y);
+                put_y(M - k, T(2) * a2.x);
+                if (k > 0) put_y(M + k, T(-2) * a2.y);
             }
         }
     }

@@ -94,6 +94,39 @@ int dispatch_contig_real_kind(int m, fft_args const &a, Launcher &L){
         default: return -1;
     }
 }
+template<typename T, typename RL, int TPL, int LPB, int MINB, int KIND, bool SCATTER, typename Launcher>
+int launch_strided_real(fft_args const &a, Launcher &L){
+    long long blocks = (a.nlines + LPB - 1) / LPB;
+    size_t smem = sizeof(cplx<T>) * (size_t)RL::N * LPB + (SCATTER ? sizeof(scatter_map) : 0);
+    if (a.backward) return L.launch(fft_strided_real_kernel<T, RL, TPL, LPB, MINB, KIND, true, SCATTER>, blocks, TPL * LPB, smem, a);
+    return L.launch(fft_strided_real_kernel<T, RL, TPL, LPB, MINB, KIND, false, SCATTER>, blocks, TPL * LPB, smem, a);
+}
+// tile [m][LPB]: a row of LPB adjacent reals is 128 bytes where shared memory allows (fp64: 16 lines, fp32: 32 lines)
+template<typename T, int KIND, bool SCATTER, typename Launcher>
+int dispatch_strided_real_kind(int m, fft_args const &a, Launcher &L){
+    constexpr int F = row_lines<T>::value / 8;    // 1 (fp64) / 2 (fp32)
+    switch(m){
+        case 16:   return launch_strided_real<T, radix_list<4, 4, 1, 1>,    4 / F, 32 * F, 2, KIND, SCATTER>(a, L);
+        case 32:   return launch_strided_real<T, radix_list<8, 4, 1, 1>,    4 / F, 32 * F, 2, KIND, SCATTER>(a, L);
+        case 64:   return launch_strided_real<T, radix_list<8, 8, 1, 1>,    8 / F, 16 * F, 2, KIND, SCATTER>(a, L);
+        case 128:  return launch_strided_real<T, radix_list<8, 4, 4, 1>,    8 / F, 16 * F, 2, KIND, SCATTER>(a, L);
+        case 256:  return launch_strided_real<T, radix_list<8, 8, 4, 1>,   16 / F, 16 * F, 3, KIND, SCATTER>(a, L);
+        case 512:  return launch_strided_real<T, radix_list<8, 8, 8, 1>,   32 / F, 16 * F, 1, KIND, SCATTER>(a, L);
+        case 1024: return launch_strided_real<T, radix_list<16, 8, 8, 1>,  32 / F,  8 * F, 1, KIND, SCATTER>(a, L);
+        case 2048: return launch_strided_real<T, radix_list<8, 8, 8, 4>,  128 / F,  4 * F, 1, KIND, SCATTER>(a, L);
+        default: return -1;
+    }
+}
+template<typename T, bool SCATTER, typename Launcher>
+int dispatch_strided_real(int kind, int m, fft_args const &a, Launcher &L){
+    switch(kind){
+        case real_r2c: return dispatch_strided_real_kind<T, real_r2c, SCATTER>(m, a, L);
+        case real_cos: return dispatch_strided_real_kind<T, real_cos, SCATTER>(m, a, L);
+        case real_sin: return dispatch_strided_real_kind<T, real_sin, SCATTER>(m, a, L);
+        default: return -1;
+    }
+}
+
 template<typename T, bool SCATTER, typename Launcher>
 int dispatch_contig_real(int kind, int m, fft_args const &a, Launcher &L){
     switch(kind){

@@ -12,7 +12,7 @@
 
 namespace b200 {
 
-enum kernel_family { family_strided = 0, family_contig = 1, family_generic = 2, family_contig_real = 3 };
+enum kernel_family { family_strided = 0, family_contig = 1, family_generic = 2, family_contig_real = 3, family_strided_real = 4 };
 
 struct host_plan {
     b200_fft1d_desc desc;
@@ -103,8 +103,10 @@ inline int make_host_plan(b200_fft1d_desc const &desc, host_plan &plan, const ch
     // power-of-two real transforms along contiguous lines: the half-length complex engine (fft_contig_real_kernel); the
     // generic plan above stays as the path for pointers that are not aligned to a complex number
     bool const real_kind_ok = (desc.kind == B200_R2C or desc.kind == B200_COS or desc.kind == B200_SIN);
-    if (real_kind_ok and is_pow2(n) and n >= real_pow2_min and n <= real_pow2_max and desc.in.stride == 1 and desc.out.stride == 1){
-        plan.family = family_contig_real;
+    bool const real_contig = (desc.in.stride == 1 and desc.out.stride == 1);
+    bool const real_strided = (desc.in.stride != 1 and desc.out.stride != 1 and desc.in.stride_a == 1 and desc.out.stride_a == 1);
+    if (real_kind_ok and is_pow2(n) and n >= real_pow2_min and n <= real_pow2_max and (real_contig or real_strided)){
+        plan.family = real_contig ? family_contig_real : family_strided_real;
         plan.real_kind = (desc.kind == B200_R2C) ? real_r2c : ((desc.kind == B200_COS) ? real_cos : real_sin);
         plan.table_extra_mod = 4LL * n; plan.table_extra = n + 1;      // W_{4n}^j, j = 0..n (the generic path reads j < n)
         plan.table_third = n / 2;
@@ -125,12 +127,13 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
     bool const backward = (direction == B200_BACKWARD);
     bool const is_float = (d.precision == B200_PREC_FLOAT);
 
-    if (plan.family == family_contig_real){
-        // the real line doubles as a line of complex numbers on the r2c load and the c2r store: pairs must be aligned
+    if (plan.family == family_contig_real or plan.family == family_strided_real){
+        // contiguous lines: the real line doubles as a line of complex numbers on the r2c load and the c2r store, so the
+        // pairs must be aligned (the strided kernel moves the reals one by one)
         size_t const csize = is_float ? 8 : 16;
         b200_line_geom const &rg = d.in;           // geometry of the real side of an r2c plan
         bool aligned = true;
-        if (d.kind == B200_R2C){
+        if (d.kind == B200_R2C and plan.family == family_contig_real){
             const void *real_side = backward ? static_cast<const void*>(out) : in;
             if (backward and scatter != nullptr) real_side = nullptr;      // scattered reals are stored one by one
             aligned = (reinterpret_cast<uintptr_t>(real_side) % csize == 0) and (rg.stride_a % 2 == 0) and (rg.stride_b % 2 == 0);
@@ -147,7 +150,7 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
             a.backward = backward ? 1 : 0;
             a.scale = scale;
             a.smap = static_cast<const scatter_map*>(scatter);
-            return L.run_real(is_float, scatter != nullptr, plan.real_kind, static_cast<int>(d.n / 2), a);
+            return L.run_real(plan.family == family_strided_real, is_float, scatter != nullptr, plan.real_kind, static_cast<int>(d.n / 2), a);
         }
     }else if (plan.family != family_generic){
         fft_args a;

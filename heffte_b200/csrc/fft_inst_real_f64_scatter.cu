@@ -1,5 +1,6 @@
 // One slice of the power-of-two FFT kernel instantiations (real-data contig kernel, double, fused-reshape store); see fft_inst_real.inc.
 #define B200_INST_NAME run_real_f64_scatter
+#define B200_INST_DISPATCH dispatch_contig_real
 #define B200_INST_TYPE double
 #define B200_INST_SCATTER true
 #include "fft_inst_real.inc"

@@ -1,5 +1,8 @@
 #include "plan_logic.h"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace b200 {
 
 namespace {
@@ -206,6 +209,144 @@ logic_plan make_logic_plan(shape const &inboxes, shape const &outboxes, int r2c_
 
     planner p(inboxes, outboxes, r2c_direction, options, subset);
     return options.use_pencils ? p.by_pencils() : p.by_slabs();
+}
+
+namespace {
+// maximum-weight perfect matching of ranks (rows) to boxes (columns): Hungarian algorithm with potentials, O(n^3)
+std::vector<int> best_assignment(std::vector<double> const &weight, int n){
+    double top = 0;
+    for(double w : weight) top = std::max(top, w);
+    auto cost = [&](int r, int c){ return top - weight[static_cast<size_t>(r) * n + c]; };
+    double const inf = 1e300;
+    std::vector<double> u(n + 1, 0.0), v(n + 1, 0.0);
+    std::vector<int> match(n + 1, 0), way(n + 1, 0);      // match[c] = row assigned to column c (1-based)
+    for(int i=1; i<=n; i++){
+        match[0] = i;
+        int j0 = 0;
+        std::vector<double> minv(n + 1, inf);
+        std::vector<char> used(n + 1, 0);
+        do{
+            used[j0] = 1;
+            int const i0 = match[j0];
+            int j1 = 0;
+            double delta = inf;
+            for(int j=1; j<=n; j++) if (not used[j]){
+                double const cur = cost(i0 - 1, j - 1) - u[i0] - v[j];
+                if (cur < minv[j]){ minv[j] = cur; way[j] = j0; }
+                if (minv[j] < delta){ delta = minv[j]; j1 = j; }
+            }
+            for(int j=0; j<=n; j++){
+                if (used[j]){ u[match[j]] += delta; v[j] -= delta; }
+                else minv[j] -= delta;
+            }
+            j0 = j1;
+        }while(match[j0] != 0);
+        do{ int const j1 = way[j0]; match[j0] = match[j1]; j0 = j1; }while(j0);
+    }
+    std::vector<int> box_of_rank(n, 0);
+    for(int j=1; j<=n; j++) box_of_rank[match[j] - 1] = j - 1;
+    return box_of_rank;
+}
+}
+
+int balance_traffic(logic_plan &plan, int r2c_direction){
+    int const n = static_cast<int>(plan.in_shape[0].size());
+    if (n < 2 or n > 64) return 0;
+    if (plan.options.subranks > 0 and plan.options.subranks < n) return 0;     // idle ranks must stay idle
+    auto weight_of = [&](int i){ return (i == 0 and r2c_direction != -1) ? 1.0 : 2.0; };   // reals of the working precision per element
+    // cost of a plan: sum over the reshapes of the busiest link end (out or in), then the total volume
+    auto cost = [&](logic_plan const &p, double &busiest, double &volume){
+        busiest = 0; volume = 0;
+        for(int i=0; i<4; i++){
+            std::vector<double> out(n, 0.0), in(n, 0.0);
+            for(int r=0; r<n; r++) for(int q=0; q<n; q++) if (q != r){
+                double const w = weight_of(i) * static_cast<double>(p.in_shape[i][r].overlap(p.out_shape[i][q]).count());
+                out[r] += w; in[q] += w;
+            }
+            double worst = 0;
+            for(int r=0; r<n; r++){ worst = std::max(worst, std::max(out[r], in[r])); volume += out[r]; }
+            busiest += worst;
+        }
+    };
+    auto better = [](double busy, double volume, double best_busy, double best_volume){
+        double const eps = 1e-9 * (best_busy + best_volume + 1.0);
+        return busy < best_busy - eps or (busy <= best_busy + eps and volume < best_volume - eps);
+    };
+    // the boxes of stage t are the outputs of reshape t and the inputs of reshape t+1: give every rank the box that shares the
+    // most with what the rank holds before (reshape t) and / or after (reshape t+1), the other stages fixed
+    auto assign_stage = [&](logic_plan &p, int t, bool look_back, bool look_ahead){
+        std::vector<double> w(static_cast<size_t>(n) * n, 0.0);
+        for(int r=0; r<n; r++) for(int c=0; c<n; c++){
+            double share = 0;
+            if (look_back)  share += weight_of(t) * static_cast<double>(p.in_shape[t][r].overlap(p.out_shape[t][c]).count());
+            if (look_ahead) share += weight_of(t+1) * static_cast<double>(p.in_shape[t+1][c].overlap(p.out_shape[t+1][r]).count());
+            w[static_cast<size_t>(r) * n + c] = share + ((r == c) ? 1e-3 : 0.0);     // ties keep the reference's choice
+        }
+        std::vector<int> const pick = best_assignment(w, n);
+        shape const outs = p.out_shape[t], ins = p.in_shape[t+1];
+        for(int r=0; r<n; r++){ p.out_shape[t][r] = outs[pick[r]]; p.in_shape[t+1][r] = ins[pick[r]]; }
+    };
+    // coordinate descent from a starting plan: one stage at a time against both neighbours, strict improvements only
+    auto descend = [&](logic_plan &p){
+        double busy, volume;
+        cost(p, busy, volume);
+        for(int sweep=0; sweep<4; sweep++){
+            bool improved = false;
+            for(int t=2; t>=0; t--){
+                logic_plan trial = p;
+                assign_stage(trial, t, true, true);
+                double b, v;
+                cost(trial, b, v);
+                if (better(b, v, busy, volume)){ p = trial; busy = b; volume = v; improved = true; }
+            }
+            if (not improved) break;
+        }
+    };
+    double best_busy, best_volume;
+    cost(plan, best_busy, best_volume);
+    int changes = 0;
+    // candidates: descent from the reference's plan; a backward chain (last stage placed next to the output boxes, then each
+    // earlier stage next to both neighbours); a forward chain (first stage next to the input boxes, ...)
+    logic_plan candidate[3] = {plan, plan, plan};
+    assign_stage(candidate[1], 2, false, true); assign_stage(candidate[1], 1, true, true); assign_stage(candidate[1], 0, true, true);
+    assign_stage(candidate[2], 0, true, false); assign_stage(candidate[2], 1, true, true); assign_stage(candidate[2], 2, true, true);
+    for(auto &c : candidate){
+        descend(c);
+        double busy, volume;
+        cost(c, busy, volume);
+        if (better(busy, volume, best_busy, best_volume)){ plan = c; best_busy = busy; best_volume = volume; changes++; }
+    }
+    // polish: pairwise swaps that lower the busiest end (small groups only: O(n^4) box overlaps per sweep)
+    if (n <= 16){
+        for(int sweep=0; sweep<4; sweep++){
+            bool improved = false;
+            for(int t=2; t>=0; t--) for(int p=0; p<n; p++) for(int q=p+1; q<n; q++){
+                std::swap(plan.out_shape[t][p], plan.out_shape[t][q]);
+                std::swap(plan.in_shape[t+1][p], plan.in_shape[t+1][q]);
+                double busy, volume;
+                cost(plan, busy, volume);
+                if (better(busy, volume, best_busy, best_volume)){ best_busy = busy; best_volume = volume; improved = true; changes++; }
+                else{
+                    std::swap(plan.out_shape[t][p], plan.out_shape[t][q]);
+                    std::swap(plan.in_shape[t+1][p], plan.in_shape[t+1][q]);
+                }
+            }
+            if (not improved) break;
+        }
+    }
+    return changes;
+}
+
+logic_plan make_execution_plan(shape const &inboxes, shape const &outboxes, int r2c_direction, plan_options const &options, int rank, int *swaps){
+    if (swaps) *swaps = 0;
+    const char *keep = std::getenv("HEFFTE_B200_REFERENCE_PLAN");
+    if (keep != nullptr and keep[0] != '0') return make_logic_plan(inboxes, outboxes, r2c_direction, options, rank);
+    plan_options exec_options = options;
+    exec_options.use_reorder = false;
+    logic_plan plan = make_logic_plan(inboxes, outboxes, r2c_direction, exec_options, rank);
+    int const n = balance_traffic(plan, r2c_direction);
+    if (swaps) *swaps = n;
+    return plan;
 }
 
 std::vector<std::array<int, 3>> stage_grids(logic_plan const &plan){

@@ -32,6 +32,22 @@ struct logic_plan {
 // r2c_direction = -1 for complex-to-complex and real-to-real transforms
 logic_plan make_logic_plan(shape const &inboxes, shape const &outboxes, int r2c_direction, plan_options const &options, int rank);
 
+// Execution-plan refinement (not in the reference): the boxes of the three intermediate stages are permuted among the ranks
+// so that the busiest GPU of every reshape sends and receives as little as possible.  The reference assigns pencil j of
+// the last stage to rank j whatever the output bricks are (src/heffte_plan_logic.cpp:163-254); at 512^3 on 8 ranks that
+// makes 6 of the 8 ranks ship their WHOLE pencil in the last reshape (268 MB instead of 134 MB).  Results are unchanged:
+// only which rank works on which pencil.  A plan that is already balanced is returned untouched (strict improvements only).
+// Returns the number of box swaps applied.
+int balance_traffic(logic_plan &plan, int r2c_direction);
+
+// The plan a b200 transform EXECUTES: the reference's plan for the same options with two refinements that do not change
+// any result -- (1) no reorder of the intermediate boxes: the strided kernels run at the same HBM rate as the contiguous
+// ones, and without a transposition every store of a fused reshape stays a full 128-byte row on the far side of NVLink;
+// (2) balance_traffic().  HEFFTE_B200_REFERENCE_PLAN=1 in the environment returns the reference's plan unchanged.
+// The sizes a plan REPORTS (size_workspace) always come from the reference's plan.
+logic_plan make_execution_plan(shape const &inboxes, shape const &outboxes, int r2c_direction, plan_options const &options, int rank,
+                               int *swaps = nullptr);
+
 // process-grid extents of the five stages (benchmark printout, reference src/heffte_plan_logic.cpp:460-487)
 std::vector<std::array<int, 3>> stage_grids(logic_plan const &plan);
 

@@ -40,7 +40,7 @@ struct cuda_launcher {
     // kernel selection of the batched FFT (fft_host_plan.h): the instantiations live in the fft_inst_*.cu slices
     int run_pow2(bool strided, bool is_float, bool scatter, int n, fft_args const &a);
     int run_generic(bool is_float, long long blocks, int threads, size_t smem, generic_args const &g);
-    int run_real(bool is_float, bool scatter, int kind, int m, fft_args const &a);
+    int run_real(bool strided, bool is_float, bool scatter, int kind, int m, fft_args const &a);
     template<typename kernel_t, typename args_t>
     int launch3(kernel_t kernel, long long gx, long long gy, long long gz, int threads, size_t smem, args_t const &args){
         if (gx <= 0 or gy <= 0 or gz <= 0) return B200_SUCCESS;

@@ -175,10 +175,15 @@ transform3d::transform3d(transform_kind kind, box3 const &inbox, box3 const &out
     }
 
     plan_options effective = options;
-    // the cosine / sine executors work on contiguous lines only in the reference (include/heffte_plan_logic.h:206-224);
-    // ours take any stride, but keeping the forced reorder keeps the intermediate shapes identical to cufft_cos/sin
+    // the cosine / sine executors work on contiguous lines only in the reference (include/heffte_plan_logic.h:206-224), which
+    // therefore forces the reorder; the reference-shaped plan below keeps that so that the reported sizes agree
     if (kind == kind_cos or kind == kind_sin or kind == kind_cos1) effective.use_reorder = true;
-    lp = make_logic_plan(ins, outs, r2c_dir, effective, me);
+    // (1) the reference's plan, box for box: it defines what the caller sees (size_workspace, tests/test_plan_logic.py)
+    logic_plan const reference_plan = make_logic_plan(ins, outs, r2c_dir, effective, me);
+    idx ref_comm = 0, ref_temp = 0;
+    workspace_count = workspace_layout(reference_plan, ref_comm, ref_temp);
+    // (2) the plan that is executed (plan_logic.h: no reorder of the intermediate boxes, traffic balancing)
+    lp = make_execution_plan(ins, outs, r2c_dir, effective, me, &balanced_swaps);
 
     inbox_count = lp.in_shape[0][me].count();
     outbox_count = lp.out_shape[3][me].count();
@@ -190,21 +195,37 @@ transform3d::transform3d(transform_kind kind, box3 const &inbox, box3 const &out
         fwd[i] = make_reshape(lp.in_shape[i], lp.out_shape[i], me, comm);
         bwd[3-i] = make_reshape(lp.out_shape[i], lp.in_shape[i], me, comm);
     }
+    // the exchange path lays its buffers out like the reference (below); when the executed plan needs more room than the
+    // reference's (reported) workspace, the plan uses a buffer of its own instead of the caller's
+    exec_workspace_count = workspace_layout(lp, comm_count, temp_count);
+}
 
-    // workspace layout (reference include/heffte_fft3d.h:625-633, include/heffte_fft3d_r2c.h:335-339)
-    comm_count = 0;
+// workspace layout (reference include/heffte_fft3d.h:625-633, include/heffte_fft3d_r2c.h:335-339): returns the total
+idx transform3d::workspace_layout(logic_plan const &p, idx &comm_elements, idx &temp_elements) const {
+    auto moves = [&](shape const &in, shape const &out){        // same decision as make_reshape
+        if (extents_match(in, out)){
+            if (in[0].same_order(out[0])) return false;
+            if (out[me].empty()) return false;
+        }
+        return true;
+    };
+    comm_elements = 0;
+    bool last_backward = false;
     for(int i=0; i<4; i++){
-        if (fwd[i]) comm_count = std::max(comm_count, fwd[i]->workspace_count());
-        if (bwd[i]) comm_count = std::max(comm_count, bwd[i]->workspace_count());
+        if (moves(p.in_shape[i], p.out_shape[i])) comm_elements = std::max(comm_elements, p.in_shape[i][me].count() + p.out_shape[i][me].count());
+        if (moves(p.out_shape[i], p.in_shape[i])){
+            comm_elements = std::max(comm_elements, p.in_shape[i][me].count() + p.out_shape[i][me].count());
+            if (i == 0) last_backward = true;      // bwd[3]: the last reshape of the backward transform
+        }
     }
-    temp_count = 0;
+    temp_elements = 0;
     for(int i=0; i<3; i++){
-        idx boxed = (i == 0 and kind == kind_r2c) ? lp.in_shape[1][me].count() : lp.out_shape[i][me].count();
-        temp_count = std::max(temp_count, boxed);
+        idx boxed = (i == 0 and tkind == kind_r2c) ? p.in_shape[1][me].count() : p.out_shape[i][me].count();
+        temp_elements = std::max(temp_elements, boxed);
     }
     idx last_chunk = 0;
-    if (kind != kind_r2c and bwd[3]) last_chunk = (lp.out_shape[0][me].count() + 1) / 2;
-    workspace_count = comm_count + temp_count + last_chunk;
+    if (tkind != kind_r2c and last_backward) last_chunk = (p.out_shape[0][me].count() + 1) / 2;
+    return comm_elements + temp_elements + last_chunk;
 }
 
 transform3d::~transform3d(){
@@ -494,7 +515,7 @@ int transform3d::ensure_executors(int precision){
 
 void* transform3d::ensure_workspace(int precision, int batch){
     size_t const unit = (precision == B200_PREC_FLOAT ? 4 : 8) * ((tkind == kind_c2c or tkind == kind_r2c) ? 2 : 1);
-    size_t const need = static_cast<size_t>(workspace_count) * unit * static_cast<size_t>(std::max(batch, 1)) + 64;
+    size_t const need = static_cast<size_t>(std::max(workspace_count, exec_workspace_count)) * unit * static_cast<size_t>(std::max(batch, 1)) + 64;
     if (need > own_workspace_bytes){
         if (own_workspace){ cudaStreamSynchronize(cstream); cudaFree(own_workspace); own_workspace = nullptr; own_workspace_bytes = 0; }
         if (cudaMalloc(&own_workspace, need) != cudaSuccess) return nullptr;
@@ -508,7 +529,7 @@ int transform3d::forward(int precision, int batch, const void *in, void *out, vo
     int rc = ensure_executors(precision);
     if (rc) return rc;
     bool const through_peers = ensure_peer(precision);
-    if (workspace == nullptr and not through_peers){
+    if ((workspace == nullptr or exec_workspace_count > workspace_count) and not through_peers){
         workspace = ensure_workspace(precision, 1);
         if (workspace == nullptr) return fail(B200_ERR_CUDA, "cannot allocate the workspace");
     }
@@ -529,7 +550,7 @@ int transform3d::backward(int precision, int batch, const void *in, void *out, v
     int rc = ensure_executors(precision);
     if (rc) return rc;
     bool const through_peers = ensure_peer(precision);
-    if (workspace == nullptr and not through_peers){
+    if ((workspace == nullptr or exec_workspace_count > workspace_count) and not through_peers){
         workspace = ensure_workspace(precision, 1);
         if (workspace == nullptr) return fail(B200_ERR_CUDA, "cannot allocate the workspace");
     }

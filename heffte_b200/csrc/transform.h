@@ -66,6 +66,7 @@ public:
     idx size_workspace() const { return workspace_count; }
     double scale_factor(int scaling) const;
     logic_plan const& plan() const { return lp; }
+    int traffic_swaps() const { return balanced_swaps; }
     transform_kind kind() const { return tkind; }
     int r2c_direction() const { return r2c_dir; }
     cudaStream_t stream() const { return cstream; }
@@ -118,7 +119,11 @@ private:
     cudaStream_t cstream;
     logic_plan lp;
     int me;
-    idx inbox_count, outbox_count, workspace_count, comm_count, temp_count;
+    idx inbox_count, outbox_count, comm_count, temp_count;
+    idx workspace_count;            // what size_workspace() reports: the reference's figure for this geometry
+    idx exec_workspace_count;       // what the executed plan needs on the exchange path
+    int balanced_swaps = 0;         // box swaps applied by balance_traffic()
+    idx workspace_layout(logic_plan const &p, idx &comm_elements, idx &temp_elements) const;
     double base_scale;
     std::unique_ptr<reshape_op> fwd[4], bwd[4];
     b200_fft1d_plan exec[2][3];

@@ -410,6 +410,22 @@ def logic_plan(inboxes, outboxes, r2c_direction=-1, use_reorder=False, algorithm
     return shapes.reshape(8, n, 9).tolist(), fdir.tolist(), count.value
 
 
+def execution_plan(inboxes, outboxes, r2c_direction=-1, use_reorder=False, algorithm=0, use_pencils=True, subranks=-1, rank=0):
+    """Pure host planning: the plan a b200 transform executes (no reorder, traffic-balanced): (shapes[8][nranks][9], fft_direction, swaps)."""
+    lib = _lib.load()
+    n = len(inboxes)
+    ib = np.array([b.nine() for b in inboxes], dtype=np.int32).reshape(-1)
+    ob = np.array([b.nine() for b in outboxes], dtype=np.int32).reshape(-1)
+    shapes = np.zeros(8 * n * 9, dtype=np.int32)
+    fdir = np.zeros(3, dtype=np.int32)
+    swaps = np.zeros(1, dtype=np.int32)
+    rc = lib.heffte_b200_execution_plan(n, _iptr(ib), _iptr(ob), r2c_direction, int(use_reorder), algorithm, int(use_pencils), subranks, rank,
+                                        _iptr(shapes), _iptr(fdir), _iptr(swaps))
+    if rc != 0:
+        raise heffte_input_error(_lib.last_error())
+    return shapes.reshape(8, n, 9).tolist(), fdir.tolist(), int(swaps[0])
+
+
 def reshape_pieces(inboxes, outboxes, me, receive):
     lib = _lib.load()
     n = len(inboxes)

@@ -152,6 +152,13 @@ const char* heffte_last_error(void);
 int heffte_b200_logic_plan(int nranks, int const *inboxes, int const *outboxes, int r2c_direction,
                            int use_reorder, int algorithm, int use_pencils, int subranks, int rank,
                            int *shapes_out, int *fft_direction, long long *index_count);
+/* The plan a b200 transform EXECUTES for the same arguments: the reference's plan without the reorder of the intermediate boxes
+ * and with those boxes assigned to the ranks so that the busiest GPU of every reshape moves as little as possible over NVLink
+ * (csrc/plan_logic.h).  Results and reported sizes are those of the reference's plan; `swaps` receives the number of box
+ * swaps the balancing applied.  HEFFTE_B200_REFERENCE_PLAN=1 makes both plans identical. */
+int heffte_b200_execution_plan(int nranks, int const *inboxes, int const *outboxes, int r2c_direction,
+                               int use_reorder, int algorithm, int use_pencils, int subranks, int rank,
+                               int *shapes_out, int *fft_direction, int *swaps);
 /* reference include/heffte_geometry.h:337-349, 643-691, 409-436 */
 void heffte_b200_make_procgrid(int nprocs, int *grid2);
 void heffte_b200_proc_setup_min_surface(int const *world_box, int nprocs, int *grid3);

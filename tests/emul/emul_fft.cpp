@@ -21,8 +21,12 @@ struct emul_launcher {
         if (is_float) return scatter ? dispatch_contig<float, true>(n, a, *this) : dispatch_contig<float, false>(n, a, *this);
         return scatter ? dispatch_contig<double, true>(n, a, *this) : dispatch_contig<double, false>(n, a, *this);
     }
-    int run_real(bool is_float, bool scatter, int kind, int m, b200::fft_args const &a){
+    int run_real(bool strided, bool is_float, bool scatter, int kind, int m, b200::fft_args const &a){
         using namespace b200;
+        if (strided){
+            if (is_float) return scatter ? dispatch_strided_real<float, true>(kind, m, a, *this) : dispatch_strided_real<float, false>(kind, m, a, *this);
+            return scatter ? dispatch_strided_real<double, true>(kind, m, a, *this) : dispatch_strided_real<double, false>(kind, m, a, *this);
+        }
         if (is_float) return scatter ? dispatch_contig_real<float, true>(kind, m, a, *this) : dispatch_contig_real<float, false>(kind, m, a, *this);
         return scatter ? dispatch_contig_real<double, true>(kind, m, a, *this) : dispatch_contig_real<double, false>(kind, m, a, *this);
     }

@@ -62,7 +62,7 @@ def _run(emul, kind, prec, box, dim, direction, data, scale=1.0, out_box=None):
     return dst, family.value
 
 
-FAMILY = {0: "strided", 1: "contig", 2: "generic", 3: "contig_real"}
+FAMILY = {0: "strided", 1: "contig", 2: "generic", 3: "contig_real", 4: "strided_real"}
 
 
 @pytest.mark.parametrize("prec", [1, 0])
@@ -93,7 +93,11 @@ def test_c2c_kernels_emulated(emul, prec, n, order, dim, expect):
                                          # power-of-two contiguous lines: the half-length complex engine (fft_contig_real_kernel)
                                          ((32, 3, 3), (0, 1, 2), 0), ((128, 5, 1), (0, 1, 2), 0), ((256, 1, 3), (0, 1, 2), 0), ((512, 2, 1), (0, 1, 2), 0),
                                          ((1024, 1, 2), (0, 1, 2), 0), ((2048, 1, 1), (0, 1, 2), 0), ((4096, 1, 1), (0, 1, 2), 0),
-                                         ((3, 64, 2), (1, 2, 0), 1), ((2, 3, 128), (2, 0, 1), 2)])
+                                         ((3, 64, 2), (1, 2, 0), 1), ((2, 3, 128), (2, 0, 1), 2),
+                                         # power-of-two lines with adjacent neighbours: fft_strided_real_kernel
+                                         ((5, 32, 2), (0, 1, 2), 1), ((20, 3, 64), (0, 1, 2), 2), ((33, 128, 1), (0, 1, 2), 1), ((17, 2, 256), (0, 1, 2), 2),
+                                         ((9, 512, 1), (0, 1, 2), 1), ((3, 1, 1024), (0, 1, 2), 2), ((2, 2048, 1), (0, 1, 2), 1), ((2, 4096, 1), (0, 1, 2), 1),
+                                         ((64, 6, 2), (1, 0, 2), 0)])
 def test_r2c_c2r_emulated(emul, prec, n, order, dim):
     box = O.Box((0, 0, 0), tuple(v - 1 for v in n), order)
     cbox = box.r2c(dim)
@@ -102,8 +106,8 @@ def test_r2c_c2r_emulated(emul, prec, n, order, dim):
     tol = 2e-6 if prec == 0 else 1e-13
     y, fam = _run(emul, 1, prec, box, dim, 0, x, out_box=cbox)
     size = n[dim]
-    if size >= 32 and size & (size - 1) == 0 and dim == order[0]:
-        assert FAMILY[fam] == "contig_real"
+    if size >= 32 and size & (size - 1) == 0:
+        assert FAMILY[fam] == ("contig_real" if dim == order[0] else "strided_real")
     ref = O.exec1d_r2c(x, box, dim)
     assert O.rel_l2(y, ref) < tol
     z, _ = _run(emul, 1, prec, box, dim, 1, ref, out_box=cbox)
@@ -114,13 +118,18 @@ def test_r2c_c2r_emulated(emul, prec, n, order, dim):
 @pytest.mark.parametrize("kind,name", [(2, "cos"), (3, "sin"), (4, "cos1")])
 @pytest.mark.parametrize("n,order,dim", [((8, 3, 2), (0, 1, 2), 0), ((7, 3, 2), (0, 1, 2), 0), ((16, 2, 2), (0, 1, 2), 0), ((3, 9, 2), (1, 0, 2), 1), ((4, 2, 6), (2, 1, 0), 2),
                                          ((32, 3, 2), (0, 1, 2), 0), ((64, 5, 1), (0, 1, 2), 0), ((256, 3, 1), (0, 1, 2), 0), ((512, 1, 2), (0, 1, 2), 0),
-                                         ((2048, 1, 1), (0, 1, 2), 0), ((2, 128, 3), (1, 0, 2), 1)])
+                                         ((2048, 1, 1), (0, 1, 2), 0), ((2, 128, 3), (1, 0, 2), 1),
+                                         ((5, 32, 2), (0, 1, 2), 1), ((18, 2, 64), (0, 1, 2), 2), ((33, 256, 1), (0, 1, 2), 1), ((3, 1, 512), (0, 1, 2), 2),
+                                         ((2, 1024, 1), (0, 1, 2), 1), ((128, 5, 2), (2, 0, 1), 0)])
 def test_r2r_emulated(emul, prec, kind, name, n, order, dim):
     box = O.Box((0, 0, 0), tuple(v - 1 for v in n), order)
     rng = np.random.default_rng(kind * 100 + n[0])
     x = rng.random(box.count())
     tol = 1e-5 if prec == 0 else 1e-12
-    y, _ = _run(emul, kind, prec, box, dim, 0, x)
+    y, fam = _run(emul, kind, prec, box, dim, 0, x)
+    size = n[dim]
+    if kind != 4 and size >= 32 and size & (size - 1) == 0:
+        assert FAMILY[fam] == ("contig_real" if dim == order[0] else "strided_real")
     assert O.rel_l2(y, O.r2r_forward(x, box, dim, name)) < tol
     z, _ = _run(emul, kind, prec, box, dim, 1, x)
     assert O.rel_l2(z, O.r2r_backward(x, box, dim, name)) < tol

@@ -125,3 +125,59 @@ def test_large_batch_512_fp64(lib):
     x = seeded(box.count(), 2, True)
     y, _ = _exec(lib, 1, 0, box, 2, 0, x, box.count(), np.complex128)
     assert O.rel_l2(y, O.exec1d_c2c(x, box, 2)) <= TOL[1]
+
+
+# ---- power-of-two real transforms: the half-length complex engine (fft_contig_real_kernel / fft_strided_real_kernel) ----------
+REAL_POW2_CASES = [((n, 3, 5), 0, "contig_real") for n in (32, 64, 128, 256, 512, 1024, 2048, 4096)] + \
+                  [((9, n, 3), 1, "strided_real") for n in (32, 64, 128, 256, 512, 1024, 2048, 4096)] + \
+                  [((37, 2, n), 2, "strided_real") for n in (32, 256, 512)] + [((1, 1, 64), 2, "contig_real"), ((512, 1, 1), 0, "contig_real")]
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("shape,dim,family", REAL_POW2_CASES)
+def test_r2c_pow2_fast_kernels(lib, prec, shape, dim, family):
+    box = O.Box((0, 0, 0), tuple(v - 1 for v in shape))
+    rt, ct = (np.float32, np.complex64) if prec == 0 else (np.float64, np.complex128)
+    x = seeded(box.count(), 13, False).astype(rt)
+    cbox = box.r2c(dim)
+    y, name = _exec(lib, prec, 1, box, dim, 0, x, cbox.count(), ct, scale=0.5, cbox=cbox)
+    assert name == family
+    ref = O.exec1d_r2c(x, box, dim)
+    assert O.rel_l2(y, 0.5 * ref) <= TOL[prec]
+    back, _ = _exec(lib, prec, 1, box, dim, 1, ref.astype(ct), box.count(), rt, cbox=cbox)
+    assert O.rel_l2(back, O.exec1d_c2r(ref, box, dim)) <= TOL[prec]
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("kind", ["cos", "sin"])
+@pytest.mark.parametrize("shape,dim,family", REAL_POW2_CASES)
+def test_r2r_pow2_fast_kernels(lib, prec, kind, shape, dim, family):
+    box = O.Box((0, 0, 0), tuple(v - 1 for v in shape))
+    rt = np.float32 if prec == 0 else np.float64
+    x = seeded(box.count(), 17, False).astype(rt)
+    kid = {"cos": 2, "sin": 3}[kind]
+    f, name = _exec(lib, prec, kid, box, dim, 0, x, box.count(), rt)
+    assert name == family
+    assert O.rel_l2(f, O.r2r_forward(x, box, dim, kind)) <= 2 * TOL[prec]
+    b, _ = _exec(lib, prec, kid, box, dim, 1, x, box.count(), rt, scale=0.125)
+    assert O.rel_l2(b, 0.125 * O.r2r_backward(x, box, dim, kind)) <= 2 * TOL[prec]
+
+
+def test_r2c_unaligned_lines_take_the_generic_kernel(lib):
+    """a real line that does not start on a complex boundary cannot be read as pairs: the plan falls back, results unchanged"""
+    box = O.Box((0, 0, 0), (63, 2, 1))
+    x = seeded(box.count() + 1, 21, False)
+    from heffte_b200._lib import b200_fft1d_desc, b200_line_geom
+    g, ca, cb = line_geometry(box, 0)
+    cbox = box.r2c(0)
+    go = line_geometry(cbox, 0)[0]
+    d = b200_fft1d_desc(1, 1, 64, ca, cb, b200_line_geom(*g), b200_line_geom(*go))
+    plan = ctypes.c_void_p()
+    assert lib.b200_fft1d_create(ctypes.byref(d), ctypes.byref(plan)) == 0
+    xin = torch.from_numpy(x).cuda()
+    out = torch.zeros(cbox.count(), dtype=torch.complex128, device="cuda")
+    rc = lib.b200_fft1d_execute(plan, 0, ctypes.c_void_p(xin.data_ptr() + 8), ctypes.c_void_p(out.data_ptr()), ctypes.c_double(1.0), None)
+    assert rc == 0, lib.b200_last_error()
+    torch.cuda.synchronize()
+    lib.b200_fft1d_destroy(plan)
+    assert O.rel_l2(out.cpu().numpy(), O.exec1d_r2c(x[1:], box, 0)) <= TOL[1]

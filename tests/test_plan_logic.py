@@ -137,3 +137,63 @@ def test_plan_sizes_against_live_reference(lib, reference):
                 assert got[2] <= ws[rank], (n, grid, kind, reorder, pencils, rank, got, ws[rank])
                 if kind != "cos":
                     assert got[2] == ws[rank], (n, grid, kind, reorder, pencils, rank)
+
+
+def _busiest(shapes, n, elem=1):
+    """sum over the four reshapes of the most a rank sends or receives (elements)"""
+    total = 0
+    for s in range(4):
+        ins, outs = shapes[s], shapes[4 + s]
+        sent, recv = [0] * n, [0] * n
+        for r in range(n):
+            for q in range(n):
+                if q == r:
+                    continue
+                ov = 1
+                for d in range(3):
+                    ov *= max(0, min(ins[r][3 + d], outs[q][3 + d]) - max(ins[r][d], outs[q][d]) + 1)
+                sent[r] += ov
+                recv[q] += ov
+        total += max(max(sent), max(recv))
+    return total
+
+
+def test_execution_plan_never_moves_more_than_the_reference(lib):
+    """the executed plan (no reorder, traffic-balanced; csrc/plan_logic.h) keeps the in/out boxes and the index set of every stage,
+    and its busiest rank never moves more than with the reference's plan"""
+    from heffte_b200 import heffte as H
+    improved = 0
+    for n, grids in (((64, 64, 64), [(2, 2, 2), (1, 2, 4), (1, 2, 2), (1, 1, 2), (1, 2, 3), (2, 2, 3), (4, 2, 2)]), ((20, 21, 22), [(2, 2, 2), (1, 3, 2)])):
+        world = O.world_box(n)
+        for grid in grids:
+            for gout in (grid, grid[::-1]):
+                for pencils in (True, False):
+                    inboxes, outboxes = [to_h(b) for b in bricks(world, grid)], [to_h(b) for b in bricks(world, gout)]
+                    nranks = len(inboxes)
+                    ref, fdir, _ = H.logic_plan(inboxes, outboxes, use_pencils=pencils)
+                    got, fdir2, swaps = H.execution_plan(inboxes, outboxes, use_pencils=pencils)
+                    assert fdir == fdir2
+                    assert got[0] == ref[0] and got[7] == ref[7]                      # the caller's boxes stay where they are
+                    for s in range(8):                                                # every stage: the same boxes, maybe on other ranks
+                        assert sorted(map(tuple, got[s])) == sorted(map(tuple, ref[s]))
+                    for s in range(3):                                                # stage s is both an output and the next input
+                        assert [b[:6] for b in got[4 + s]] == [b[:6] for b in got[s + 1]]
+                    a, b = _busiest(got, nranks), _busiest(ref, nranks)
+                    assert a <= b
+                    improved += 1 if a < b else 0
+                    assert (swaps > 0) == (got != ref)
+    assert improved > 0
+
+
+def test_execution_plan_512_on_8_ranks(lib):
+    """512^3 on the 2x2x2 brick grid: the reference makes 6 of 8 ranks ship their whole pencil in the last reshape"""
+    from heffte_b200 import heffte as H
+    world = O.world_box((512, 512, 512))
+    boxes = [to_h(b) for b in bricks(world, (2, 2, 2))]
+    ref, _, _ = H.logic_plan(boxes, boxes)
+    got, _, swaps = H.execution_plan(boxes, boxes)
+    assert swaps > 0
+    assert _busiest(ref, 8) == 46137344 and _busiest(got, 8) <= 41943040
+    # a reorder request does not change the executed plan
+    again, _, _ = H.execution_plan(boxes, boxes, use_reorder=True)
+    assert again == got
