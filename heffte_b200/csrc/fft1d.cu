@@ -102,6 +102,14 @@ int b200_copy_on_device(const void *source, void *destination, size_t bytes, voi
     return check_cuda(cudaMemcpyAsync(destination, source, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)), "copy on device");
 }
 int b200_stream_synchronize(void *stream){ return check_cuda(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "stream synchronize"); }
+int b200_stream_create(void **stream){
+    if (stream == nullptr) return fail(B200_ERR_INVALID, "null argument");
+    cudaStream_t s = nullptr;
+    int rc = check_cuda(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreateWithFlags");
+    *stream = s;
+    return rc;
+}
+int b200_stream_destroy(void *stream){ return (stream == nullptr) ? B200_SUCCESS : check_cuda(cudaStreamDestroy(static_cast<cudaStream_t>(stream)), "cudaStreamDestroy"); }
 int b200_device_set(int device){ return check_cuda(cudaSetDevice(device), "cudaSetDevice"); }
 
 int b200_fft1d_create(const b200_fft1d_desc *desc, b200_fft1d_plan *out){

@@ -374,7 +374,7 @@ __host__ __device__ constexpr unsigned pad_index(unsigned i){ return i + (i >> 3
 
 // IN_SMEM: the first pass finds its input in the row (a prologue put it there); OUT_SMEM: the last pass leaves its output
 // in the row, natural order (an epilogue takes it from there).  Used by the real-data kernels below.
-template<typename T, typename RL, int S, int NS, int TPL, bool BWD, bool SCATTER, bool IN_SMEM = false, bool OUT_SMEM = false>
+template<typename T, typename RL, int S, int NS, int TPL, bool BWD, bool SCATTER, bool IN_SMEM = false, bool OUT_SMEM = false, bool NEGATE_UPPER = false>
 __device__ __forceinline__ void contig_pass(cplx<T> *row, unsigned j, bool valid, const cplx<T> *gin, cplx<T> *gout,
                                             long long istride, long long ostride, const cplx<T> *tw, T scale, bool do_scale,
                                             scatter_ctx const &sc){
@@ -402,7 +402,12 @@ __device__ __forceinline__ void contig_pass(cplx<T> *row, unsigned j, bool valid
             }
         }else{
             #pragma unroll
-            for(unsigned r=0; r<R; r++) v[u][r] = row[pad_index(q + r * NB)];
+            for(unsigned r=0; r<R; r++){
+                cplx<T> x = row[pad_index(q + r * NB)];
+                // DST-II (first pass only): the odd samples fill the upper half of the permuted sequence and carry a minus sign
+                if (NEGATE_UPPER && S == 0 && r >= R / 2){ x.x = -x.x; x.y = -x.y; }
+                v[u][r] = x;
+            }
         }
     }
     if constexpr (!FIRST) __syncthreads();   // every leg has been read before anybody overwrites the row
@@ -545,34 +550,63 @@ __global__ void __launch_bounds__((RL::N / RL::rmax) * LPB, MINB) fft_contig_rea
     const bool do_scale = a.scale != 1.0;
 
     // ---- prologue: build the (swapped, for the backward engine) complex input of the M-point transform in the row -------
+    // Global memory is read with asynchronous copies straight into shared memory (the whole line in flight at once).
     if constexpr (PROLOGUE){
-        if (valid){
-            if constexpr (!BWD){
-                // DCT-II / DST-II: Makhoul permutation of the real line, coalesced read, two interleaved write streams
+        if constexpr (!BWD){
+            // DCT-II / DST-II: Makhoul permutation of the real line; the sign of the sine variant rides on the first pass
+            if (valid){
+                #pragma unroll 4
                 for(unsigned i = j; i < NR; i += TPL){
-                    T x = rin[i];
-                    if (KIND == real_sin && (i & 1)) x = -x;
                     const unsigned p = (i & 1) ? NR - 1 - (i >> 1) : (i >> 1);
-                    rrow[real_pos(p)] = x;
+                    async_copy<sizeof(T)>(rrow + real_pos(p), rin + i);
                 }
-            }else{
-                for(unsigned k = j; k <= M / 2; k += TPL){
-                    cplx<T> vk, vm;     // spectrum of the real sequence at k and M-k
+            }
+            async_wait_all();
+            __syncthreads();
+        }else{
+            // stage the line as it is (M+1 complex numbers, or n reals), then every thread pulls its pairs (k, M-k) into
+            // registers, and only after a barrier writes Z_k and Z_{M-k} over them
+            if (valid){
+                if constexpr (R2C){
+                    #pragma unroll 4
+                    for(unsigned k = j; k <= M; k += TPL) async_copy<sizeof(cplx<T>)>(row + pad_index(k), cin + k);
+                }else{
+                    #pragma unroll 4
+                    for(unsigned i = j; i < NR; i += TPL) async_copy<sizeof(T)>(rrow + real_pos(i), rin + i);
+                }
+            }
+            async_wait_all();
+            __syncthreads();
+            constexpr unsigned KPT = (M / 2 + TPL) / TPL;      // pairs per thread: ceil((M/2 + 1) / TPL)
+            cplx<T> vk[KPT], vm[KPT];
+            #pragma unroll
+            for(unsigned u=0; u<KPT; u++){
+                const unsigned k = j + u * TPL;
+                if (k <= M / 2){
                     if constexpr (R2C){
-                        vk = cin[k]; vm = cin[M - k];
-                        if (k == 0){ vk.y = 0; vm.y = 0; }      // c2r ignores the imaginary part of the self-conjugate entries
+                        vk[u] = row[pad_index(k)]; vm[u] = row[pad_index(M - k)];
+                        if (k == 0){ vk[u].y = 0; vm[u].y = 0; }      // c2r ignores the imaginary part of the self-conjugate entries
                     }else{
                         T yk, ynk, ymk, ypk;   // y_k, y_{n-k}, y_{M-k}, y_{M+k} of the (reversed, for the sine) input
                         if constexpr (KIND == real_cos){
-                            yk = rin[k]; ynk = (k == 0) ? T(0) : rin[NR - k]; ymk = rin[M - k]; ypk = rin[M + k];
+                            yk = rrow[real_pos(k)]; ynk = (k == 0) ? T(0) : rrow[real_pos(NR - k)];
+                            ymk = rrow[real_pos(M - k)]; ypk = rrow[real_pos(M + k)];
                         }else{
-                            yk = rin[NR - 1 - k]; ynk = (k == 0) ? T(0) : rin[k - 1]; ymk = rin[M - 1 + k]; ypk = rin[M - 1 - k];
+                            yk = rrow[real_pos(NR - 1 - k)]; ynk = (k == 0) ? T(0) : rrow[real_pos(k - 1)];
+                            ymk = rrow[real_pos(M - 1 + k)]; ypk = rrow[real_pos(M - 1 - k)];
                         }
                         const cplx<T> wk = ldg_c<T>(tx + k), wm = ldg_c<T>(tx + (M - k));
-                        vk = cmul(mk<T>(yk, -ynk), mk<T>(wk.x, -wk.y));
-                        vm = cmul(mk<T>(ymk, -ypk), mk<T>(wm.x, -wm.y));
+                        vk[u] = cmul(mk<T>(yk, -ynk), mk<T>(wk.x, -wk.y));
+                        vm[u] = cmul(mk<T>(ymk, -ypk), mk<T>(wm.x, -wm.y));
                     }
-                    const cplx<T> A = mk<T>(vk.x + vm.x, vk.y - vm.y), B = mk<T>(vk.x - vm.x, vk.y + vm.y);
+                }
+            }
+            __syncthreads();
+            #pragma unroll
+            for(unsigned u=0; u<KPT; u++){
+                const unsigned k = j + u * TPL;
+                if (k <= M / 2){
+                    const cplx<T> A = mk<T>(vk[u].x + vm[u].x, vk[u].y - vm[u].y), B = mk<T>(vk[u].x - vm[u].x, vk[u].y + vm[u].y);
                     const cplx<T> w = ldg_c<T>(tx + 4 * k);
                     const cplx<T> wb = cmul(mk<T>(w.x, -w.y), B);         // W_n^{-k} B
                     const cplx<T> C = mk<T>(-wb.y, wb.x);                 // i W_n^{-k} B
@@ -580,15 +614,15 @@ __global__ void __launch_bounds__((RL::N / RL::rmax) * LPB, MINB) fft_contig_rea
                     if (k > 0) row[pad_index(M - k)] = mk<T>(-(A.y - C.y), A.x - C.x);    // swap(conj(A - C))
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     // ---- the M-point complex transform ---------------------------------------------------------------------------
     constexpr int P = RL::passes;
     constexpr int N1 = RL::radix(0), N2 = N1 * RL::radix(1), N3 = N2 * RL::radix(2);
     // swaps of the backward engine live in the prologue / epilogue when those exist
-    contig_pass<T, RL, 0, 1, TPL, BWD, false, PROLOGUE, (EPILOGUE && P == 1)>(row, j, valid, cin, cout, 1, 1, tw, scale, do_scale, sc);
+    contig_pass<T, RL, 0, 1, TPL, BWD, false, PROLOGUE, (EPILOGUE && P == 1), (KIND == real_sin && !BWD)>(row, j, valid, cin, cout, 1, 1, tw, scale, do_scale, sc);
     if constexpr (P > 1){
         __syncthreads();
         contig_pass<T, RL, 1, N1, TPL, BWD, false, false, (EPILOGUE && P == 2)>(row, j, valid, cin, cout, 1, 1, tw, scale, do_scale, sc);

@@ -337,16 +337,70 @@ int balance_traffic(logic_plan &plan, int r2c_direction){
     return changes;
 }
 
+// Estimated cost of executing a plan with the fused reshapes, in bytes that cross NVLink at the busiest GPU (reals of the
+// working precision count 1): every reshape that moves data costs what its busiest rank sends or receives, but never less
+// than the HBM traffic of the transform fused in front of it; a transform with nothing to fuse into, and the final copy into
+// the caller's array, cost their HBM traffic.  HBM bytes are converted with the ratio of the two rates (~770 GB/s : ~6.5 TB/s).
+double execution_cost(logic_plan const &p, int r2c_direction){
+    int const n = static_cast<int>(p.in_shape[0].size());
+    double const hbm_to_nvlink = 0.12;
+    auto weight_of = [&](int i){ return (i == 0 and r2c_direction != -1) ? 1.0 : 2.0; };
+    double total = 0;
+    for(int i=0; i<4; i++){
+        bool const moves = not (extents_match(p.in_shape[i], p.out_shape[i]) and p.in_shape[i][0].same_order(p.out_shape[i][0]));
+        double busiest = 0, largest = 0;
+        std::vector<double> out(n, 0.0), in(n, 0.0);
+        for(int r=0; r<n; r++){
+            largest = std::max(largest, weight_of(i) * static_cast<double>(p.in_shape[i][r].count()));
+            for(int q=0; q<n; q++) if (q != r){
+                double const w = weight_of(i) * static_cast<double>(p.in_shape[i][r].overlap(p.out_shape[i][q]).count());
+                out[r] += w; in[q] += w;
+            }
+        }
+        for(int r=0; r<n; r++) busiest = std::max(busiest, std::max(out[r], in[r]));
+        double const pass = hbm_to_nvlink * 2.0 * largest;            // read + write of the box in local memory
+        if (moves) total += std::max(busiest, pass);
+        else if (i > 0) total += pass;                                // transform i-1 runs alone
+        if (i == 3){
+            if (moves) total += pass;                                 // copy from the arena into the caller's array
+            // the third transform runs before reshape 3 whether or not it moves: counted above in both branches
+        }
+    }
+    return total;
+}
+
 logic_plan make_execution_plan(shape const &inboxes, shape const &outboxes, int r2c_direction, plan_options const &options, int rank, int *swaps){
     if (swaps) *swaps = 0;
     const char *keep = std::getenv("HEFFTE_B200_REFERENCE_PLAN");
     if (keep != nullptr and keep[0] != '0') return make_logic_plan(inboxes, outboxes, r2c_direction, options, rank);
-    plan_options exec_options = options;
-    exec_options.use_reorder = false;
-    logic_plan plan = make_logic_plan(inboxes, outboxes, r2c_direction, exec_options, rank);
-    int const n = balance_traffic(plan, r2c_direction);
-    if (swaps) *swaps = n;
-    return plan;
+    // both decompositions are planned (pencils: three exchanges of part of the data; slabs: two exchanges of more of it) and
+    // the cheaper one by execution_cost() runs; the caller's use_pencils decides ties.  HEFFTE_B200_DECOMPOSITION=pencils|slabs
+    // forces one of them.
+    const char *forced = std::getenv("HEFFTE_B200_DECOMPOSITION");
+    logic_plan best;
+    double best_cost = -1;
+    int best_swaps = 0;
+    for(int attempt=0; attempt<2; attempt++){
+        plan_options exec_options = options;
+        exec_options.use_reorder = false;
+        if (attempt == 1) exec_options.use_pencils = not options.use_pencils;
+        if (forced != nullptr and (forced[0] == 'p' or forced[0] == 's')){
+            if (attempt == 1) break;
+            exec_options.use_pencils = (forced[0] == 'p');
+        }
+        if (attempt == 1 and options.subranks > 0) break;     // sub-communicator plans keep the caller's decomposition
+        try{
+            logic_plan plan = make_logic_plan(inboxes, outboxes, r2c_direction, exec_options, rank);
+            int const n = balance_traffic(plan, r2c_direction);
+            double const c = execution_cost(plan, r2c_direction);
+            if (best_cost < 0 or c < best_cost * (1.0 - 1e-9)){ best = plan; best_cost = c; best_swaps = n + ((attempt == 1) ? 1 : 0); }
+        }catch(std::exception &){
+            if (attempt == 0) throw;
+        }
+    }
+    best.options.use_pencils = options.use_pencils;
+    if (swaps) *swaps = best_swaps;
+    return best;
 }
 
 std::vector<std::array<int, 3>> stage_grids(logic_plan const &plan){

@@ -43,8 +43,11 @@ int balance_traffic(logic_plan &plan, int r2c_direction);
 // The plan a b200 transform EXECUTES: the reference's plan for the same options with two refinements that do not change
 // any result -- (1) no reorder of the intermediate boxes: the strided kernels run at the same HBM rate as the contiguous
 // ones, and without a transposition every store of a fused reshape stays a full 128-byte row on the far side of NVLink;
-// (2) balance_traffic().  HEFFTE_B200_REFERENCE_PLAN=1 in the environment returns the reference's plan unchanged.
+// (2) balance_traffic(); (3) the decomposition -- pencils or slabs -- that moves the least over NVLink at the busiest GPU
+// (execution_cost(); the caller's use_pencils decides ties; HEFFTE_B200_DECOMPOSITION=pencils|slabs forces one).
+// HEFFTE_B200_REFERENCE_PLAN=1 in the environment returns the reference's plan unchanged.
 // The sizes a plan REPORTS (size_workspace) always come from the reference's plan.
+double execution_cost(logic_plan const &plan, int r2c_direction);
 logic_plan make_execution_plan(shape const &inboxes, shape const &outboxes, int r2c_direction, plan_options const &options, int rank,
                                int *swaps = nullptr);
 

@@ -158,6 +158,11 @@ transform3d::transform3d(transform_kind kind, box3 const &inbox, box3 const &out
     for(int p=0; p<2; p++) for(int i=0; i<3; i++) exec[p][i] = nullptr;
     me = comm->rank();
     int const n = comm->size();
+#ifndef B200_HOST_EMULATION
+    // ranks that share one process share the default stream: the stream-ordered barrier between them could never complete
+    if (n > 1 and stream == nullptr and std::strcmp(comm->kind(), "threads") == 0)
+        throw std::runtime_error("ranks that are host threads of one process need one CUDA stream per rank (create the plan on a stream)");
+#endif
 
     // plan-time allgather of (inbox, outbox): 18 64-bit integers per rank (reference include/heffte_geometry.h:707-718)
     std::vector<long long> mine(18), all(18 * static_cast<size_t>(n));

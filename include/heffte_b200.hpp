@@ -205,6 +205,19 @@ namespace gpu {
         }
         template<typename T> static std::vector<T> unload(vector<T> const &device){ return unload(nullptr, device); }
     };
+    //! RAII non-blocking CUDA stream for callers that do not include the CUDA headers; ranks that are host threads of one
+    //! process (comm::threads) must give every rank its own stream
+    class stream {
+    public:
+        stream() : handle(nullptr){ b200_detail::check(b200_stream_create(&handle), "b200_stream_create"); }
+        stream(stream const&) = delete;
+        stream& operator = (stream const&) = delete;
+        ~stream(){ if (handle) b200_stream_destroy(handle); }
+        void* get() const { return handle; }
+        void synchronize() const { b200_detail::check(b200_stream_synchronize(handle), "b200_stream_synchronize"); }
+    private:
+        void *handle;
+    };
     inline int device_count(){ return b200_device_count(); }
     inline void device_set(int device){ b200_detail::check(b200_device_set(device), "b200_device_set"); }
     inline void synchronize_default_stream(){ b200_detail::check(b200_stream_synchronize(nullptr), "b200_stream_synchronize"); }
@@ -217,7 +230,9 @@ namespace b200_detail {
     public:
         plan_base(plan_base const&) = delete;
         plan_base& operator = (plan_base const&) = delete;
-        plan_base(plan_base &&other) noexcept : plan(other.plan){ other.plan = nullptr; }
+        plan_base(plan_base &&other) noexcept : plan(other.plan), cstream(other.cstream){ other.plan = nullptr; }
+        //! the CUDA stream of the plan (cudaStream_t as void*, null = default stream)
+        void* stream() const { return cstream; }
         ~plan_base(){ if (plan) heffte_plan_destroy(plan); }
         //! number of entries of the input / output / workspace arrays (in units of the respective element type)
         size_t size_inbox() const { return static_cast<size_t>(heffte_size_inbox64(plan)); }
@@ -228,7 +243,7 @@ namespace b200_detail {
         bool uses_peer_memory(int precision = B200_PREC_DOUBLE) const { return heffte_b200_uses_peer_memory(plan, precision) == 1; }
     protected:
         plan_base(int backend_id, void *stream, box3d<index> const &inbox, box3d<index> const &outbox, int r2c_direction, comm const &c, plan_options const &o)
-            : plan(nullptr){
+            : plan(nullptr), cstream(stream){
             int const lo_in[3] = {static_cast<int>(inbox.low[0]), static_cast<int>(inbox.low[1]), static_cast<int>(inbox.low[2])};
             int const hi_in[3] = {static_cast<int>(inbox.high[0]), static_cast<int>(inbox.high[1]), static_cast<int>(inbox.high[2])};
             int const lo_out[3] = {static_cast<int>(outbox.low[0]), static_cast<int>(outbox.low[1]), static_cast<int>(outbox.low[2])};
@@ -242,6 +257,7 @@ namespace b200_detail {
             check(heffte_execute(plan, precision, direction, batch, input, output, workspace, static_cast<int>(scaling)), "heffte::fft3d (b200) transform");
         }
         heffte_plan plan;
+        void *cstream;
     };
 }
 
@@ -278,9 +294,9 @@ public:
         if (is_fft and not b200_detail::is_complex<input_type>::value){
             // real input of a complex plan: promote with a zero imaginary part (reference cufft executor, heffte_backend_cuda.h:527-536)
             gpu::vector<output_type> promoted(batch_size * this->size_inbox());
-            b200_detail::check(b200_convert_r2c(prec, static_cast<long long>(promoted.size()), input, promoted.data(), nullptr), "b200_convert_r2c");
+            b200_detail::check(b200_convert_r2c(prec, static_cast<long long>(promoted.size()), input, promoted.data(), this->stream()), "b200_convert_r2c");
             this->execute(prec, B200_FORWARD, batch_size, promoted.data(), output, workspace, scaling);
-            b200_detail::check(b200_stream_synchronize(nullptr), "b200_stream_synchronize");
+            b200_detail::check(b200_stream_synchronize(this->stream()), "b200_stream_synchronize");
         }else{
             this->execute(prec, B200_FORWARD, batch_size, input, output, workspace, scaling);
         }
@@ -299,8 +315,8 @@ public:
         if (is_fft and not b200_detail::is_complex<output_type>::value){
             gpu::vector<input_type> full(batch_size * this->size_inbox());
             this->execute(prec, B200_BACKWARD, batch_size, input, full.data(), workspace, scaling);
-            b200_detail::check(b200_convert_c2r(prec, static_cast<long long>(full.size()), full.data(), output, nullptr), "b200_convert_c2r");
-            b200_detail::check(b200_stream_synchronize(nullptr), "b200_stream_synchronize");
+            b200_detail::check(b200_convert_c2r(prec, static_cast<long long>(full.size()), full.data(), output, this->stream()), "b200_convert_c2r");
+            b200_detail::check(b200_stream_synchronize(this->stream()), "b200_stream_synchronize");
         }else{
             this->execute(prec, B200_BACKWARD, batch_size, input, output, workspace, scaling);
         }

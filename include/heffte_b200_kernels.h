@@ -56,6 +56,11 @@ int b200_copy_to_device(const void *host, void *device, size_t bytes, void *stre
 int b200_copy_to_host(const void *device, void *host, size_t bytes, void *stream);
 int b200_copy_on_device(const void *source, void *destination, size_t bytes, void *stream);
 int b200_stream_synchronize(void *stream);
+/* a non-blocking CUDA stream (cudaStream_t as void*).  Ranks that are host threads of one process (heffte_comm_create_threads)
+ * need ONE STREAM PER RANK: the stream-ordered barrier between the ranks of a plan cannot complete on a shared stream.
+ * Replaces the stream handling of heffte::backend::device_instance<tag::gpu> (include/heffte_backend_cuda.h:201-215). */
+int b200_stream_create(void **stream);
+int b200_stream_destroy(void *stream);
 int b200_device_set(int device);
 
 /*

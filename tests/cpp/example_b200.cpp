@@ -18,18 +18,20 @@ void compute_dft(heffte::comm const &comm){
     heffte::box3d<> const left_box  = {{0, 0, 0}, {3, 3, 1}};
     heffte::box3d<> const right_box = {{0, 0, 2}, {3, 3, 3}};
     heffte::box3d<> const my_box = (me == 0) ? left_box : right_box;
+    // ranks that are threads of one process: one CUDA stream per rank (the barrier between the ranks is stream ordered)
+    heffte::gpu::stream stream;
 
-    heffte::fft3d<backend_tag> fft(my_box, my_box, comm);
+    heffte::fft3d<backend_tag> fft(stream.get(), my_box, my_box, comm);
     if (fft.size_inbox() != 32 or fft.size_outbox() != 32 or fft.size_workspace() < 32){ std::printf("rank %d: wrong sizes\n", me); failures++; return; }
 
     std::vector<std::complex<double>> input(fft.size_inbox());
     std::iota(input.begin(), input.end(), 0);
-    heffte::gpu::vector<std::complex<double>> gpu_input = heffte::gpu::transfer().load(input);
+    heffte::gpu::vector<std::complex<double>> gpu_input = heffte::gpu::transfer().load(stream.get(), input);
     heffte::gpu::vector<std::complex<double>> gpu_output(fft.size_outbox());
     heffte::fft3d<backend_tag>::buffer_container<std::complex<double>> workspace(fft.size_workspace());
 
     fft.forward(gpu_input.data(), gpu_output.data(), workspace.data());
-    std::vector<std::complex<double>> spectrum = heffte::gpu::transfer::unload(gpu_output);
+    std::vector<std::complex<double>> spectrum = heffte::gpu::transfer::unload(stream.get(), gpu_output);
     // test/test_c.c:47-74
     std::vector<std::complex<double>> expect(32, 0.0);
     if (me == 0){
@@ -40,30 +42,30 @@ void compute_dft(heffte::comm const &comm){
     for(size_t i=0; i<32; i++) err = std::max(err, std::abs(spectrum[i] - expect[i]));
 
     heffte::gpu::vector<std::complex<double>> gpu_inverse = fft.backward(gpu_output, heffte::scale::full);
-    std::vector<std::complex<double>> inverse = heffte::gpu::transfer::unload(gpu_inverse);
+    std::vector<std::complex<double>> inverse = heffte::gpu::transfer::unload(stream.get(), gpu_inverse);
     for(size_t i=0; i<input.size(); i++) err = std::max(err, std::abs(inverse[i] - input[i]));
 
     // real-to-complex along dimension 2 (test/test_c.c:180-227): rank 0 keeps planes k = 0..1 of the 3 complex planes, rank 1 keeps k = 2
     heffte::box3d<> const cbox = (me == 0) ? heffte::box3d<>({0, 0, 0}, {3, 3, 1}) : heffte::box3d<>({0, 0, 2}, {3, 3, 2});
-    heffte::fft3d_r2c<backend_tag> rfft(my_box, cbox, 2, comm);
+    heffte::fft3d_r2c<backend_tag> rfft(stream.get(), my_box, cbox, 2, comm);
     if (rfft.size_outbox() != (me == 0 ? 32u : 16u)){ std::printf("rank %d: wrong r2c sizes\n", me); failures++; }
     std::vector<float> rinput(32);
     std::iota(rinput.begin(), rinput.end(), 0.0f);
-    auto gpu_rin = heffte::gpu::transfer::load(rinput);
+    auto gpu_rin = heffte::gpu::transfer::load(stream.get(), rinput);
     auto gpu_rout = rfft.forward(gpu_rin);
     auto gpu_rback = rfft.backward(gpu_rout, heffte::scale::full);
-    std::vector<float> rback = heffte::gpu::transfer::unload(gpu_rback);
+    std::vector<float> rback = heffte::gpu::transfer::unload(stream.get(), gpu_rback);
     double rerr = 0.0;
     for(size_t i=0; i<32; i++) rerr = std::max(rerr, std::abs(double(rback[i]) - double(rinput[i])));
 
     // cosine transform (examples/heffte_example_r2r.cpp): forward with full scaling, then backward, returns the input
-    heffte::fft3d<heffte::backend::b200_cos> cfft(my_box, my_box, comm);
+    heffte::fft3d<heffte::backend::b200_cos> cfft(stream.get(), my_box, my_box, comm);
     std::vector<double> dinput(32);
     std::iota(dinput.begin(), dinput.end(), 1.0);
-    auto gpu_din = heffte::gpu::transfer::load(dinput);
+    auto gpu_din = heffte::gpu::transfer::load(stream.get(), dinput);
     auto gpu_dct = cfft.forward(gpu_din, heffte::scale::full);
     auto gpu_dback = cfft.backward(gpu_dct);
-    std::vector<double> dback = heffte::gpu::transfer::unload(gpu_dback);
+    std::vector<double> dback = heffte::gpu::transfer::unload(stream.get(), gpu_dback);
     double derr = 0.0;
     for(size_t i=0; i<32; i++) derr = std::max(derr, std::abs(dback[i] - dinput[i]));
 

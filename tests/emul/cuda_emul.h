@@ -98,6 +98,9 @@ inline cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, int
 inline cudaError_t cudaMemcpyPeerAsync(void *dst, int, const void *src, int, size_t bytes, cudaStream_t){ std::memmove(dst, src, bytes); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *dst, int value, size_t bytes){ std::memset(dst, value, bytes); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t){ return cudaSuccess; }
+enum { cudaStreamNonBlocking = 1 };
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned){ static char token[64]; static int next = 0; *s = token + (next++ % 64); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t){ return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize(){ return cudaSuccess; }
 inline cudaError_t cudaGetLastError(){ return cudaSuccess; }
 inline cudaError_t cudaPeekAtLastError(){ return cudaSuccess; }

@@ -158,7 +158,7 @@ def _busiest(shapes, n, elem=1):
     return total
 
 
-def test_execution_plan_never_moves_more_than_the_reference(lib):
+def test_execution_plan_never_moves_more_than_the_reference(lib, monkeypatch):
     """the executed plan (no reorder, traffic-balanced; csrc/plan_logic.h) keeps the in/out boxes and the index set of every stage,
     and its busiest rank never moves more than with the reference's plan"""
     from heffte_b200 import heffte as H
@@ -171,7 +171,13 @@ def test_execution_plan_never_moves_more_than_the_reference(lib):
                     inboxes, outboxes = [to_h(b) for b in bricks(world, grid)], [to_h(b) for b in bricks(world, gout)]
                     nranks = len(inboxes)
                     ref, fdir, _ = H.logic_plan(inboxes, outboxes, use_pencils=pencils)
+                    # free choice of the decomposition: never worse than the caller's
+                    free, _, _ = H.execution_plan(inboxes, outboxes, use_pencils=pencils)
+                    assert free[0] == ref[0] and free[7] == ref[7]
+                    # the caller's decomposition, balanced
+                    monkeypatch.setenv("HEFFTE_B200_DECOMPOSITION", "pencils" if pencils else "slabs")
                     got, fdir2, swaps = H.execution_plan(inboxes, outboxes, use_pencils=pencils)
+                    monkeypatch.delenv("HEFFTE_B200_DECOMPOSITION")
                     assert fdir == fdir2
                     assert got[0] == ref[0] and got[7] == ref[7]                      # the caller's boxes stay where they are
                     for s in range(8):                                                # every stage: the same boxes, maybe on other ranks
@@ -185,7 +191,7 @@ def test_execution_plan_never_moves_more_than_the_reference(lib):
     assert improved > 0
 
 
-def test_execution_plan_512_on_8_ranks(lib):
+def test_execution_plan_512_on_8_ranks(lib, monkeypatch):
     """512^3 on the 2x2x2 brick grid: the reference makes 6 of 8 ranks ship their whole pencil in the last reshape"""
     from heffte_b200 import heffte as H
     world = O.world_box((512, 512, 512))
@@ -194,6 +200,14 @@ def test_execution_plan_512_on_8_ranks(lib):
     got, _, swaps = H.execution_plan(boxes, boxes)
     assert swaps > 0
     assert _busiest(ref, 8) == 46137344 and _busiest(got, 8) <= 41943040
+    monkeypatch.setenv("HEFFTE_B200_DECOMPOSITION", "pencils")
+    pencils, _, _ = H.execution_plan(boxes, boxes)
+    assert _busiest(got, 8) <= _busiest(pencils, 8) <= 41943040
+    monkeypatch.setenv("HEFFTE_B200_REFERENCE_PLAN", "1")
+    same, _, swaps = H.execution_plan(boxes, boxes)
+    assert same == ref and swaps == 0
+    monkeypatch.delenv("HEFFTE_B200_REFERENCE_PLAN")
+    monkeypatch.delenv("HEFFTE_B200_DECOMPOSITION")
     # a reorder request does not change the executed plan
     again, _, _ = H.execution_plan(boxes, boxes, use_reorder=True)
     assert again == got
