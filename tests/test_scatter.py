@@ -76,44 +76,55 @@ def test_fft_with_fused_reshape(emul, prec, case):  # noqa: F811
                 assert O.rel_l2(got[:b.count()], O.get_subbox(world, b, expect_world)) < (3e-6 if prec == 0 else 1e-13)
 
 
-@pytest.mark.parametrize("kind", ["r2c", "c2r", "cos"])
-def test_real_transforms_with_fused_reshape(emul, kind):  # noqa: F811
+@pytest.mark.parametrize("prec", [1, 0])
+@pytest.mark.parametrize("n,dim,src_grid,dst_grid", [
+    ((12, 6, 5), 0, (1, 2, 2), (3, 1, 2)),      # generic kernel
+    ((64, 6, 5), 0, (1, 2, 2), (3, 1, 2)),      # fft_contig_real_kernel, scatter variant
+    ((6, 64, 4), 1, (2, 1, 2), (1, 3, 2)),      # fft_strided_real_kernel (middle axis), scatter variant
+    ((5, 3, 32), 2, (2, 2, 1), (1, 1, 3)),      # fft_strided_real_kernel (slow axis), scatter variant
+    ((40, 128, 1), 1, (3, 1, 1), (2, 2, 1)),    # more lines than one tile row, ragged last tile
+])
+@pytest.mark.parametrize("kind", ["r2c", "c2r", "cos", "sin", "cos_b", "sin_b"])
+def test_real_transforms_with_fused_reshape(emul, kind, n, dim, src_grid, dst_grid, prec):  # noqa: F811
     from heffte_b200 import _lib
-    n, dim = (12, 6, 5), 0
     world = O.world_box(n)
     cworld = world.r2c(dim)
     rng = np.random.default_rng(1)
+    rdt, cdt = (np.float32, np.complex64) if prec == 0 else (np.float64, np.complex128)
     if kind == "r2c":
         x = rng.random(world.count())
-        src_boxes, dst_world = bricks(world, (1, 2, 2)), cworld
+        src_boxes, dst_world = bricks(world, src_grid), cworld
         expect_world = O.exec1d_r2c(x, world, dim)
-        in_world, in_dtype, out_dtype, kcode, direction = world, np.float64, np.complex128, 1, 0
+        in_world, in_dtype, out_dtype, kcode, direction = world, rdt, cdt, 1, 0
     elif kind == "c2r":
         x = O.exec1d_r2c(rng.random(world.count()), world, dim)
-        src_boxes, dst_world = bricks(cworld, (1, 2, 2)), world
+        src_boxes, dst_world = bricks(cworld, src_grid), world
         expect_world = O.exec1d_c2r(x, world, dim)
-        in_world, in_dtype, out_dtype, kcode, direction = cworld, np.complex128, np.float64, 1, 1
+        in_world, in_dtype, out_dtype, kcode, direction = cworld, cdt, rdt, 1, 1
     else:
+        name, backward = kind[:3], kind.endswith("_b")
         x = rng.random(world.count())
-        src_boxes, dst_world = bricks(world, (1, 2, 2)), world
-        expect_world = O.r2r_forward(x, world, dim, "cos")
-        in_world, in_dtype, out_dtype, kcode, direction = world, np.float64, np.float64, 2, 0
-    dst_boxes = bricks(dst_world, (3, 1, 2))
+        src_boxes, dst_world = bricks(world, src_grid), world
+        expect_world = O.r2r_backward(x, world, dim, name) if backward else O.r2r_forward(x, world, dim, name)
+        in_world, in_dtype, out_dtype, kcode, direction = world, rdt, rdt, {"cos": 2, "sin": 3}[name], int(backward)
+    dst_boxes = bricks(dst_world, dst_grid)
     outs = [np.zeros(max(b.count(), 1), dtype=out_dtype) for b in dst_boxes]
     for me, box in enumerate(src_boxes):
         local = np.ascontiguousarray(O.get_subbox(in_world, box, x).astype(in_dtype))
         # the descriptor always speaks about the REAL box; the scatter map about the box the kernel writes
-        rbox = O.Box(box.low, (world.high[0],) + box.high[1:], box.order) if kind == "c2r" else box
+        high = list(box.high)
+        high[dim] = world.high[dim]
+        rbox = O.Box(box.low, tuple(high), box.order) if kind == "c2r" else box
         cbox = rbox.r2c(dim)
         gi, ca, cb = unlumped_geometry(rbox, dim)
         go = unlumped_geometry(cbox, dim)[0] if kcode == 1 else gi
-        d = _lib.b200_fft1d_desc(1, kcode, rbox.size[dim], ca, cb, _lib.b200_line_geom(*gi), _lib.b200_line_geom(*go))
-        written = rbox if kind in ("c2r", "cos") else cbox
+        d = _lib.b200_fft1d_desc(prec, kcode, rbox.size[dim], ca, cb, _lib.b200_line_geom(*gi), _lib.b200_line_geom(*go))
+        written = cbox if kind == "r2c" else rbox
         rc = emul.emul_fft1d_reshape(ctypes.byref(d), direction, local.ctypes.data, _nine([written]).ctypes.data, dim, len(dst_boxes),
                                      _nine(dst_boxes).ctypes.data, _bases(outs), np.dtype(out_dtype).itemsize, ctypes.c_double(1.0))
         assert rc == 0
     for b, got in zip(dst_boxes, outs):
-        assert O.rel_l2(got[:b.count()], O.get_subbox(dst_world, b, expect_world)) < 1e-13
+        assert O.rel_l2(got[:b.count()], O.get_subbox(dst_world, b, expect_world)) < (1e-5 if prec == 0 else 1e-12)
 
 
 @pytest.mark.parametrize("elem", [np.float32, np.float64, np.complex128])
