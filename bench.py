@@ -37,7 +37,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, nargs=3, default=[512, 512, 512])
     ap.add_argument("--precision", default="double", choices=["float", "double"])
-    ap.add_argument("--kind", default="c2c", choices=["c2c", "r2c", "r2r"], help="r2r = DCT-II / DCT-III (speed3d_r2r ... cos)")
+    ap.add_argument("--kind", default="c2c", choices=["c2c", "r2c", "r2r", "conv"],
+                    help="r2r = DCT-II / DCT-III (speed3d_r2r ... cos); conv = benchmarks/convolution.cpp: forward(scale full), x *= x, backward, c2c in place")
     ap.add_argument("--reorder", action="store_true")
     ap.add_argument("--slabs", action="store_true")
     ap.add_argument("--io-pencils", action="store_true", help="pencil-shaped in/out boxes (speed3d -io_pencils)")
@@ -266,8 +267,12 @@ def b200_arm(args):
     reference_copy = data_in.clone()
     work = torch.empty(fft.size_workspace(), dtype=rdtype if r2r else cdtype, device="cuda")
 
+    conv = args.kind == "conv"
+
     def step():
         fft.forward_buffered(data_in, data_out, work, hf.scale.full)
+        if conv:
+            data_out.mul_(data_out)      # the caller's pointwise product in spectral space (benchmarks/convolution.cpp:89-94)
         fft.backward_buffered(data_out, data_in, work, hf.scale.none)
 
     def barrier():
@@ -279,7 +284,7 @@ def b200_arm(args):
         step()
     barrier()
     # accuracy of the round trip (benchmarks/speed3d.h:213-220)
-    err = float((data_in - reference_copy).abs().max().item())
+    err = float((data_in - reference_copy).abs().max().item()) if not conv else float("nan")
     data_in.copy_(reference_copy)
 
     sampler = ClockSampler(local_rank)
@@ -309,7 +314,7 @@ def b200_arm(args):
 
     # ---- end to end: host buffers in, host buffers out, through the public plan API ---------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not conv:
         real_bytes = 4 if prec == 0 else 8
         host_in = torch.empty(nin if r2c else max(nin, nout), dtype=rdtype if (r2c or r2r) else cdtype).pin_memory()
         host_mid = torch.empty(nout if r2c else max(nin, nout), dtype=rdtype if r2r else cdtype).pin_memory()
@@ -378,7 +383,7 @@ def b200_arm(args):
         stage_box = [int(v) for v in inbox.size]
         if world_size > 1:
             stage_box = None  # stage boxes differ per stage; report per-stage numbers only on one GPU
-        if stage_box is not None:
+        if stage_box is not None and not conv:
             n0, n1, n2 = stage_box
             rsize = 4 if prec == 0 else 8
             csize = 2 * rsize
@@ -465,7 +470,7 @@ def b200_arm(args):
 
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample ------------------------------
     cpu = None
-    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline and not conv:
         size = args.cpu_size or args.size
         r = run_reference_speed3d(args.kind, args.precision, size, 1)
         if r is not None and "error" not in r:
@@ -485,7 +490,7 @@ def b200_arm(args):
                            "slabs" if args.slabs else "pencils"),
                        "l2": "working set %.0f MB per GPU exceeds the 126 MB L2" % (max(nin, nout) * (8 if prec == 0 else 16) / 1e6),
                        "comm": ("peer memory: NVLink stores fused into the FFT kernels" if (multi and multi["peer_memory"]) else "nccl send/recv") if distributed else "none"},
-            "max_roundtrip_error": err,
+            "max_roundtrip_error": None if conv else err,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": e2e,

@@ -22,6 +22,15 @@ int b200_direct_unpack(int elem_bytes, long long nfast, long long nmid, long lon
     return (rc == B200_ERR_INVALID) ? fail(rc, "element size must be 4, 8 or 16 bytes") : rc;
 }
 
+int b200_copy_subbox(int elem_bytes, long long nfast, long long nmid, long long nslow,
+                     long long src_line_stride, long long src_plane_stride, long long dst_line_stride, long long dst_plane_stride,
+                     const void *src, void *dst, void *stream){
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    copy3d_args a{src, dst, nfast, nmid, nslow, src_line_stride, src_plane_stride, dst_line_stride, dst_plane_stride};
+    int rc = launch_copy3d(elem_bytes, a, L);
+    return (rc == B200_ERR_INVALID) ? fail(rc, "element size must be 4, 8 or 16 bytes") : rc;
+}
+
 int b200_transpose_unpack(int elem_bytes, long long nfast, long long nmid, long long nslow,
                           long long line_stride, long long plane_stride,
                           long long buff_line_stride, long long buff_plane_stride,

@@ -1,6 +1,7 @@
 #include "transform.h"
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -299,6 +300,7 @@ bool transform3d::ensure_peer(int precision){
 
     // scatter maps: ((direction * 4 + stage) * 2 + buffer)
     std::vector<scatter_map> maps(16);
+    std::vector<int> owners(16 * scatter_max_cells, -1);
     std::string why;
     int built = 1;
     for(int dir=0; dir<2 and built; dir++){
@@ -323,11 +325,12 @@ bool transform3d::ensure_peer(int precision){
             for(int w=0; w<2; w++){
                 std::vector<void*> bases(n);
                 for(int r=0; r<n; r++) bases[r] = static_cast<char*>(arenas[r]) + 4096 + static_cast<size_t>(w) * P.buffer_bytes;
-                if (not build_scatter_map(written, k_pos, dest, bases, bytes, maps[(dir * 4 + st) * 2 + w], why)){ built = 0; break; }
+                if (not build_scatter_map(written, k_pos, dest, bases, bytes, maps[(dir * 4 + st) * 2 + w], why,
+                                          owners.data() + static_cast<size_t>((dir * 4 + st) * 2 + w) * scatter_max_cells)){ built = 0; break; }
             }
         }
     }
-    if (built and cudaMalloc(&P.maps, maps.size() * sizeof(scatter_map)) != cudaSuccess){ P.maps = nullptr; cudaGetLastError(); built = 0; }
+    if (built and cudaMalloc(&P.maps, (maps.size() + 2) * sizeof(scatter_map)) != cudaSuccess){ P.maps = nullptr; cudaGetLastError(); built = 0; }
     if (built and cudaMemcpy(P.maps, maps.data(), maps.size() * sizeof(scatter_map), cudaMemcpyHostToDevice) != cudaSuccess) built = 0;
     {
         std::vector<int> votes(n);
@@ -341,6 +344,8 @@ bool transform3d::ensure_peer(int precision){
         if (P.maps){ cudaFree(P.maps); P.maps = nullptr; }
         return false;
     }
+    P.host_maps = maps;
+    P.owners = owners;
     P.active = true;
     return true;
 }
@@ -412,6 +417,10 @@ int transform3d::run_peer(int precision, bool is_backward, const void *in, void 
         return (output != is_backward) ? cplx_bytes : real_bytes;   // r2c forward writes complex, c2r backward writes real
     };
 
+    // the last reshape can deliver my own part straight into the caller's array (not for the real output of a c2r transform
+    // that still has complex stages in the arena: there the arena element type differs only before stage 3, which is fine)
+    bool const direct_local = P.fused[dir][3] and std::getenv("HEFFTE_B200_NO_DIRECT_OUTPUT") == nullptr;
+    bool landed_direct = false;
     const void *cur = in;
     int cur_buffer = -1;             // -1: caller memory
     if (P.fused[dir][0]){
@@ -435,8 +444,27 @@ int transform3d::run_peer(int precision, bool is_backward, const void *in, void 
         if (P.fused[dir][st]){
             int const w = (cur_buffer < 0) ? 0 : (cur_buffer ^ 1);
             if (touched & (1u << w)){ rc = peer_fence(precision); if (rc) return rc; touched = 0; }
+            const void *stage_map = map_of(st, w);
+            if (st == 3 and direct_local){
+                // last stage: the part of my output that I produce myself goes straight into the caller's array (the cells of the
+                // map that point into my own arena are re-based); only what the other GPUs send lands in the arena
+                if (P.patched_out[dir] != out or P.patched_buffer[dir] != w){
+                    scatter_map patched = P.host_maps[(dir * 4 + 3) * 2 + w];
+                    long long const arena_base = static_cast<long long>(reinterpret_cast<intptr_t>(P.buffer(w)));
+                    const int *owner = P.owners.data() + static_cast<size_t>((dir * 4 + 3) * 2 + w) * scatter_max_cells;
+                    for(int c=0; c<patched.ncells; c++)
+                        if (owner[c] == me) patched.cell[c].base += static_cast<long long>(reinterpret_cast<intptr_t>(out)) - arena_base;
+                    char *slot = static_cast<char*>(P.maps) + sizeof(scatter_map) * static_cast<size_t>(16 + dir);
+                    if (cudaMemcpyAsync(slot, &patched, sizeof(scatter_map), cudaMemcpyHostToDevice, cstream) != cudaSuccess)
+                        return fail(B200_ERR_CUDA, "cudaMemcpyAsync failed (scatter map)");
+                    if (cudaStreamSynchronize(cstream) != cudaSuccess) return fail(B200_ERR_CUDA, "stream synchronisation failed");   // `patched` is a local
+                    P.patched_out[dir] = out; P.patched_buffer[dir] = w;
+                }
+                stage_map = static_cast<const char*>(P.maps) + sizeof(scatter_map) * static_cast<size_t>(16 + dir);
+                landed_direct = true;
+            }
             if (X[e]){
-                rc = b200_fft1d_execute_scatter(X[e], direction, cur, map_of(st, w), stage_scale, cstream);
+                rc = b200_fft1d_execute_scatter(X[e], direction, cur, stage_map, stage_scale, cstream);
                 if (rc) return rc;
             }
             {
@@ -477,7 +505,25 @@ int transform3d::run_peer(int precision, bool is_backward, const void *in, void 
             cur = dst; cur_buffer = dst_buffer;     // also without a transform (empty box): every rank follows the same buffers
         }
     }
-    if (cur != out){
+    if (cur != out and landed_direct){
+        // what the other GPUs sent sits in the arena at its final position inside my box: move those sub-boxes only
+        bool const real_out = (tkind == kind_r2c and is_backward) or not complex_data;
+        int const elem = real_out ? real_bytes : cplx_bytes;
+        shape const &from = is_backward ? lp.out_shape[0] : lp.in_shape[3];
+        box3 const &mine = is_backward ? lp.in_shape[0][me] : lp.out_shape[3][me];
+        long long moved = 0;
+        for(int r=0; r<ccomm->size() and not mine.empty(); r++){
+            if (r == me) continue;
+            box3 const piece = mine.overlap(from[r]);
+            if (piece.empty()) continue;
+            idx const offset = mine.offset_of(piece.low);
+            rc = b200_copy_subbox(elem, piece.osize(0), piece.osize(1), piece.osize(2), mine.osize(0), mine.osize(0) * mine.osize(1),
+                                  mine.osize(0), mine.osize(0) * mine.osize(1), advance(cur, offset, elem), advance(out, offset, elem), cstream);
+            if (rc) return rc;
+            moved += piece.count();
+        }
+        mark("received sub-boxes to the caller's array", 2 * moved * elem, 0);
+    }else if (cur != out){
         idx const count = is_backward ? inbox_count : outbox_count;
         bool const real_out = (tkind == kind_r2c and is_backward) or not complex_data;
         size_t const bytes = static_cast<size_t>(count) * (real_out ? real_bytes : cplx_bytes);

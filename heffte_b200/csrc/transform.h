@@ -13,6 +13,7 @@
 #include "../../include/heffte_b200_kernels.h"
 #include "comm.h"
 #include "plan_logic.h"
+#include "scatter_map.h"
 
 namespace b200 {
 
@@ -101,7 +102,12 @@ private:
         std::vector<void*> arenas;             // address of every rank's arena as seen from this device
         std::vector<void*> remote_slots;       // my slot in every rank's flag array
         unsigned long long epoch = 0;
-        void *maps = nullptr;                  // device array of scatter maps, index ((direction * 4 + stage) * 2 + buffer)
+        void *maps = nullptr;                  // device array of scatter maps, index ((direction * 4 + stage) * 2 + buffer); two more
+                                               // entries (16 + direction) hold the last stage's map patched for the caller's array
+        std::vector<scatter_map> host_maps;    // host copy of the 16 plan-time maps
+        std::vector<int> owners;               // rank every cell of those maps lands on (16 x scatter_max_cells)
+        void *patched_out[2] = {nullptr, nullptr};   // caller array the patched map of that direction points to
+        int patched_buffer[2] = {-1, -1};
         bool fused[2][4] = {{false, false, false, false}, {false, false, false, false}};   // reshape of that stage moves data (global fact)
         char* buffer(int index) const { return static_cast<char*>(arena) + 4096 + static_cast<size_t>(index) * buffer_bytes; }
     };

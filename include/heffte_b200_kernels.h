@@ -117,6 +117,11 @@ int b200_direct_pack(int elem_bytes, long long nfast, long long nmid, long long 
                      long long line_stride, long long plane_stride, const void *src, void *dst, void *stream);
 int b200_direct_unpack(int elem_bytes, long long nfast, long long nmid, long long nslow,
                        long long line_stride, long long plane_stride, const void *src, void *dst, void *stream);
+/* Sub-box copy between two strided boxes (no reference counterpart: used after a fused reshape to move the sub-boxes received
+ * from other GPUs out of the plan's arena into the caller's array):  dst[s*dplane + m*dline + f] = src[s*splane + m*sline + f] */
+int b200_copy_subbox(int elem_bytes, long long nfast, long long nmid, long long nslow,
+                     long long src_line_stride, long long src_plane_stride, long long dst_line_stride, long long dst_plane_stride,
+                     const void *src, void *dst, void *stream);
 /*
  * Unpack with axis permutation.
  * Replaces heffte::cuda::transpose_unpack (src/heffte_backend_cuda.cu:90-133, 404-441):
