@@ -33,8 +33,14 @@ __global__ void __launch_bounds__(256) scatter_copy_kernel(scatter_copy_args a){
     const int tx = threadIdx.x & (a.tf - 1), ty = threadIdx.x / a.tf;
     const int rows = blockDim.x / a.tf;                         // lines handled side by side by one CTA
     const long long nlines = static_cast<long long>(a.nmid) * a.nslow;
+    // planes are visited round-robin over the nb destination ranges of the slow axis: the CTAs that run side by side then write
+    // to every destination GPU at once instead of all of them to the same one (the ranks of a plan walk their boxes in step, so
+    // a plane-by-plane sweep would aim every sender at the same receiver at the same time)
+    const int ranges = (smap->nb > 1 && a.nslow % smap->nb == 0) ? smap->nb : 1;
+    const int per_range = a.nslow / ranges;
     for(long long line = static_cast<long long>(blockIdx.x) * rows + ty; line < nlines; line += static_cast<long long>(gridDim.x) * rows){
-        const int s = static_cast<int>(line / a.nmid), m = static_cast<int>(line - static_cast<long long>(s) * a.nmid);
+        const int visit = static_cast<int>(line / a.nmid), m = static_cast<int>(line - static_cast<long long>(visit) * a.nmid);
+        const int s = (visit % ranges) * per_range + visit / ranges;
         const int row = scatter_row(smap, m, s);
         const V *from = src + s * a.plane + m * a.line;
         int f = tx;

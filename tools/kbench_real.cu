@@ -1,0 +1,95 @@
+// Developer micro-benchmark (not part of the product): times variants (radix schedule, lines per CTA, occupancy) of the
+// real-data FFT kernels on the 512^3 fp64 problem: r2c / DCT-II forward / DCT-III backward along the contiguous axis
+// (fft_contig_real_kernel) and along the middle axis (fft_strided_real_kernel).
+#include "../heffte_b200/csrc/fft_host_plan.h"
+#include <cstdio>
+#include <vector>
+using namespace b200;
+
+#define CK(x) do{ cudaError_t e = (x); if (e != cudaSuccess){ printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} }while(0)
+
+struct L { cudaStream_t s = 0;
+  template<typename K, typename A> int launch(K k, long long blocks, int threads, size_t smem, A const &a){
+    if (smem > 48*1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
+    k<<<(unsigned)blocks, threads, smem, s>>>(a); return 0; } };
+
+template<typename F> float timeit(F f, int reps = 10){
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    for(int i=0;i<3;i++) f();
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(a); for(int i=0;i<reps;i++) f(); cudaEventRecord(b); CK(cudaEventSynchronize(b));
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    CK(cudaGetLastError());
+    return ms / reps;
+}
+
+int main(){
+    const int n = 512; const long long elems = (long long)n*n*n;
+    double *x; double2 *y; CK(cudaMalloc(&x, elems * 8)); CK(cudaMalloc(&y, (long long)(n/2+1)*n*n * 16));
+    CK(cudaMemset(x, 0, elems*8)); CK(cudaMemset(y, 0, (long long)(n/2+1)*n*n*16));
+    host_plan hp; const char *why;
+    b200_fft1d_desc d{}; d.precision = 1; d.kind = B200_COS; d.n = n; d.count_a = (long long)n*n; d.count_b = 1; d.in = {1, n, 0}; d.out = d.in;
+    make_host_plan(d, hp, &why);
+    auto table = make_twiddle_table<double>(hp); char *tw; CK(cudaMalloc(&tw, table.size()*8)); CK(cudaMemcpy(tw, table.data(), table.size()*8, cudaMemcpyHostToDevice));
+    L l;
+    const double gb_r2r = 2.0 * elems * 8 * 1e-9, gb_r2c = (elems * 8.0 + (double)(n/2+1)*n*n*16) * 1e-9;
+    auto report = [&](const char *name, double gb, float ms){ printf("%-60s %8.3f ms  %7.1f GB/s\n", name, ms, gb / ms * 1e3); fflush(stdout); };
+
+    fft_args a; a.twiddle = tw + 16 * (hp.table_main + hp.table_extra); a.twiddle2 = tw + 16 * hp.table_main;
+    a.nlines = elems / n; a.scale = 1.0; a.smap = nullptr;
+    using R884 = radix_list<8,8,4,1>; using R1616 = radix_list<16,16,1,1>; using R488 = radix_list<4,8,8,1>;
+
+    // ---- contiguous axis --------------------------------------------------------------------------------------------
+    a.count_a = n * n;
+    for(int kind : {real_r2c, real_cos}){
+        for(int backward=0; backward<2; backward++){
+            a.backward = backward;
+            if (kind == real_r2c){
+                line_geom rg{1, n, 0}, cg{1, n/2+1, 0};
+                a.in = backward ? (void*)y : (void*)x; a.out = backward ? (void*)x : (void*)y;
+                a.ig = backward ? cg : rg; a.og = backward ? rg : cg;
+            }else{ a.in = x; a.out = x; a.ig = a.og = line_geom{1, n, 0}; }
+            double gb = (kind == real_r2c) ? gb_r2c : gb_r2r;
+            printf("-- contig kind %s %s\n", kind == real_r2c ? "r2c" : "cos", backward ? "backward" : "forward");
+#define CV(RL, LPB, MINB, label) if (kind == real_r2c) report(label, gb, timeit([&]{ launch_contig_real<double, RL, LPB, MINB, real_r2c, false>(a, l); })); \
+                                 else report(label, gb, timeit([&]{ launch_contig_real<double, RL, LPB, MINB, real_cos, false>(a, l); }));
+            CV(R884, 4, 6, "contig_real <8,8,4> LPB4 minb6 (current)")
+            CV(R884, 2, 12, "contig_real <8,8,4> LPB2 minb12")
+            CV(R884, 8, 3, "contig_real <8,8,4> LPB8 minb3")
+            CV(R884, 4, 4, "contig_real <8,8,4> LPB4 minb4")
+            CV(R488, 4, 6, "contig_real <4,8,8> LPB4 minb6")
+            CV(R1616, 4, 6, "contig_real <16,16> LPB4 minb6 (64thr)")
+            CV(R1616, 8, 3, "contig_real <16,16> LPB8 minb3 (128thr)")
+            CV(R1616, 8, 4, "contig_real <16,16> LPB8 minb4 (128thr)")
+            CV(R1616, 2, 12, "contig_real <16,16> LPB2 minb12 (32thr)")
+        }
+    }
+    // ---- middle axis (stride n, neighbours adjacent) ----------------------------------------------------------------------
+    a.in = x; a.out = x; a.ig = a.og = line_geom{n, 1, (long long)n*n}; a.count_a = n;
+    for(int backward=0; backward<2; backward++){
+        a.backward = backward;
+        printf("-- strided kind cos %s\n", backward ? "backward" : "forward");
+#define SV(RL, TPL, LPB, MINB, label) report(label, gb_r2r, timeit([&]{ launch_strided_real<double, RL, TPL, LPB, MINB, real_cos, false>(a, l); }));
+        SV(R884, 16, 16, 3, "strided_real <8,8,4> TPL16 LPB16 minb3 (current)")
+        SV(R884, 16, 16, 2, "strided_real <8,8,4> TPL16 LPB16 minb2")
+        SV(R884, 32, 16, 1, "strided_real <8,8,4> TPL32 LPB16 minb1 (512thr)")
+        SV(R884, 32, 8, 3, "strided_real <8,8,4> TPL32 LPB8 minb3 (256thr 32KB)")
+        SV(R884, 32, 8, 6, "strided_real <8,8,4> TPL32 LPB8 minb6 (256thr 32KB)")
+        SV(R884, 16, 8, 6, "strided_real <8,8,4> TPL16 LPB8 minb6 (128thr 32KB)")
+        SV(R884, 8, 16, 3, "strided_real <8,8,4> TPL8 LPB16 minb3 (128thr)")
+        SV(R1616, 16, 16, 3, "strided_real <16,16> TPL16 LPB16 minb3")
+        SV(R1616, 16, 16, 2, "strided_real <16,16> TPL16 LPB16 minb2")
+        SV(R1616, 16, 8, 4, "strided_real <16,16> TPL16 LPB8 minb4 (128thr 32KB)")
+        SV(R488, 16, 16, 3, "strided_real <4,8,8> TPL16 LPB16 minb3")
+    }
+    // r2c along the middle axis
+    {
+        line_geom rg{n, 1, (long long)n*n}, cg{n, 1, (long long)n*(n/2+1)};
+        a.backward = 0; a.in = x; a.out = y; a.ig = rg; a.og = cg;
+        printf("-- strided kind r2c forward\n");
+        report("strided_real r2c <8,8,4> TPL16 LPB16 minb3", gb_r2c, timeit([&]{ launch_strided_real<double, R884, 16, 16, 3, real_r2c, false>(a, l); }));
+        report("strided_real r2c <16,16> TPL16 LPB16 minb3", gb_r2c, timeit([&]{ launch_strided_real<double, R1616, 16, 16, 3, real_r2c, false>(a, l); }));
+    }
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
