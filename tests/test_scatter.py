@@ -45,6 +45,10 @@ CASES = [
     ((20, 21, 22), (1, 1, 2), (0, 1, 2), (1, 2, 1), (0, 1, 2), 1),   # generic kernel along the middle axis, uneven halves
     ((10, 9, 22), (1, 2, 1), (0, 1, 2), (1, 1, 2), (0, 1, 2), 2),    # generic kernel along the slow axis
     ((7, 6, 5), (1, 1, 1), (0, 1, 2), (1, 1, 1), (0, 1, 2), 1),      # one rank, one cell
+    # whole tiles per box row and destination ranges that divide the slow line axis: the tiles visit the ranges round-robin
+    ((64, 16, 8), (1, 1, 1), (0, 1, 2), (2, 1, 2), (0, 1, 2), 1),    # strided kernel, 2 (fp64) / 1 (fp32) tiles per row, nb = 2
+    ((16, 64, 6), (1, 1, 1), (0, 1, 2), (1, 2, 3), (0, 1, 2), 0),    # contig kernel, nb = 3
+    ((64, 4, 16), (1, 2, 1), (0, 1, 2), (2, 4, 1), (0, 1, 2), 2),    # strided kernel along the slow axis, nb = 2 per source rank
 ]
 
 
@@ -83,6 +87,8 @@ def test_fft_with_fused_reshape(emul, prec, case):  # noqa: F811
     ((6, 64, 4), 1, (2, 1, 2), (1, 3, 2)),      # fft_strided_real_kernel (middle axis), scatter variant
     ((5, 3, 32), 2, (2, 2, 1), (1, 1, 3)),      # fft_strided_real_kernel (slow axis), scatter variant
     ((40, 128, 1), 1, (3, 1, 1), (2, 2, 1)),    # more lines than one tile row, ragged last tile
+    ((32, 64, 4), 0, (1, 1, 1), (1, 2, 2)),     # contiguous real kernel, whole tiles per row: round-robin visit of nb = 2 ranges
+    ((64, 32, 4), 1, (1, 1, 1), (2, 1, 2)),     # strided real kernel, whole tiles per row: round-robin visit of nb = 2 ranges
 ])
 @pytest.mark.parametrize("kind", ["r2c", "c2r", "cos", "sin", "cos_b", "sin_b"])
 def test_real_transforms_with_fused_reshape(emul, kind, n, dim, src_grid, dst_grid, prec):  # noqa: F811
