@@ -3,6 +3,8 @@
 // CPU-only development container.  Never compiled into the product library.
 #pragma once
 #include <barrier>
+#include <condition_variable>
+#include <mutex>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -34,9 +36,61 @@ struct block_state {
 inline thread_local dim3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 inline thread_local block_state *t_block = nullptr;
 
-// One pool of host threads per launch (one per CUDA thread of a block); the pool walks the blocks of the grid in order.
-// Every block gets its own __syncthreads barrier (threads that leave the kernel early drop out of it, like on the GPU) and
-// the pool meets on a second barrier between blocks so shared memory can be reused.
+// A pool of host threads per calling thread (one worker per CUDA thread of a block), kept alive between launches: creating
+// the threads again for every emulated launch used to dominate the run time of the CPU test-suite.
+class worker_pool {
+public:
+    ~worker_pool(){
+        { std::lock_guard<std::mutex> lock(guard); stopping = true; generation++; }
+        wake.notify_all();
+        for(auto &t : workers) t.join();
+    }
+    // runs job(0) ... job(n-1) concurrently, returns when all of them have finished
+    void run(unsigned n, std::function<void(unsigned)> const &job){
+        {
+            std::lock_guard<std::mutex> lock(guard);
+            while(workers.size() < n){
+                unsigned const id = static_cast<unsigned>(workers.size());
+                unsigned long long const seen = generation;
+                workers.emplace_back([this, id, seen]{ loop(id, seen); });
+            }
+            current = &job; active = n; remaining = n; generation++;
+        }
+        wake.notify_all();
+        std::unique_lock<std::mutex> lock(guard);
+        done.wait(lock, [&]{ return remaining == 0; });
+        current = nullptr;
+    }
+private:
+    void loop(unsigned id, unsigned long long seen){
+        for(;;){
+            std::function<void(unsigned)> const *job = nullptr;
+            {
+                std::unique_lock<std::mutex> lock(guard);
+                wake.wait(lock, [&]{ return generation != seen; });
+                seen = generation;
+                if (stopping) return;
+                if (id < active) job = current;
+            }
+            if (job == nullptr) continue;
+            (*job)(id);
+            std::lock_guard<std::mutex> lock(guard);
+            if (--remaining == 0) done.notify_all();
+        }
+    }
+    std::vector<std::thread> workers;
+    std::mutex guard;
+    std::condition_variable wake, done;
+    std::function<void(unsigned)> const *current = nullptr;
+    unsigned active = 0, remaining = 0;
+    unsigned long long generation = 0;
+    bool stopping = false;
+};
+inline worker_pool& pool(){ static thread_local worker_pool p; return p; }
+
+// The pool walks the blocks of the grid in order.  Every block gets its own __syncthreads barrier (threads that leave the
+// kernel early drop out of it, like on the GPU) and the pool meets on a second barrier between blocks so that shared memory
+// can be reused.
 template<typename kernel_t, typename args_t>
 void launch(kernel_t kernel, dim3 grid, dim3 block, size_t smem_bytes, args_t args){
     unsigned const nthreads = block.x * block.y;
@@ -44,30 +98,26 @@ void launch(kernel_t kernel, dim3 grid, dim3 block, size_t smem_bytes, args_t ar
     if (nblocks == 0 or nthreads == 0) return;
     std::vector<block_state> states(nblocks);
     std::barrier<> between(nthreads);
-    std::vector<std::thread> pool;
-    for(unsigned ty = 0; ty < block.y; ty++)
-    for(unsigned tx = 0; tx < block.x; tx++){
-        pool.emplace_back([&, tx, ty]{
-            size_t index = 0;
-            for(unsigned bz = 0; bz < grid.z; bz++)
-            for(unsigned by = 0; by < grid.y; by++)
-            for(unsigned bx = 0; bx < grid.x; bx++, index++){
-                block_state &state = states[index];
-                if (tx == 0 and ty == 0){
-                    state.smem.assign(smem_bytes + 64, 0);
-                    state.bar.reset(new std::barrier<>(nthreads));
-                }
-                between.arrive_and_wait();
-                t_threadIdx = dim3(tx, ty); t_blockIdx = dim3(bx, by, bz); t_blockDim = block; t_gridDim = grid;
-                t_block = &state;
-                kernel(args);
-                state.bar->arrive_and_drop();
-                between.arrive_and_wait();
-                if (tx == 0 and ty == 0){ state.smem.clear(); state.smem.shrink_to_fit(); }
+    pool().run(nthreads, [&](unsigned id){
+        unsigned const tx = id % block.x, ty = id / block.x;
+        size_t index = 0;
+        for(unsigned bz = 0; bz < grid.z; bz++)
+        for(unsigned by = 0; by < grid.y; by++)
+        for(unsigned bx = 0; bx < grid.x; bx++, index++){
+            block_state &state = states[index];
+            if (id == 0){
+                state.smem.assign(smem_bytes + 64, 0);
+                state.bar.reset(new std::barrier<>(nthreads));
             }
-        });
-    }
-    for(auto &t : pool) t.join();
+            between.arrive_and_wait();
+            t_threadIdx = dim3(tx, ty); t_blockIdx = dim3(bx, by, bz); t_blockDim = block; t_gridDim = grid;
+            t_block = &state;
+            kernel(args);
+            state.bar->arrive_and_drop();
+            between.arrive_and_wait();
+            if (id == 0){ state.smem.clear(); state.smem.shrink_to_fit(); }
+        }
+    });
 }
 } // namespace emul
 

@@ -12,10 +12,17 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("nranks,mode,stride", [(2, "peer", 4), (4, "peer", 5), (8, "peer", 9), (3, "peer", 3), (6, "peer", 4),
-                                                (2, "exchange", 6), (4, "exchange", 9)])
-def test_emulated_ranks(nranks, mode, stride):
+@pytest.mark.parametrize("nranks,mode,stride,env", [
+    (2, "peer", 4, {}), (4, "peer", 5, {}), (8, "peer", 9, {}), (3, "peer", 3, {}), (6, "peer", 4, {}),
+    (2, "exchange", 6, {}), (4, "exchange", 9, {}),
+    # the switches of the executed plan: the reference's plan as it is (reorder, transposing fused reshapes),
+    # one pinned decomposition, and the whole output landing in the arena before the copy
+    (4, "peer", 11, {"HEFFTE_B200_REFERENCE_PLAN": "1"}),
+    (4, "exchange", 13, {"HEFFTE_B200_REFERENCE_PLAN": "1"}),
+    (8, "peer", 17, {"HEFFTE_B200_DECOMPOSITION": "pencils", "HEFFTE_B200_NO_DIRECT_OUTPUT": "1"}),
+])
+def test_emulated_ranks(nranks, mode, stride, env):
     cmd = [sys.executable, os.path.join(ROOT, "tests", "emul_worker.py"), str(nranks), mode, str(stride)]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1700)
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1700, env=dict(os.environ, **env))
     assert out.returncode == 0, out.stdout[-3000:] + "\n" + out.stderr[-3000:]
     assert " ok" in out.stdout
