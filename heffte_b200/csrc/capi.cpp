@@ -26,9 +26,13 @@ struct plan_state {
     // device staging of the *_host entry points
     void *dev_in = nullptr, *dev_out = nullptr;
     size_t dev_in_bytes = 0, dev_out_bytes = 0;
+    // complex staging of the real-data entry points (s2c / d2z / c2s / z2d) of a complex-to-complex plan
+    void *promoted = nullptr;
+    size_t promoted_bytes = 0;
     ~plan_state(){
         if (dev_in) cudaFree(dev_in);
         if (dev_out) cudaFree(dev_out);
+        if (promoted) cudaFree(promoted);
     }
 };
 
@@ -99,6 +103,32 @@ plan_state* state_of(heffte_plan const plan){
 
 void run_or_report(heffte_plan const plan, int precision, int direction, void const *input, void *output, void *workspace, int scale){
     int rc = heffte_execute(plan, precision, direction, 1, input, output, workspace, scale);
+    if (rc != 0) std::fprintf(stderr, "heffte(b200): transform failed (%d): %s\n", rc, heffte_last_error());
+}
+
+// The real-data entry points (heffte_forward_s2c / d2z, heffte_backward_c2s / z2d).  On an r2c plan they are the transform
+// itself; on a complex-to-complex plan the reference promotes the real input with a zero imaginary part and drops the
+// imaginary part of the result (fft3d::forward(real, complex) / backward(complex, real), include/heffte_fft3d.h:353-389 with
+// the cuFFT executor's convert overloads, include/heffte_backend_cuda.h:527-545).
+void run_real_side(heffte_plan const plan, int precision, int direction, void const *input, void *output, void *workspace, int scale){
+    plan_state *s = state_of(plan);
+    if (s == nullptr or s->fft->kind() != kind_c2c){ run_or_report(plan, precision, direction, input, output, workspace, scale); return; }
+    transform3d &fft = *s->fft;
+    size_t const count = static_cast<size_t>(fft.size_inbox());
+    size_t const bytes = count * ((precision == B200_PREC_FLOAT) ? 8 : 16);
+    int rc = 0;
+    if (bytes > s->promoted_bytes){
+        if (s->promoted){ cudaStreamSynchronize(fft.stream()); cudaFree(s->promoted); s->promoted = nullptr; s->promoted_bytes = 0; }
+        if (cudaMalloc(&s->promoted, bytes) != cudaSuccess){ std::fprintf(stderr, "heffte(b200): cannot allocate the complex staging array\n"); return; }
+        s->promoted_bytes = bytes;
+    }
+    if (direction == B200_FORWARD){
+        rc = b200_convert_r2c(precision, static_cast<long long>(count), input, s->promoted, fft.stream());
+        if (rc == 0) rc = heffte_execute(plan, precision, B200_FORWARD, 1, s->promoted, output, workspace, scale);
+    }else{
+        rc = heffte_execute(plan, precision, B200_BACKWARD, 1, input, s->promoted, workspace, scale);
+        if (rc == 0) rc = b200_convert_c2r(precision, static_cast<long long>(count), s->promoted, output, fft.stream());
+    }
     if (rc != 0) std::fprintf(stderr, "heffte(b200): transform failed (%d): %s\n", rc, heffte_last_error());
 }
 
@@ -270,22 +300,22 @@ int heffte_execute_host(heffte_plan const plan, int precision, int direction, in
     return 0;
 }
 
-void heffte_forward_s2c(heffte_plan const plan, float const *input, void *output, int scale){ run_or_report(plan, B200_PREC_FLOAT, B200_FORWARD, input, output, nullptr, scale); }
+void heffte_forward_s2c(heffte_plan const plan, float const *input, void *output, int scale){ run_real_side(plan, B200_PREC_FLOAT, B200_FORWARD, input, output, nullptr, scale); }
 void heffte_forward_c2c(heffte_plan const plan, void const *input, void *output, int scale){ run_or_report(plan, B200_PREC_FLOAT, B200_FORWARD, input, output, nullptr, scale); }
-void heffte_forward_d2z(heffte_plan const plan, double const *input, void *output, int scale){ run_or_report(plan, B200_PREC_DOUBLE, B200_FORWARD, input, output, nullptr, scale); }
+void heffte_forward_d2z(heffte_plan const plan, double const *input, void *output, int scale){ run_real_side(plan, B200_PREC_DOUBLE, B200_FORWARD, input, output, nullptr, scale); }
 void heffte_forward_z2z(heffte_plan const plan, void const *input, void *output, int scale){ run_or_report(plan, B200_PREC_DOUBLE, B200_FORWARD, input, output, nullptr, scale); }
-void heffte_forward_s2c_buffered(heffte_plan const plan, float const *input, void *output, void *workspace, int scale){ run_or_report(plan, B200_PREC_FLOAT, B200_FORWARD, input, output, workspace, scale); }
+void heffte_forward_s2c_buffered(heffte_plan const plan, float const *input, void *output, void *workspace, int scale){ run_real_side(plan, B200_PREC_FLOAT, B200_FORWARD, input, output, workspace, scale); }
 void heffte_forward_c2c_buffered(heffte_plan const plan, void const *input, void *output, void *workspace, int scale){ run_or_report(plan, B200_PREC_FLOAT, B200_FORWARD, input, output, workspace, scale); }
-void heffte_forward_d2z_buffered(heffte_plan const plan, double const *input, void *output, void *workspace, int scale){ run_or_report(plan, B200_PREC_DOUBLE, B200_FORWARD, input, output, workspace, scale); }
+void heffte_forward_d2z_buffered(heffte_plan const plan, double const *input, void *output, void *workspace, int scale){ run_real_side(plan, B200_PREC_DOUBLE, B200_FORWARD, input, output, workspace, scale); }
 void heffte_forward_z2z_buffered(heffte_plan const plan, void const *input, void *output, void *workspace, int scale){ run_or_report(plan, B200_PREC_DOUBLE, B200_FORWARD, input, output, workspace, scale); }
 
-void heffte_backward_c2s(heffte_plan const plan, void const *input, float *output, int scale){ run_or_report(plan, B200_PREC_FLOAT, B200_BACKWARD, input, output, nullptr, scale); }
+void heffte_backward_c2s(heffte_plan const plan, void const *input, float *output, int scale){ run_real_side(plan, B200_PREC_FLOAT, B200_BACKWARD, input, output, nullptr, scale); }
 void heffte_backward_c2c(heffte_plan const plan, void const *input, void *output, int scale){ run_or_report(plan, B200_PREC_FLOAT, B200_BACKWARD, input, output, nullptr, scale); }
-void heffte_backward_z2d(heffte_plan const plan, void const *input, double *output, int scale){ run_or_report(plan, B200_PREC_DOUBLE, B200_BACKWARD, input, output, nullptr, scale); }
+void heffte_backward_z2d(heffte_plan const plan, void const *input, double *output, int scale){ run_real_side(plan, B200_PREC_DOUBLE, B200_BACKWARD, input, output, nullptr, scale); }
 void heffte_backward_z2z(heffte_plan const plan, void const *input, void *output, int scale){ run_or_report(plan, B200_PREC_DOUBLE, B200_BACKWARD, input, output, nullptr, scale); }
-void heffte_backward_c2s_buffered(heffte_plan const plan, void const *input, float *output, void *workspace, int scale){ run_or_report(plan, B200_PREC_FLOAT, B200_BACKWARD, input, output, workspace, scale); }
+void heffte_backward_c2s_buffered(heffte_plan const plan, void const *input, float *output, void *workspace, int scale){ run_real_side(plan, B200_PREC_FLOAT, B200_BACKWARD, input, output, workspace, scale); }
 void heffte_backward_c2c_buffered(heffte_plan const plan, void const *input, void *output, void *workspace, int scale){ run_or_report(plan, B200_PREC_FLOAT, B200_BACKWARD, input, output, workspace, scale); }
-void heffte_backward_z2d_buffered(heffte_plan const plan, void const *input, double *output, void *workspace, int scale){ run_or_report(plan, B200_PREC_DOUBLE, B200_BACKWARD, input, output, workspace, scale); }
+void heffte_backward_z2d_buffered(heffte_plan const plan, void const *input, double *output, void *workspace, int scale){ run_real_side(plan, B200_PREC_DOUBLE, B200_BACKWARD, input, output, workspace, scale); }
 void heffte_backward_z2z_buffered(heffte_plan const plan, void const *input, void *output, void *workspace, int scale){ run_or_report(plan, B200_PREC_DOUBLE, B200_BACKWARD, input, output, workspace, scale); }
 
 void heffte_forward_s2s_buffered(heffte_plan const plan, float const *input, float *output, float *workspace, int scale){ run_or_report(plan, B200_PREC_FLOAT, B200_FORWARD, input, output, workspace, scale); }

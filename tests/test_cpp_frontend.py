@@ -16,10 +16,14 @@ SRC = os.path.join(ROOT, "tests", "cpp", "example_b200.cpp")
 OUT = os.path.join(ROOT, "tests", "emul", "_build")
 
 
-def _compile(libdir, libname, exe):
+C_SRC = os.path.join(ROOT, "tests", "c", "test_c_b200.c")
+
+
+def _compile(libdir, libname, exe, source=SRC):
     os.makedirs(OUT, exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), SRC, "-o", exe, "-L", libdir, "-l" + libname,
-           "-Wl,-rpath," + libdir, "-lpthread"]
+    compiler = ["gcc", "-std=c99", "-pedantic"] if source.endswith(".c") else ["g++", "-std=c++17"]
+    cmd = compiler + ["-O1", "-Wall", "-I", os.path.join(ROOT, "include"), source, "-o", exe, "-L", libdir, "-l" + libname,
+                      "-Wl,-rpath," + libdir, "-lpthread", "-lm"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return exe
@@ -45,3 +49,21 @@ def test_cpp_program_runs_on_the_gpu(built_library):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "example_b200: ok" in r.stdout
+
+
+def test_c_program_runs_on_the_emulated_library():
+    """tests/c/test_c_b200.c: the scenario and golden values of the reference's test/test_c.c against include/heffte_b200.h, plain C99"""
+    from tests.emul.build_emul_library import build
+    lib = build()
+    exe = _compile(os.path.dirname(lib), "heffte_b200_emul", os.path.join(OUT, "test_c_b200_emul"), C_SRC)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "test_c_b200: ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_program_runs_on_the_gpu(built_library):
+    exe = _compile(os.path.dirname(built_library), "heffte_b200", os.path.join(OUT, "test_c_b200"), C_SRC)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "test_c_b200: ok" in r.stdout
