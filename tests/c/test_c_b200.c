@@ -60,7 +60,7 @@ static void* rank_body(void *p){
     {   /* expected spectrum of the index-valued input (interleaved complex) */
         double expect[64]; float expect_f[64];
         double zin[64], zout[64], zback[64]; float cin[64], cout[64], cback[64]; double din[32]; float sin_[32];
-        void *d_in, *d_out, *d_back, *d_work;
+        void *d_zin, *d_din, *d_cin, *d_sin, *d_out, *d_back, *d_work;
         memset(expect, 0, sizeof(expect));
         if (me == 0){
             expect[0] = 992.0; expect[2] = -32.0; expect[3] = 32.0; expect[4] = -32.0; expect[6] = -32.0; expect[7] = -32.0;
@@ -70,43 +70,42 @@ static void* rank_body(void *p){
         memset(zin, 0, sizeof(zin)); memset(cin, 0, sizeof(cin));
         for(i=0; i<32; i++){ zin[2*i] = i; cin[2*i] = (float) i; din[i] = i; sin_[i] = (float) i; }
 
-        /* z2z, buffered, forward then backward with full scaling */
-        d_in = to_device(stream, zin, sizeof(zin));
+        /* every device array is allocated before the first transform and freed after the last one: cudaFree waits for the whole
+         * device, and the other rank (a thread of this process on the same GPU) may already be spinning in a barrier of the
+         * next transform that only this thread's next launches can release */
+        d_zin = to_device(stream, zin, sizeof(zin)); d_din = to_device(stream, din, sizeof(din));
+        d_cin = to_device(stream, cin, sizeof(cin)); d_sin = to_device(stream, sin_, sizeof(sin_));
         CHECK(b200_device_alloc(sizeof(zout), &d_out) == 0 && b200_device_alloc(sizeof(zback), &d_back) == 0);
         CHECK(b200_device_alloc(96 * 2 * sizeof(double), &d_work) == 0);
-        heffte_forward_z2z_buffered(plan, d_in, d_out, d_work, Heffte_SCALE_NONE);
+        /* z2z, buffered, forward then backward with full scaling */
+        heffte_forward_z2z_buffered(plan, d_zin, d_out, d_work, Heffte_SCALE_NONE);
         to_host(stream, d_out, zout, sizeof(zout));
         CHECK(max_diff(zout, expect, 64) < 1e-11);
         heffte_backward_z2z_buffered(plan, d_out, d_back, d_work, Heffte_SCALE_FULL);
         to_host(stream, d_back, zback, sizeof(zback));
         CHECK(max_diff(zback, zin, 64) < 1e-11);
         /* d2z / z2d: real input of the complex plan */
-        b200_device_free(d_in);
-        d_in = to_device(stream, din, sizeof(din));
-        heffte_forward_d2z(plan, (double const*) d_in, d_out, Heffte_SCALE_NONE);
+        heffte_forward_d2z(plan, (double const*) d_din, d_out, Heffte_SCALE_NONE);
         to_host(stream, d_out, zout, sizeof(zout));
         CHECK(max_diff(zout, expect, 64) < 1e-11);
         heffte_backward_z2d(plan, d_out, (double*) d_back, Heffte_SCALE_FULL);
         to_host(stream, d_back, zback, 32 * sizeof(double));
         CHECK(max_diff(zback, din, 32) < 1e-11);
-        b200_device_free(d_in);
         /* c2c and s2c / c2s in single precision */
-        d_in = to_device(stream, cin, sizeof(cin));
-        heffte_forward_c2c(plan, d_in, d_out, Heffte_SCALE_NONE);
+        heffte_forward_c2c(plan, d_cin, d_out, Heffte_SCALE_NONE);
         to_host(stream, d_out, cout, sizeof(cout));
         CHECK(max_diff_f(cout, expect_f, 64) < 1e-4);
         heffte_backward_c2c(plan, d_out, d_back, Heffte_SCALE_FULL);
         to_host(stream, d_back, cback, sizeof(cback));
         CHECK(max_diff_f(cback, cin, 64) < 1e-4);
-        b200_device_free(d_in);
-        d_in = to_device(stream, sin_, sizeof(sin_));
-        heffte_forward_s2c(plan, (float const*) d_in, d_out, Heffte_SCALE_NONE);
+        heffte_forward_s2c(plan, (float const*) d_sin, d_out, Heffte_SCALE_NONE);
         to_host(stream, d_out, cout, sizeof(cout));
         CHECK(max_diff_f(cout, expect_f, 64) < 1e-4);
         heffte_backward_c2s(plan, d_out, (float*) d_back, Heffte_SCALE_FULL);
         to_host(stream, d_back, cback, 32 * sizeof(float));
         CHECK(max_diff_f(cback, sin_, 32) < 1e-4);
-        b200_device_free(d_in); b200_device_free(d_out); b200_device_free(d_back); b200_device_free(d_work);
+        b200_device_free(d_zin); b200_device_free(d_din); b200_device_free(d_cin); b200_device_free(d_sin);
+        b200_device_free(d_out); b200_device_free(d_back); b200_device_free(d_work);
     }
     CHECK(heffte_plan_destroy(plan) == 0);
 
