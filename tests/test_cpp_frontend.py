@@ -4,7 +4,8 @@ gpu::vector / gpu::transfer) exercised by a user program shaped like the referen
 (tests/cpp/example_b200.cpp, golden values of test/test_c.c:47-74).
   * CPU: the program compiles with plain g++ (no CUDA headers) and links against libheffte_b200.so; it also RUNS against the
     emulated build of the library (tests/emul/), two thread-ranks, c2c + r2c + cosine plans.
-  * GPU: the same program runs against the real library.
+  * GPU: the same programs run against the real library (tests/test_z_programs_gpu.py: the file sorts last on purpose, the
+    programs drive two thread-ranks on one GPU and are the slowest to fail).
 """
 import os
 import subprocess
@@ -43,27 +44,11 @@ def test_cpp_program_runs_on_the_emulated_library():
     assert "example_b200: ok" in r.stdout
 
 
-@pytest.mark.gpu
-def test_cpp_program_runs_on_the_gpu(built_library):
-    exe = _compile(os.path.dirname(built_library), "heffte_b200", os.path.join(OUT, "example_b200"))
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert "example_b200: ok" in r.stdout
-
-
 def test_c_program_runs_on_the_emulated_library():
     """tests/c/test_c_b200.c: the scenario and golden values of the reference's test/test_c.c against include/heffte_b200.h, plain C99"""
     from tests.emul.build_emul_library import build
     lib = build()
     exe = _compile(os.path.dirname(lib), "heffte_b200_emul", os.path.join(OUT, "test_c_b200_emul"), C_SRC)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert "test_c_b200: ok" in r.stdout
-
-
-@pytest.mark.gpu
-def test_c_program_runs_on_the_gpu(built_library):
-    exe = _compile(os.path.dirname(built_library), "heffte_b200", os.path.join(OUT, "test_c_b200"), C_SRC)
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "test_c_b200: ok" in r.stdout
