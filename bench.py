@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--reorder", action="store_true")
     ap.add_argument("--slabs", action="store_true")
     ap.add_argument("--io-pencils", action="store_true", help="pencil-shaped in/out boxes (speed3d -io_pencils)")
+    ap.add_argument("--l2-slab-mb", type=float, default=None,
+                    help="experimental: run pairs of local transforms slab by slab through the L2 cache (sets HEFFTE_B200_L2_SLAB_MB)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-size", type=int, nargs=3, default=None, help="size of the CPU sample (default: the workload itself)")
@@ -198,6 +200,8 @@ def reference_arm(args):
 # the b200 arm
 # ----------------------------------------------------------------------------------------------------------------
 def b200_arm(args):
+    if args.l2_slab_mb is not None:
+        os.environ["HEFFTE_B200_L2_SLAB_MB"] = str(args.l2_slab_mb)
     import numpy as np
     import torch
     import heffte_b200 as hf
@@ -489,6 +493,7 @@ def b200_arm(args):
                            args.kind, args.precision, n[0], n[1], n[2], grid, "reorder" if args.reorder else "no-reorder",
                            "slabs" if args.slabs else "pencils"),
                        "l2": "working set %.0f MB per GPU exceeds the 126 MB L2" % (max(nin, nout) * (8 if prec == 0 else 16) / 1e6),
+                       "l2_slab_mb": os.environ.get("HEFFTE_B200_L2_SLAB_MB"),
                        "comm": ("peer memory: NVLink stores fused into the FFT kernels" if (multi and multi["peer_memory"]) else "nccl send/recv") if distributed else "none"},
             "max_roundtrip_error": None if conv else err,
             "gpu_launches": int(launches),

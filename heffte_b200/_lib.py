@@ -63,6 +63,7 @@ def load():
     sig("b200_fft1d_create", c_int, ctypes.POINTER(b200_fft1d_desc), ctypes.POINTER(c_vp))
     sig("b200_fft1d_destroy", c_int, c_vp)
     sig("b200_fft1d_execute", c_int, c_vp, c_int, c_vp, c_vp, c_dbl, c_vp)
+    sig("b200_fft1d_execute_range", c_int, c_vp, c_int, c_vp, c_vp, c_dbl, c_vp, c_ll, c_ll)
     sig("b200_fft1d_kernel_name", ctypes.c_char_p, c_vp)
     sig("b200_direct_pack", c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_vp, c_vp, c_vp)
     sig("b200_direct_unpack", c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_vp, c_vp, c_vp)

@@ -162,6 +162,16 @@ int b200_fft1d_execute(b200_fft1d_plan plan, int direction, const void *in, void
     return rc;
 }
 
+int b200_fft1d_execute_range(b200_fft1d_plan plan, int direction, const void *in, void *out, double scale, void *stream, long long b_begin, long long b_count){
+    if (plan == nullptr) return fail(B200_ERR_INVALID, "null plan");
+    if (b_count < 0) return fail(B200_ERR_INVALID, "negative line count");
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    int rc = run_host_plan(plan->host, plan->twiddle, direction, in, out, scale, L, nullptr, b_begin, b_count);
+    if (rc == -1) return fail(B200_ERR_UNSUPPORTED, "no kernel for this length");
+    if (rc == B200_ERR_INVALID) return fail(rc, "line range outside the plan");
+    return rc;
+}
+
 int b200_fft1d_execute_scatter(b200_fft1d_plan plan, int direction, const void *in, const void *device_scatter_map, double scale, void *stream){
     if (plan == nullptr or device_scatter_map == nullptr) return fail(B200_ERR_INVALID, "null plan or scatter map");
     cuda_launcher L{static_cast<cudaStream_t>(stream)};

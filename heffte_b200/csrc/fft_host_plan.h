@@ -118,14 +118,25 @@ inline line_geom to_geom(b200_line_geom const &g){ return line_geom{g.stride, g.
 
 // runs the plan through a Launcher (CUDA stream launcher in the product, thread emulation in tests/emul)
 // `scatter` (device pointer to a scatter_map, or null) fuses the following reshape into the store of the transform
+// b_begin / b_count (b_count >= 0) restrict the launch to the lines with b in [b_begin, b_begin + b_count): a slab of the box
 template<typename Launcher>
 int run_host_plan(host_plan const &plan, const void *twiddle, int direction, const void *in, void *out, double scale, Launcher &L,
-                  const void *scatter = nullptr){
+                  const void *scatter = nullptr, long long b_begin = 0, long long b_count = -1){
     b200_fft1d_desc const &d = plan.desc;
-    long long const nlines = d.count_a * d.count_b;
-    if (nlines == 0) return B200_SUCCESS;
     bool const backward = (direction == B200_BACKWARD);
     bool const is_float = (d.precision == B200_PREC_FLOAT);
+    long long nlines = d.count_a * d.count_b;
+    if (b_count >= 0){
+        if (b_begin < 0 or b_begin + b_count > d.count_b or scatter != nullptr) return B200_ERR_INVALID;
+        size_t const rsize = is_float ? 4 : 8;
+        bool const real_in = (d.kind == B200_R2C) ? not backward : (d.kind != B200_C2C);
+        bool const real_out = (d.kind == B200_R2C) ? backward : (d.kind != B200_C2C);
+        b200_line_geom const &gi = backward ? d.out : d.in, &go = backward ? d.in : d.out;
+        in = static_cast<const char*>(in) + b_begin * gi.stride_b * static_cast<long long>(real_in ? rsize : 2 * rsize);
+        out = static_cast<char*>(out) + b_begin * go.stride_b * static_cast<long long>(real_out ? rsize : 2 * rsize);
+        nlines = d.count_a * b_count;
+    }
+    if (nlines == 0) return B200_SUCCESS;
 
     if (plan.family == family_contig_real or plan.family == family_strided_real){
         // contiguous lines: the real line doubles as a line of complex numbers on the r2c load and the c2r store, so the

@@ -534,6 +534,25 @@ int transform3d::run_peer(int precision, bool is_backward, const void *in, void 
     return B200_SUCCESS;
 }
 
+// HEFFTE_B200_L2_SLAB_MB=<megabytes> (default: off) pairs two consecutive local transforms of the same box slab by slab:
+// the first writes a slab of that many megabytes, the second reads it back from the L2 cache instead of HBM (126 MB on
+// B200) and overwrites it in place, so the pair costs one read and one write of HBM instead of two of each.
+// Returns the number of planes (index of the slowest axis) per slab, 0 when the pairing does not apply.
+idx transform3d::l2_slab_planes(int first, int second, int elem_bytes) const {
+    const char *setting = std::getenv("HEFFTE_B200_L2_SLAB_MB");
+    if (setting == nullptr) return 0;
+    double const megabytes = std::atof(setting);
+    if (not (megabytes > 0)) return 0;
+    box3 const &a = lp.out_shape[first][me], &b = lp.out_shape[second][me];
+    if (a.empty() or not a.same_extent(b) or not a.same_order(b)) return 0;
+    int const slow = a.order[2];
+    if (lp.fft_direction[first] == slow or lp.fft_direction[second] == slow) return 0;
+    double const plane_bytes = static_cast<double>(a.osize(0)) * static_cast<double>(a.osize(1)) * elem_bytes;
+    idx planes = static_cast<idx>(megabytes * 1e6 / plane_bytes);
+    planes = std::max<idx>(planes, 1);
+    return (planes >= a.osize(2)) ? 0 : planes;       // one slab = the whole box: nothing to gain
+}
+
 double transform3d::scale_factor(int scaling) const {
     if (scaling == 0) return 1.0;
     return (scaling == 2) ? std::sqrt(base_scale) : base_scale;
@@ -646,6 +665,22 @@ int transform3d::run(int precision, bool is_backward, const void *in, void *out,
             }
             if (s < 3 and X[E[s]]){
                 void *dst = writable ? const_cast<void*>(cur) : ((done_reshapes < total_reshapes) ? temp : out);
+                // two transforms of the same box with nothing between them, neither along the slowest axis: run them slab by slab
+                // so that the second one finds its input in the L2 cache (opt-in, see l2_slab_planes())
+                idx const planes = (s < 2 and not R[s+1] and X[E[s+1]]) ? l2_slab_planes(E[s], E[s+1], elem) : 0;
+                if (planes > 0){
+                    idx const count_b = lp.out_shape[E[s]][me].osize(2);
+                    for(idx b0 = 0; b0 < count_b; b0 += planes){
+                        idx const nb = std::min(planes, count_b - b0);
+                        int rc = b200_fft1d_execute_range(X[E[s]], direction, cur, dst, stage_scale(s), cstream, b0, nb);
+                        if (rc) return rc;
+                        rc = b200_fft1d_execute_range(X[E[s+1]], direction, dst, dst, stage_scale(s+1), cstream, b0, nb);
+                        if (rc) return rc;
+                    }
+                    cur = dst; writable = true;
+                    s++;            // the second transform of the pair is done
+                    continue;
+                }
                 int rc = b200_fft1d_execute(X[E[s]], direction, cur, dst, stage_scale(s), cstream);
                 if (rc) return rc;
                 cur = dst; writable = true;

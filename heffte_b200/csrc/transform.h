@@ -130,6 +130,7 @@ private:
     idx exec_workspace_count;       // what the executed plan needs on the exchange path
     int balanced_swaps = 0;         // box swaps applied by balance_traffic()
     idx workspace_layout(logic_plan const &p, idx &comm_elements, idx &temp_elements) const;
+    idx l2_slab_planes(int first, int second, int elem_bytes) const;
     double base_scale;
     std::unique_ptr<reshape_op> fwd[4], bwd[4];
     b200_fft1d_plan exec[2][3];

@@ -95,6 +95,11 @@ int b200_fft1d_destroy(b200_fft1d_plan plan);
  * the separate scaling kernel (src/heffte_backend_cuda.cu:138-145, 471-478).  in == out is allowed for C2C/r2r
  * when the two geometries coincide. */
 int b200_fft1d_execute(b200_fft1d_plan plan, int direction, const void *in, void *out, double scale, void *stream);
+/* The same transform restricted to the lines with b in [b_begin, b_begin + b_count) (b = line / count_a): a slab of the box.
+ * `in` / `out` are the addresses of the whole box.  Lets the caller run two transforms slab by slab so that the second one
+ * finds its input in the L2 cache (csrc/transform.cpp, HEFFTE_B200_L2_SLAB_MB). */
+int b200_fft1d_execute_range(b200_fft1d_plan plan, int direction, const void *in, void *out, double scale, void *stream,
+                             long long b_begin, long long b_count);
 /*
  * Same transform with the FOLLOWING RESHAPE FUSED INTO THE STORE: every output element is written straight into the box
  * of the rank that owns it after the reshape -- in local memory or in a peer GPU's memory mapped over NVLink.

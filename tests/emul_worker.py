@@ -31,7 +31,7 @@ def main():
     todo.append((dict(kind="c2c", n=(8, 9, 10), prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 2))
     # power-of-two lines of 32 points: the real-data fast kernels (contiguous and strided, plain and fused-reshape stores)
     for kind, extra, prec in (("r2c", dict(r2c_dir=0), 1), ("r2c", dict(r2c_dir=2), 0), ("cos", {}, 1), ("sin", {}, 0)):
-        if nranks in (2, 8):
+        if nranks in (1, 2, 8):
             todo.append((dict(kind=kind, n=(32, 32, 32), prec=prec, reorder=(kind in ("cos", "sin")), pencils=True, alg=0, gin=gin, gout=gout,
                               order_out=(0, 1, 2), **extra), 1))
     comms = hf.comm_threads(nranks)

@@ -20,6 +20,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     (4, "peer", 11, {"HEFFTE_B200_REFERENCE_PLAN": "1"}),
     (4, "exchange", 13, {"HEFFTE_B200_REFERENCE_PLAN": "1"}),
     (8, "peer", 17, {"HEFFTE_B200_DECOMPOSITION": "pencils", "HEFFTE_B200_NO_DIRECT_OUTPUT": "1"}),
+    # one rank: pairs of local transforms run slab by slab (one plane per slab here), and the plain path next to it
+    (1, "exchange", 2, {"HEFFTE_B200_L2_SLAB_MB": "0.002"}),
+    (1, "exchange", 3, {}),
 ])
 def test_emulated_ranks(nranks, mode, stride, env):
     cmd = [sys.executable, os.path.join(ROOT, "tests", "emul_worker.py"), str(nranks), mode, str(stride)]
