@@ -254,6 +254,20 @@ def b200_arm(args):
     options = hf.plan_options(tag, use_reorder=args.reorder, use_pencils=not args.slabs)
     fft = hf.fft3d_r2c(tag, inbox, outbox, 0, comm, options) if r2c else hf.fft3d(tag, inbox, outbox, comm, options)
 
+    # the plan that runs (pure host planning, csrc/plan_logic.h): process grids of input, the three transform stages, output
+    executed = None
+    try:
+        world_boxes_in = hf.heffte.split_world(world, in_grid)
+        world_boxes_out = hf.heffte.split_world(cworld if r2c else world, out_grid)
+        shapes, _, swaps = hf.heffte.execution_plan(world_boxes_in, world_boxes_out, r2c_direction=0 if r2c else -1,
+                                                    use_reorder=bool(args.reorder or r2r), use_pencils=not args.slabs)
+
+        def grid_of(boxes):
+            return "x".join(str(len({(b[d], b[3 + d]) for b in boxes if all(b[3 + k] >= b[k] for k in range(3))})) for d in range(3))
+        executed = {"grids": " -> ".join(grid_of(shapes[i]) for i in (0, 4, 5, 6, 7)), "refinements_applied": swaps}
+    except Exception as e:  # noqa: BLE001  (reporting only)
+        executed = {"error": repr(e)}
+
     gen = torch.Generator(device="cuda")
     gen.manual_seed(4242 + rank)
     nin, nout = fft.size_inbox(), fft.size_outbox()
@@ -494,6 +508,7 @@ def b200_arm(args):
                            "slabs" if args.slabs else "pencils"),
                        "l2": "working set %.0f MB per GPU exceeds the 126 MB L2" % (max(nin, nout) * (8 if prec == 0 else 16) / 1e6),
                        "l2_slab_mb": os.environ.get("HEFFTE_B200_L2_SLAB_MB"),
+                       "executed_plan": executed,
                        "comm": ("peer memory: NVLink stores fused into the FFT kernels" if (multi and multi["peer_memory"]) else "nccl send/recv") if distributed else "none"},
             "max_roundtrip_error": None if conv else err,
             "gpu_launches": int(launches),

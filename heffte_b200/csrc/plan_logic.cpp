@@ -1,4 +1,5 @@
 #include "plan_logic.h"
+#include "scatter_build.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -369,6 +370,23 @@ double execution_cost(logic_plan const &p, int r2c_direction){
     return total;
 }
 
+// true when every reshape of the plan, in both directions and on every rank, can be expressed as a scatter map (at most
+// scatter_max_cuts cells per axis): otherwise the plan falls back, collectively, to pack / exchange / unpack
+bool fits_scatter_maps(logic_plan const &p){
+    int const n = static_cast<int>(p.in_shape[0].size());
+    std::vector<void*> bases(n, nullptr);
+    scatter_map map;
+    std::string why;
+    for(int i=0; i<4; i++){
+        if (extents_match(p.in_shape[i], p.out_shape[i]) and p.in_shape[i][0].same_order(p.out_shape[i][0])) continue;
+        for(int r=0; r<n; r++){
+            if (not build_scatter_map(p.in_shape[i][r], 0, p.out_shape[i], bases, 1, map, why)) return false;
+            if (not build_scatter_map(p.out_shape[i][r], 0, p.in_shape[i], bases, 1, map, why)) return false;
+        }
+    }
+    return true;
+}
+
 logic_plan make_execution_plan(shape const &inboxes, shape const &outboxes, int r2c_direction, plan_options const &options, int rank, int *swaps){
     if (swaps) *swaps = 0;
     const char *keep = std::getenv("HEFFTE_B200_REFERENCE_PLAN");
@@ -392,7 +410,8 @@ logic_plan make_execution_plan(shape const &inboxes, shape const &outboxes, int 
         try{
             logic_plan plan = make_logic_plan(inboxes, outboxes, r2c_direction, exec_options, rank);
             int const n = balance_traffic(plan, r2c_direction);
-            double const c = execution_cost(plan, r2c_direction);
+            double c = execution_cost(plan, r2c_direction);
+            if (not fits_scatter_maps(plan)) c *= 4.0;      // the exchange path: about four times slower (profiles/r01_multi_8gpu)
             if (best_cost < 0 or c < best_cost * (1.0 - 1e-9)){ best = plan; best_cost = c; best_swaps = n + ((attempt == 1) ? 1 : 0); }
         }catch(std::exception &){
             if (attempt == 0) throw;

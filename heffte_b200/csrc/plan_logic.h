@@ -48,6 +48,7 @@ int balance_traffic(logic_plan &plan, int r2c_direction);
 // HEFFTE_B200_REFERENCE_PLAN=1 in the environment returns the reference's plan unchanged.
 // The sizes a plan REPORTS (size_workspace) always come from the reference's plan.
 double execution_cost(logic_plan const &plan, int r2c_direction);
+bool fits_scatter_maps(logic_plan const &plan);
 logic_plan make_execution_plan(shape const &inboxes, shape const &outboxes, int r2c_direction, plan_options const &options, int rank,
                                int *swaps = nullptr);
 

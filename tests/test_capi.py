@@ -84,6 +84,25 @@ def test_plan_lifecycle_and_return_codes(lib):
     assert lib.heffte_plan_create_r2c(H.backend.b200, ip(world.low), ip(world.high), None, ip(cworld.low), ip(cworld.high), None, 7, comm.handle, None, ctypes.byref(plan)) == 2
 
 
+def test_thread_ranks_need_their_own_stream(lib):
+    """ranks that are host threads of one process share the default stream: plan creation on it is refused (code 2, the
+    exception path of src/heffte_c.cpp:273-277) before any collective call is made"""
+    from heffte_b200 import _lib, heffte as H
+    comms = H.comm_threads(2)
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    low, high = np.array([0, 0, 0], dtype=np.int32), np.array([3, 3, 1], dtype=np.int32)
+    plan = _lib.LP_plan()
+    rc = lib.heffte_plan_create(H.backend.b200, ip(low), ip(high), None, ip(low), ip(high), None, comms[0].handle, None, ctypes.byref(plan))
+    assert rc == 2 and "stream" in _lib.last_error()
+
+
+def test_real_side_entry_points_and_helpers_are_exported(lib):
+    """entry points added next to the reference's: streams, sub-box copy, ranged 1-D execution, executed-plan introspection"""
+    for name in ("b200_stream_create", "b200_stream_destroy", "b200_copy_subbox", "b200_fft1d_execute_range", "heffte_b200_execution_plan",
+                 "heffte_forward_d2z", "heffte_backward_z2d", "heffte_forward_s2c", "heffte_backward_c2s"):
+        assert hasattr(lib, name), name
+
+
 def test_no_cpu_fallback(lib):
     """Without a CUDA device every compute entry point must fail loudly (never compute on the host)."""
     if lib.b200_device_count() > 0:
