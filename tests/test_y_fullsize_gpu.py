@@ -15,6 +15,8 @@ from tests.helpers import TOL, to_h
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
+FULL = (512, 512, 512)      # speed3d_c2c / r2c / r2r double 512^3 of BASELINE.json
+
 
 def _rel(a, b):
     return float((torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b)).item())
@@ -77,7 +79,7 @@ def test_c2c_properties_at_full_size(lib, n, prec):
 def test_r2c_matches_the_complex_plan_at_512(lib):
     """speed3d_r2c double 512^3: the half spectrum equals the first 257 entries (dimension 0) of the complex transform"""
     import heffte_b200 as hf
-    n = (512, 512, 512)
+    n = FULL
     count, half = n[0] * n[1] * n[2], (n[0] // 2 + 1) * n[1] * n[2]
     gen = torch.Generator(device="cuda")
     gen.manual_seed(11)
@@ -100,7 +102,7 @@ def test_dct_properties_at_512(lib):
     """speed3d_r2r double 512^3 (DCT-II forward, DCT-III backward): round trip with scale::full, linearity, and the
     zero-frequency entry 8 * sum(x) of the unnormalised REDFT10 (include/heffte_fft3d.h:737-746)"""
     import heffte_b200 as hf
-    n = (512, 512, 512)
+    n = FULL
     count = n[0] * n[1] * n[2]
     gen = torch.Generator(device="cuda")
     gen.manual_seed(5)
