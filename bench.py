@@ -499,6 +499,7 @@ def b200_arm(args):
 
     if rank == 0:
         grid = "x".join(str(v) for v in in_grid)
+        working_set_mb = max(nin, nout) * ((4 if prec == 0 else 8) * (1 if r2r else 2)) / 1e6
         line = {
             "metric": "speed3d_%s GFlop/s (5*N*log2(N)/t)" % args.kind, "value": value, "unit": "GFlop/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -506,7 +507,8 @@ def b200_arm(args):
             "config": {"workload": "speed3d_%s %s %dx%dx%d, bricks %s, %s, %s, in-place, step = forward(scale full)+backward" % (
                            args.kind, args.precision, n[0], n[1], n[2], grid, "reorder" if args.reorder else "no-reorder",
                            "slabs" if args.slabs else "pencils"),
-                       "l2": "working set %.0f MB per GPU exceeds the 126 MB L2" % (max(nin, nout) * (8 if prec == 0 else 16) / 1e6),
+                       "l2": ("working set %.0f MB per GPU exceeds the 126 MB L2" if working_set_mb > 126 else
+                              "working set %.0f MB per GPU FITS in the 126 MB L2 and nothing flushes it: not a valid bench configuration") % working_set_mb,
                        "l2_slab_mb": os.environ.get("HEFFTE_B200_L2_SLAB_MB"),
                        "executed_plan": executed,
                        "comm": ("peer memory: NVLink stores fused into the FFT kernels" if (multi and multi["peer_memory"]) else "nccl send/recv") if distributed else "none"},
