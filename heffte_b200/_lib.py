@@ -85,6 +85,8 @@ def load():
     sig("heffte_plan_create", c_int, c_int, ip, ip, ip, ip, ip, ip, c_vp, ctypes.POINTER(heffte_plan_options), ctypes.POINTER(LP_plan))
     sig("heffte_plan_create_r2c", c_int, c_int, ip, ip, ip, ip, ip, ip, c_int, c_vp, ctypes.POINTER(heffte_plan_options), ctypes.POINTER(LP_plan))
     sig("heffte_plan_create_stream", c_int, c_int, c_vp, ip, ip, ip, ip, ip, ip, c_int, c_vp, ctypes.POINTER(heffte_plan_options), ctypes.POINTER(LP_plan))
+    sig("heffte_plan_create_subcomm", c_int, c_int, c_vp, ip, ip, ip, ip, ip, ip, c_int, c_vp, ctypes.POINTER(heffte_plan_options), c_int,
+        ctypes.POINTER(LP_plan))
     sig("heffte_plan_destroy", c_int, LP_plan)
     for name in ("heffte_size_inbox", "heffte_size_outbox", "heffte_size_workspace", "heffte_get_backend", "heffte_is_r2c"):
         sig(name, c_int, LP_plan)

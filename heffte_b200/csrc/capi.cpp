@@ -71,7 +71,7 @@ plan_options options_from(int backend, heffte_plan_options const *o){
 
 int create_plan(int backend, void *stream, int const inbox_low[3], int const inbox_high[3], int const *inbox_order,
                 int const outbox_low[3], int const outbox_high[3], int const *outbox_order,
-                int r2c_direction, bool r2c, heffte_comm const comm, heffte_plan_options const *options, heffte_plan *plan){
+                int r2c_direction, bool r2c, heffte_comm const comm, heffte_plan_options const *options, heffte_plan *plan, int subranks = -1){
     if (plan == nullptr) return 2;
     *plan = nullptr;
     if (not known_backend(backend)){ set_error("invalid backend id (this library implements Heffte_BACKEND_B200*)"); return 1; }
@@ -81,9 +81,11 @@ int create_plan(int backend, void *stream, int const inbox_low[3], int const inb
     if (r2c and (r2c_direction < 0 or r2c_direction > 2)){ set_error("r2c_direction must be 0, 1 or 2"); return 2; }
     try{
         std::unique_ptr<plan_state> state(new plan_state());
+        plan_options effective = options_from(backend, options);
+        effective.subranks = subranks;
         state->fft.reset(new transform3d(kind_of(backend, r2c), box_from(inbox_low, inbox_high, inbox_order),
                                          box_from(outbox_low, outbox_high, outbox_order), r2c_direction,
-                                         comm->impl.get(), options_from(backend, options), static_cast<cudaStream_t>(stream)));
+                                         comm->impl.get(), effective, static_cast<cudaStream_t>(stream)));
         heffte_fft_plan *handle = new heffte_fft_plan;
         handle->backend_type = backend;
         handle->using_r2c = r2c ? 1 : 0;
@@ -208,6 +210,13 @@ int heffte_plan_create_stream(int backend, void *cuda_stream, int const inbox_lo
                               int r2c_direction, heffte_comm const comm, heffte_plan_options const *options, heffte_plan *plan){
     return create_plan(backend, cuda_stream, inbox_low, inbox_high, inbox_order, outbox_low, outbox_high, outbox_order,
                        r2c_direction, r2c_direction >= 0, comm, options, plan);
+}
+
+int heffte_plan_create_subcomm(int backend, void *cuda_stream, int const inbox_low[3], int const inbox_high[3], int const *inbox_order,
+                               int const outbox_low[3], int const outbox_high[3], int const *outbox_order,
+                               int r2c_direction, heffte_comm const comm, heffte_plan_options const *options, int num_subranks, heffte_plan *plan){
+    return create_plan(backend, cuda_stream, inbox_low, inbox_high, inbox_order, outbox_low, outbox_high, outbox_order,
+                       r2c_direction, r2c_direction >= 0, comm, options, plan, (num_subranks > 0) ? num_subranks : -1);
 }
 
 int heffte_plan_destroy(heffte_plan plan){

@@ -85,6 +85,11 @@ class plan_options:
         self.algorithm = algorithm
         self.use_pencils = bool(use_pencils)
         self.use_gpu_aware = bool(use_gpu_aware)
+        self.num_subranks = -1
+
+    def use_subcomm(self, num_subranks):
+        """reference include/heffte_plan_logic.h:100-129 (C++ only there): intermediate stages on the first num_subranks ranks"""
+        self.num_subranks = int(num_subranks)
 
     def as_struct(self):
         return heffte_plan_options(int(self.use_reorder), int(self.algorithm), int(self.use_pencils), int(self.use_gpu_aware))
@@ -215,10 +220,11 @@ def _create(backend_tag, inbox, outbox, r2c_direction, comm, options, stream):
     plan.backend_tag = backend_tag
     plan.use_r2c = r2c_direction >= 0
     plan.plan = LP_plan()
-    opts = (options if options is not None else plan_options(backend_tag)).as_struct()
-    herr = lib.heffte_plan_create_stream(backend_tag, ctypes.c_void_p(stream or 0), _iptr(inbox.low), _iptr(inbox.high), _iptr(inbox.order),
-                                         _iptr(outbox.low), _iptr(outbox.high), _iptr(outbox.order), r2c_direction,
-                                         comm.handle, ctypes.byref(opts), ctypes.byref(plan.plan))
+    chosen = options if options is not None else plan_options(backend_tag)
+    opts = chosen.as_struct()
+    herr = lib.heffte_plan_create_subcomm(backend_tag, ctypes.c_void_p(stream or 0), _iptr(inbox.low), _iptr(inbox.high), _iptr(inbox.order),
+                                          _iptr(outbox.low), _iptr(outbox.high), _iptr(outbox.order), r2c_direction,
+                                          comm.handle, ctypes.byref(opts), getattr(chosen, "num_subranks", -1), ctypes.byref(plan.plan))
     if herr != 0:
         plan.plan = None
         raise heffte_input_error("heFFTe encountered internal error with code: {0:1d} ({1})".format(herr, _lib.last_error()))

@@ -93,6 +93,13 @@ int heffte_comm_destroy(heffte_comm comm);
 int heffte_plan_create_stream(int backend, void *cuda_stream, int const inbox_low[3], int const inbox_high[3], int const *inbox_order,
                               int const outbox_low[3], int const outbox_high[3], int const *outbox_order,
                               int r2c_direction /* -1 unless r2c */, heffte_comm const comm, heffte_plan_options const *options, heffte_plan *plan);
+/* same with the C++-only option plan_options::use_subcomm(num_subranks) (include/heffte_plan_logic.h:100-129): the intermediate
+ * stages of the transform are held by the first num_subranks ranks only (small problems on many GPUs); <= 0 or >= the size of
+ * the communicator means all ranks */
+int heffte_plan_create_subcomm(int backend, void *cuda_stream, int const inbox_low[3], int const inbox_high[3], int const *inbox_order,
+                               int const outbox_low[3], int const outbox_high[3], int const *outbox_order,
+                               int r2c_direction /* -1 unless r2c */, heffte_comm const comm, heffte_plan_options const *options,
+                               int num_subranks, heffte_plan *plan);
 /* heffte_c.h:87  */ int heffte_plan_destroy(heffte_plan plan);
 /* heffte_c.h:93  */ int heffte_size_inbox(heffte_plan const plan);
 /* heffte_c.h:98  */ int heffte_size_outbox(heffte_plan const plan);

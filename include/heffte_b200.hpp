@@ -113,6 +113,11 @@ struct plan_options {
     reshape_algorithm algorithm;
     bool use_pencils;
     bool use_gpu_aware;
+    //! include/heffte_plan_logic.h:100-129: hold the intermediate stages on the first num_subranks ranks only
+    void use_subcomm(int num_subranks){ num_sub = num_subranks; }
+    int get_subranks() const { return num_sub; }
+private:
+    int num_sub = -1;
 };
 template<typename backend_tag> inline plan_options default_options(){ return plan_options(backend_tag()); }
 
@@ -249,8 +254,8 @@ namespace b200_detail {
             int const lo_out[3] = {static_cast<int>(outbox.low[0]), static_cast<int>(outbox.low[1]), static_cast<int>(outbox.low[2])};
             int const hi_out[3] = {static_cast<int>(outbox.high[0]), static_cast<int>(outbox.high[1]), static_cast<int>(outbox.high[2])};
             heffte_plan_options opts{o.use_reorder ? 1 : 0, static_cast<int>(o.algorithm), o.use_pencils ? 1 : 0, o.use_gpu_aware ? 1 : 0};
-            int const code = heffte_plan_create_stream(backend_id, stream, lo_in, hi_in, inbox.order.data(), lo_out, hi_out, outbox.order.data(),
-                                                       r2c_direction, c.get(), &opts, &plan);
+            int const code = heffte_plan_create_subcomm(backend_id, stream, lo_in, hi_in, inbox.order.data(), lo_out, hi_out, outbox.order.data(),
+                                                        r2c_direction, c.get(), &opts, o.get_subranks(), &plan);
             if (code != 0) throw std::runtime_error(std::string("heffte::fft3d (b200) plan creation failed: ") + heffte_last_error());
         }
         void execute(int precision, int direction, int batch, void const *input, void *output, void *workspace, scale scaling) const {

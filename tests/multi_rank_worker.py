@@ -52,6 +52,12 @@ def configs(nranks, quick):
                                     order_out=(0, 1, 2), r2c_dir=r2c_dir))
         for kind in ("cos", "sin", "cos1"):
             out.append(dict(kind=kind, n=sizes[0], prec=1, reorder=True, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)))
+    # sub-communicators (test/test_subcomm.cpp): the intermediate stages live on the first ranks only
+    if nranks >= 4:
+        gin, gout = grids_for(nranks)[0]
+        for kind, sub in (("c2c", nranks // 2), ("r2c", 1), ("c2c", 3)):
+            out.append(dict(kind=kind, n=sizes[0], prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2),
+                            subranks=sub, r2c_dir=0))
     # power-of-two sizes that take the fast kernels on every stage
     n = (64, 64, 64) if quick else (128, 128, 128)
     gin, gout = grids_for(nranks)[0]
@@ -108,6 +114,8 @@ def run_config(hf, torch, comm, rank, c, batch=1, stream=None, expect_peer=None,
     x = x.astype(cdt if complex_in else rdt)
     tag = {"c2c": hf.backend.b200, "r2c": hf.backend.b200, "cos": hf.backend.b200_cos, "sin": hf.backend.b200_sin, "cos1": hf.backend.b200_cos1}[kind]
     opts = hf.plan_options(tag, use_reorder=c["reorder"], algorithm=c["alg"], use_pencils=c["pencils"])
+    if c.get("subranks"):
+        opts.use_subcomm(c["subranks"])      # test/test_subcomm.cpp: intermediate stages on fewer ranks
     if kind == "r2c":
         fft = hf.fft3d_r2c(tag, to_h(inbox), to_h(outbox), r2c_dir, comm, opts, stream=stream)
     else:
