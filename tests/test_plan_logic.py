@@ -84,6 +84,27 @@ def test_plan_sweep_against_live_reference(lib, reference):
     assert checked > 300
 
 
+def test_subcomm_plans_against_live_reference(lib, reference):
+    """plan_options::use_num_subranks (include/heffte_plan_logic.h:100-129, test/test_subcomm.cpp): intermediate stages on the
+    first ranks only, the others hold empty boxes"""
+    from heffte_b200 import heffte as H
+    checked = 0
+    for n, nranks in itertools.product([(8, 8, 8), (12, 10, 9), (16, 16, 16)], (4, 6, 8, 12)):
+        world = O.world_box(n)
+        gin = reference.proc_setup_min_surface(world, nranks)
+        inboxes = bricks(world, gin)
+        for sub, r2c_dir, reorder, pencils in itertools.product((1, 2, 3, nranks // 2), (-1, 0), (False, True), (True, False)):
+            oworld = world.r2c(r2c_dir) if r2c_dir >= 0 else world
+            outboxes = bricks(oworld, gin)
+            for rank in (0, nranks - 1):
+                ref = reference.plan_operations(inboxes, outboxes, r2c_dir=r2c_dir, use_reorder=reorder, use_pencils=pencils, subranks=sub, rank=rank)
+                mine = H.logic_plan([to_h(b) for b in inboxes], [to_h(b) for b in outboxes], r2c_direction=r2c_dir, use_reorder=reorder,
+                                    use_pencils=pencils, subranks=sub, rank=rank)
+                assert mine[1] == ref[1] and mine[0] == ref[0], (n, nranks, sub, r2c_dir, reorder, pencils, rank)
+                checked += 1
+    assert checked > 300
+
+
 def test_reshape_pieces_against_oracle(lib):
     from heffte_b200 import heffte as H
     world = O.world_box((9, 10, 11))
