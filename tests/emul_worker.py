@@ -26,7 +26,7 @@ def main():
     import heffte_b200 as hf
     from tests.multi_rank_worker import HostArrays, configs, grids_for, run_config
 
-    todo = [(c, 1) for c in configs(nranks, quick=True) if max(c["n"]) <= 32][::stride]
+    todo = [(c, 1) for c in configs(nranks, quick=True, subcomm=True) if max(c["n"]) <= 32][::stride]
     gin, gout = grids_for(nranks)[0]
     todo.append((dict(kind="c2c", n=(8, 9, 10), prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 2))
     # power-of-two lines of 32 points: the real-data fast kernels (contiguous and strided, plain and fused-reshape stores)

@@ -32,7 +32,7 @@ def grids_for(nranks):
     return table.get(nranks, [((1, 1, nranks), (nranks, 1, 1))])
 
 
-def configs(nranks, quick):
+def configs(nranks, quick, subcomm=False):
     out = []
     sizes = [(16, 16, 16), (20, 21, 22)] if quick else [(16, 16, 16), (20, 21, 22), (64, 64, 64), (32, 48, 40)]
     for gi, (gin, gout) in enumerate(grids_for(nranks)):
@@ -53,7 +53,7 @@ def configs(nranks, quick):
         for kind in ("cos", "sin", "cos1"):
             out.append(dict(kind=kind, n=sizes[0], prec=1, reorder=True, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)))
     # sub-communicators (test/test_subcomm.cpp): the intermediate stages live on the first ranks only
-    if nranks >= 4:
+    if subcomm and nranks >= 4:
         gin, gout = grids_for(nranks)[0]
         for kind, sub in (("c2c", nranks // 2), ("r2c", 1), ("c2c", 3)):
             out.append(dict(kind=kind, n=sizes[0], prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2),
@@ -185,7 +185,7 @@ def main():
     done, worst = 0, 0.0
     failed = None
     gin, gout = grids_for(size)[0]
-    todo = [(c, 1) for c in configs(size, args.quick)]
+    todo = [(c, 1) for c in configs(size, args.quick, subcomm=True)]
     # batched transforms across ranks (test/test_fft3d.h:505-572)
     todo.append((dict(kind="c2c", n=(16, 18, 20), prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 3))
     flag = torch.zeros(1, device="cuda", dtype=torch.int32)

@@ -1,5 +1,6 @@
 """
-The user programs of tests/test_cpp_frontend.py (C++ front-end example, plain-C scenario of the reference's test/test_c.c) run
+Late additions of the round (the file sorts last): sub-communicator plans on thread-ranks, and
+the user programs of tests/test_cpp_frontend.py (C++ front-end example, plain-C scenario of the reference's test/test_c.c) run
 against the real library on the GPU: two thread-ranks on one device, one CUDA stream per rank, c2c + r2c + cosine plans.
 """
 import os
@@ -24,3 +25,15 @@ def test_c_program_runs_on_the_gpu(built_library):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "test_c_b200: ok" in r.stdout
+
+
+@pytest.mark.parametrize("nranks", [4, 8])
+def test_subcomm_plans_on_thread_ranks(lib, nranks):
+    """plan_options::use_subcomm (test/test_subcomm.cpp): the intermediate stages live on the first ranks, the others hold empty boxes"""
+    from tests.multi_rank_worker import configs
+    from tests.test_gpu_threads import _run_group
+    os.environ.pop("HEFFTE_B200_DISABLE_P2P", None)
+    todo = [(c, 1) for c in configs(nranks, quick=True, subcomm=True) if c.get("subranks")]
+    assert len(todo) == 3
+    done, _ = _run_group(nranks, todo, expect_peer=True)
+    assert done == len(todo)
