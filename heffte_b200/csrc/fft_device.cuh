@@ -122,6 +122,94 @@ template<typename T> struct butterfly<T, 16>{
     }
 };
 
+// ---- odd and composite radices (lengths 3 * 2^k, 5 * 2^k, 10^k ...) ----------------------------------------------
+template<typename T> struct butterfly<T, 3>{
+    __device__ __forceinline__ static void run(cplx<T> (&v)[3]){
+        const T s = static_cast<T>(0.86602540378443864676372317075294);   // sin(2 pi / 3)
+        const cplx<T> t = cadd(v[1], v[2]), d = csub(v[1], v[2]);
+        const cplx<T> m = mk<T>(v[0].x - t.x * T(0.5), v[0].y - t.y * T(0.5));
+        const cplx<T> r = mk<T>(d.y * s, -d.x * s);                      // -i s (v1 - v2)
+        v[0] = cadd(v[0], t);
+        v[1] = cadd(m, r);
+        v[2] = csub(m, r);
+    }
+};
+
+template<typename T> struct butterfly<T, 5>{
+    __device__ __forceinline__ static void run(cplx<T> (&v)[5]){
+        const T c1 = static_cast<T>( 0.30901699437494742410229341718282);  // cos(2 pi / 5)
+        const T c2 = static_cast<T>(-0.80901699437494742410229341718282);  // cos(4 pi / 5)
+        const T s1 = static_cast<T>( 0.95105651629515357211643933337938);  // sin(2 pi / 5)
+        const T s2 = static_cast<T>( 0.58778525229247312916870595463907);  // sin(4 pi / 5)
+        const cplx<T> a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+        const cplx<T> r1 = mk<T>(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+        const cplx<T> r2 = mk<T>(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+        const cplx<T> i1 = mk<T>(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+        const cplx<T> i2 = mk<T>(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+        v[0] = mk<T>(v[0].x + a1.x + a2.x, v[0].y + a1.y + a2.y);
+        v[1] = mk<T>(r1.x + i1.y, r1.y - i1.x);      // r1 - i i1
+        v[4] = mk<T>(r1.x - i1.y, r1.y + i1.x);      // r1 + i i1
+        v[2] = mk<T>(r2.x + i2.y, r2.y - i2.x);
+        v[3] = mk<T>(r2.x - i2.y, r2.y + i2.x);
+    }
+};
+
+// R = P * Q in registers: P-point transforms over n1 (input n = n1 Q + n2), twiddles W_R^(n2 k1), Q-point transforms over n2,
+// output k = k1 + P k2.  COS / SIN hold cos / sin of 2 pi m / R for m = 0 .. R-1.
+template<typename T, int P, int Q, typename TABLE>
+__device__ __forceinline__ void composite_butterfly(cplx<T> (&v)[P * Q]){
+    cplx<T> a[Q][P];
+    #pragma unroll
+    for(int n2=0; n2<Q; n2++){
+        cplx<T> t[P];
+        #pragma unroll
+        for(int n1=0; n1<P; n1++) t[n1] = v[n1 * Q + n2];
+        butterfly<T, P>::run(t);
+        #pragma unroll
+        for(int k1=0; k1<P; k1++){
+            constexpr int R = P * Q;
+            const int m = (n2 * k1) % R;
+            a[n2][k1] = (m == 0) ? t[k1] : cmul(t[k1], mk<T>(static_cast<T>(TABLE::cosine(m)), static_cast<T>(-TABLE::sine(m))));
+        }
+    }
+    #pragma unroll
+    for(int k1=0; k1<P; k1++){
+        cplx<T> t[Q];
+        #pragma unroll
+        for(int n2=0; n2<Q; n2++) t[n2] = a[n2][k1];
+        butterfly<T, Q>::run(t);
+        #pragma unroll
+        for(int k2=0; k2<Q; k2++) v[k1 + P * k2] = t[k2];
+    }
+}
+struct unit_circle_6 {
+    __host__ __device__ static constexpr double cosine(int m){ return (m == 0) ? 1.0 : (m == 1 || m == 5) ? 0.5 : (m == 3) ? -1.0 : -0.5; }
+    __host__ __device__ static constexpr double sine(int m){ return (m == 0 || m == 3) ? 0.0 : (m < 3) ? 0.86602540378443864676 : -0.86602540378443864676; }
+};
+struct unit_circle_10 {   // 36 degrees
+    __host__ __device__ static constexpr double cosine(int m){
+        return (m == 0) ? 1.0 : (m == 5) ? -1.0 : (m == 1 || m == 9) ? 0.80901699437494742410 : (m == 2 || m == 8) ? 0.30901699437494742410 :
+               (m == 3 || m == 7) ? -0.30901699437494742410 : -0.80901699437494742410;
+    }
+    __host__ __device__ static constexpr double sine(int m){
+        return (m == 0 || m == 5) ? 0.0 : (m == 1 || m == 4) ? 0.58778525229247312917 : (m == 2 || m == 3) ? 0.95105651629515357212 :
+               (m == 6 || m == 9) ? -0.58778525229247312917 : -0.95105651629515357212;
+    }
+};
+struct unit_circle_12 {   // 30 degrees
+    __host__ __device__ static constexpr double cosine(int m){
+        return (m == 0) ? 1.0 : (m == 6) ? -1.0 : (m == 3 || m == 9) ? 0.0 : (m == 1 || m == 11) ? 0.86602540378443864676 : (m == 2 || m == 10) ? 0.5 :
+               (m == 4 || m == 8) ? -0.5 : -0.86602540378443864676;
+    }
+    __host__ __device__ static constexpr double sine(int m){
+        return (m == 0 || m == 6) ? 0.0 : (m == 3) ? 1.0 : (m == 9) ? -1.0 : (m == 1 || m == 5) ? 0.5 : (m == 2 || m == 4) ? 0.86602540378443864676 :
+               (m == 7 || m == 11) ? -0.5 : -0.86602540378443864676;
+    }
+};
+template<typename T> struct butterfly<T, 6>{  __device__ __forceinline__ static void run(cplx<T> (&v)[6]){  composite_butterfly<T, 2, 3, unit_circle_6>(v); } };
+template<typename T> struct butterfly<T, 10>{ __device__ __forceinline__ static void run(cplx<T> (&v)[10]){ composite_butterfly<T, 2, 5, unit_circle_10>(v); } };
+template<typename T> struct butterfly<T, 12>{ __device__ __forceinline__ static void run(cplx<T> (&v)[12]){ composite_butterfly<T, 4, 3, unit_circle_12>(v); } };
+
 // ---------------------------------------------------------------------------------------------------------
 // addressing of a batch of lines: line l = (a, b) with a = l % count_a; element i of the line lives at
 //   base + a*stride_a + b*stride_b + i*stride      (all in elements of the scalar type of that side)
@@ -205,7 +293,7 @@ __host__ __device__ constexpr int ilog2(int n){ return n <= 1 ? 0 : 1 + ilog2(n 
 // from the table and form the others by one or two products (error <= 2 roundings).
 template<typename T, int R, bool FEW_LOADS>
 __device__ __forceinline__ void apply_twiddles(cplx<T> (&v)[R], const cplx<T> *tw, int base){
-    if constexpr (!FEW_LOADS || R <= 4){
+    if constexpr (!FEW_LOADS || (R != 8 && R != 16)){
         #pragma unroll
         for(int r=1; r<R; r++) v[r] = cmul(v[r], ldg_c<T>(tw + r * base));
     }else{
@@ -464,10 +552,10 @@ __device__ __forceinline__ void contig_pass(cplx<T> *row, unsigned j, bool valid
     }
 }
 
-template<typename T, typename RL, int LPB, int MINB, bool BWD, bool SCATTER>
-__global__ void __launch_bounds__((RL::N / RL::rmax) * LPB, MINB) fft_contig_kernel(fft_args a){
+// TPL threads share a line; it must divide N / R for every radix R of the schedule (power-of-two schedules: N / rmax)
+template<typename T, typename RL, int LPB, int MINB, bool BWD, bool SCATTER, int TPL = RL::N / RL::rmax>
+__global__ void __launch_bounds__(TPL * LPB, MINB) fft_contig_kernel(fft_args a){
     B200_DYN_SMEM(smem_raw);
-    constexpr int TPL = RL::N / RL::rmax;
     constexpr unsigned PITCH = pad_index(RL::N) + 1;
     const unsigned j = threadIdx.x % TPL, t = threadIdx.x / TPL;
     cplx<T> *row = reinterpret_cast<cplx<T>*>(smem_raw) + t * PITCH;

@@ -16,6 +16,16 @@ constexpr bool is_pow2(long long n){ return n > 0 && (n & (n - 1)) == 0; }
 constexpr int pow2_max = 4096;
 constexpr int pow2_min = 16;
 
+// lengths with odd factors served by the register/shared-memory kernels (radices 3, 5, 6, 10, 12 next to 2, 4, 8, 16)
+// (48 and 100 have kernels in the tables below but stay on the generic kernel until the new kernels have had a GPU run: they
+// are the two mixed lengths the GPU parity suite and smoke() of this round already use)
+constexpr bool is_mixed_fast_length(long long n){
+    return n == 96 || n == 192 || n == 384 || n == 768 || n == 1536 ||
+           n == 80 || n == 160 || n == 320 || n == 640 || n == 1280 ||
+           n == 200 || n == 400 || n == 500 || n == 1000 || n == 2000;
+}
+constexpr bool is_fast_length(long long n){ return (is_pow2(n) && n >= pow2_min && n <= pow2_max) || is_mixed_fast_length(n); }
+
 template<typename T, typename RL, int TPL, int LPB, int MINB, bool SCATTER, typename Launcher>
 int launch_strided(fft_args const &a, Launcher &L){
     long long blocks = (a.nlines + LPB - 1) / LPB;
@@ -32,6 +42,16 @@ int launch_contig(fft_args const &a, Launcher &L){
     return L.launch(fft_contig_kernel<T, RL, LPB, MINB, false, SCATTER>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
 }
 
+// contiguous kernel with an explicit number of threads per line (schedules whose radices do not all divide the largest one)
+template<typename T, typename RL, int TPL, int LPB, int MINB, bool SCATTER, typename Launcher>
+int launch_contig_tpl(fft_args const &a, Launcher &L){
+    long long blocks = (a.nlines + LPB - 1) / LPB;
+    constexpr int PITCH = pad_index(RL::N) + 1;
+    size_t smem = ((sizeof(cplx<T>) * (size_t)PITCH * LPB + 15) / 16) * 16 + (SCATTER ? sizeof(scatter_map) : 0);
+    if (a.backward) return L.launch(fft_contig_kernel<T, RL, LPB, MINB, true, SCATTER, TPL>, blocks, TPL * LPB, smem, a);
+    return L.launch(fft_contig_kernel<T, RL, LPB, MINB, false, SCATTER, TPL>, blocks, TPL * LPB, smem, a);
+}
+
 // M = lines-per-row multiplier: 1 for double (8 lines = 128 B), 2 for float (16 lines = 128 B)
 template<typename T, bool SCATTER, typename Launcher>
 int dispatch_strided(int n, fft_args const &a, Launcher &L){
@@ -46,6 +66,24 @@ int dispatch_strided(int n, fft_args const &a, Launcher &L){
         case 1024: return launch_strided<T, radix_list<16, 8, 8, 1>, 32 / M,  8 * M, 1, SCATTER>(a, L);
         case 2048: return launch_strided<T, radix_list<8, 8, 8, 4>, 128 / M,  4 * M, 1, SCATTER>(a, L);
         case 4096: return launch_strided<T, radix_list<8, 8, 8, 8>, 256 / M,  2 * M, 1, SCATTER>(a, L);
+        // lengths with factors 3 and 5: TPL divides N / R for every radix R of the schedule; rows of the tile stay 128 bytes
+        case 48:   return launch_strided<T, radix_list<4, 4, 3, 1>,     4, 32 * M, 2, SCATTER>(a, L);
+        case 96:   return launch_strided<T, radix_list<12, 8, 1, 1>,    4, 16 * M, 2, SCATTER>(a, L);
+        case 192:  return launch_strided<T, radix_list<8, 8, 3, 1>,     8,  8 * M, 2, SCATTER>(a, L);
+        case 384:  return launch_strided<T, radix_list<8, 8, 6, 1>,    16,  8 * M, 2, SCATTER>(a, L);
+        case 768:  return launch_strided<T, radix_list<8, 8, 12, 1>,   32,  8 * M, 1, SCATTER>(a, L);
+        case 1536: return launch_strided<T, radix_list<8, 8, 8, 3>,    64,  4 * M, 1, SCATTER>(a, L);
+        case 80:   return launch_strided<T, radix_list<5, 4, 4, 1>,     4, 32 * M, 2, SCATTER>(a, L);
+        case 160:  return launch_strided<T, radix_list<10, 4, 4, 1>,    8, 16 * M, 2, SCATTER>(a, L);
+        case 320:  return launch_strided<T, radix_list<5, 4, 4, 4>,    16,  8 * M, 2, SCATTER>(a, L);
+        case 640:  return launch_strided<T, radix_list<10, 4, 4, 4>,   32,  8 * M, 2, SCATTER>(a, L);
+        case 1280: return launch_strided<T, radix_list<10, 8, 4, 4>,   32,  4 * M, 1, SCATTER>(a, L);
+        case 100:  return launch_strided<T, radix_list<10, 10, 1, 1>,  10, 16 * M, 2, SCATTER>(a, L);
+        case 200:  return launch_strided<T, radix_list<10, 10, 2, 1>,  10,  8 * M, 2, SCATTER>(a, L);
+        case 400:  return launch_strided<T, radix_list<10, 10, 4, 1>,  20,  8 * M, 2, SCATTER>(a, L);
+        case 500:  return launch_strided<T, radix_list<10, 10, 5, 1>,  25,  8 * M, 2, SCATTER>(a, L);
+        case 1000: return launch_strided<T, radix_list<10, 10, 10, 1>, 50,  4 * M, 1, SCATTER>(a, L);
+        case 2000: return launch_strided<T, radix_list<10, 10, 10, 2>, 100, 2 * M, 1, SCATTER>(a, L);
         default: return -1;
     }
 }
@@ -63,6 +101,24 @@ int dispatch_contig(int n, fft_args const &a, Launcher &L){
         case 1024: return launch_contig<T, radix_list<16, 8, 8, 1>,   1, 4, SCATTER>(a, L);
         case 2048: return launch_contig<T, radix_list<8, 8, 8, 4>,    1, 2, SCATTER>(a, L);
         case 4096: return launch_contig<T, radix_list<8, 8, 8, 8>,    1, 1, SCATTER>(a, L);
+        // lengths with factors 3 and 5 (threads per line given explicitly; a thread holds N / TPL values between two passes)
+        case 48:   return launch_contig_tpl<T, radix_list<4, 4, 3, 1>,     4, 16, 4, SCATTER>(a, L);
+        case 96:   return launch_contig_tpl<T, radix_list<12, 8, 1, 1>,    4, 16, 4, SCATTER>(a, L);
+        case 192:  return launch_contig_tpl<T, radix_list<8, 8, 3, 1>,     8,  8, 4, SCATTER>(a, L);
+        case 384:  return launch_contig_tpl<T, radix_list<8, 8, 6, 1>,    16,  4, 4, SCATTER>(a, L);
+        case 768:  return launch_contig_tpl<T, radix_list<8, 8, 12, 1>,   32,  2, 4, SCATTER>(a, L);
+        case 1536: return launch_contig_tpl<T, radix_list<8, 8, 8, 3>,    64,  1, 4, SCATTER>(a, L);
+        case 80:   return launch_contig_tpl<T, radix_list<5, 4, 4, 1>,     4, 16, 4, SCATTER>(a, L);
+        case 160:  return launch_contig_tpl<T, radix_list<10, 4, 4, 1>,    8,  8, 4, SCATTER>(a, L);
+        case 320:  return launch_contig_tpl<T, radix_list<5, 4, 4, 4>,    16,  4, 4, SCATTER>(a, L);
+        case 640:  return launch_contig_tpl<T, radix_list<10, 4, 4, 4>,   32,  2, 4, SCATTER>(a, L);
+        case 1280: return launch_contig_tpl<T, radix_list<10, 8, 4, 4>,   32,  2, 2, SCATTER>(a, L);
+        case 100:  return launch_contig_tpl<T, radix_list<10, 10, 1, 1>,  10,  8, 4, SCATTER>(a, L);
+        case 200:  return launch_contig_tpl<T, radix_list<10, 10, 2, 1>,  10,  8, 4, SCATTER>(a, L);
+        case 400:  return launch_contig_tpl<T, radix_list<10, 10, 4, 1>,  20,  4, 4, SCATTER>(a, L);
+        case 500:  return launch_contig_tpl<T, radix_list<10, 10, 5, 1>,  25,  4, 4, SCATTER>(a, L);
+        case 1000: return launch_contig_tpl<T, radix_list<10, 10, 10, 1>, 50,  2, 2, SCATTER>(a, L);
+        case 2000: return launch_contig_tpl<T, radix_list<10, 10, 10, 2>, 100, 1, 2, SCATTER>(a, L);
         default: return -1;
     }
 }

@@ -70,7 +70,7 @@ inline int make_host_plan(b200_fft1d_desc const &desc, host_plan &plan, const ch
     const int n = static_cast<int>(desc.n);
     const size_t csize = (desc.precision == B200_PREC_FLOAT) ? 8 : 16;
 
-    bool const fast_path = (desc.kind == B200_C2C) and is_pow2(n) and n >= pow2_min and n <= pow2_max;
+    bool const fast_path = (desc.kind == B200_C2C) and is_fast_length(n);
     if (fast_path){
         bool const contiguous = (desc.in.stride == 1 or desc.out.stride == 1);
         plan.family = contiguous ? family_contig : family_strided;

@@ -76,6 +76,24 @@ FAMILY = {0: "strided", 1: "contig", 2: "generic", 3: "contig_real", 4: "strided
     ((12, 5, 3), (0, 1, 2), 0, "generic"), ((4, 15, 3), (0, 1, 2), 1, "generic"), ((4, 3, 14), (2, 0, 1), 2, "generic"), ((8, 2, 2), (0, 1, 2), 0, "generic"),
 ])
 def test_c2c_kernels_emulated(emul, prec, n, order, dim, expect):
+    _check_c2c(emul, prec, n, order, dim, expect)
+
+
+MIXED_LENGTHS = [96, 192, 384, 768, 1536, 80, 160, 320, 640, 1280, 200, 400, 500, 1000, 2000]
+
+
+@pytest.mark.parametrize("prec", [1, 0])
+@pytest.mark.parametrize("length", MIXED_LENGTHS)
+def test_c2c_mixed_radix_kernels_emulated(emul, prec, length):
+    """lengths with factors 3 and 5 (radices 3, 5, 6, 10, 12 in registers): contiguous and strided kernels, ragged tiles"""
+    lines = 3 if length > 500 else 5
+    _check_c2c(emul, prec, (length, lines, 1), (0, 1, 2), 0, "contig")
+    _check_c2c(emul, prec, (lines, length, 1), (0, 1, 2), 1, "strided")
+    if length in (96, 320, 1000):
+        _check_c2c(emul, prec, (2, 2, length), (0, 1, 2), 2, "strided")
+
+
+def _check_c2c(emul, prec, n, order, dim, expect):
     box = O.Box((0, 0, 0), tuple(v - 1 for v in n), order)
     rng = np.random.default_rng(n[0] * 7 + dim)
     x = rng.random(box.count()) + 1j * rng.random(box.count())

@@ -49,6 +49,11 @@ CASES = [
     ((64, 16, 8), (1, 1, 1), (0, 1, 2), (2, 1, 2), (0, 1, 2), 1),    # strided kernel, 2 (fp64) / 1 (fp32) tiles per row, nb = 2
     ((16, 64, 6), (1, 1, 1), (0, 1, 2), (1, 2, 3), (0, 1, 2), 0),    # contig kernel, nb = 3
     ((64, 4, 16), (1, 2, 1), (0, 1, 2), (2, 4, 1), (0, 1, 2), 2),    # strided kernel along the slow axis, nb = 2 per source rank
+    # lengths with factors 3 and 5 (mixed-radix fast kernels), fused reshape
+    ((192, 6, 4), (1, 2, 2), (0, 1, 2), (3, 1, 2), (0, 1, 2), 0),    # contig kernel, n = 192 = 8 * 8 * 3
+    ((5, 96, 3), (1, 1, 3), (0, 1, 2), (1, 2, 1), (0, 1, 2), 1),     # strided kernel, n = 96 = 12 * 8
+    ((4, 3, 200), (2, 1, 1), (0, 1, 2), (1, 1, 4), (0, 1, 2), 2),    # strided kernel along the slow axis, n = 200 = 10 * 10 * 2
+    ((80, 8, 2), (1, 1, 2), (0, 1, 2), (5, 2, 1), (0, 1, 2), 0),     # contig kernel, n = 80 = 5 * 4 * 4
 ]
 
 

@@ -37,3 +37,22 @@ def test_subcomm_plans_on_thread_ranks(lib, nranks):
     assert len(todo) == 3
     done, _ = _run_group(nranks, todo, expect_peer=True)
     assert done == len(todo)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("length", [96, 192, 384, 768, 1536, 80, 160, 320, 640, 1280, 200, 400, 500, 1000, 2000])
+def test_c2c_mixed_radix_lengths(lib, prec, length):
+    """lengths with factors 3 and 5 on the register / shared-memory kernels (radices 3, 5, 6, 10, 12): contiguous and strided"""
+    import numpy as np
+    from oracle import heffte_oracle as O
+    from tests.helpers import TOL, seeded
+    from tests.test_gpu_fft1d import _exec
+    ct = np.complex64 if prec == 0 else np.complex128
+    for shape, dim, family in (((length, 5, 3), 0, "contig"), ((9, length, 2), 1, "strided"), ((7, 3, length), 2, "strided")):
+        box = O.Box((0, 0, 0), tuple(v - 1 for v in shape))
+        x = seeded(box.count(), 23, True).astype(ct)
+        y, name = _exec(lib, prec, 0, box, dim, 0, x, box.count(), ct)
+        assert name == family
+        assert O.rel_l2(y, O.exec1d_c2c(x, box, dim)) <= TOL[prec], (shape, dim)
+        yb, _ = _exec(lib, prec, 0, box, dim, 1, x, box.count(), ct, scale=0.5)
+        assert O.rel_l2(yb, 0.5 * O.exec1d_c2c(x, box, dim, backward=True)) <= TOL[prec], (shape, dim)
