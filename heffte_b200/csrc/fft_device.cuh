@@ -617,11 +617,12 @@ enum real_kind : int { real_r2c = 0, real_cos = 1, real_sin = 2 };
 // position of real number p of a line inside a padded complex row (re/im interleaved)
 __host__ __device__ constexpr unsigned real_pos(unsigned p){ return 2 * pad_index(p >> 1) + (p & 1); }
 
-template<typename T, typename RL, int LPB, int MINB, int KIND, bool BWD, bool SCATTER>
-__global__ void __launch_bounds__((RL::N / RL::rmax) * LPB, MINB) fft_contig_real_kernel(fft_args a){
+// (TPL_: threads per line, see fft_contig_kernel; the first radix of the schedule must be even for the sine kinds)
+template<typename T, typename RL, int LPB, int MINB, int KIND, bool BWD, bool SCATTER, int TPL_ = RL::N / RL::rmax>
+__global__ void __launch_bounds__(TPL_ * LPB, MINB) fft_contig_real_kernel(fft_args a){
     B200_DYN_SMEM(smem_raw);
     constexpr unsigned M = RL::N, NR = 2 * RL::N;
-    constexpr int TPL = RL::N / RL::rmax;
+    constexpr int TPL = TPL_;
     constexpr unsigned PITCH = pad_index(RL::N) + 1;
     constexpr bool R2C = (KIND == real_r2c);
     constexpr bool PROLOGUE = !(R2C && !BWD);               // everything but the real-to-complex forward load

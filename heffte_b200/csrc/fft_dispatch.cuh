@@ -135,6 +135,19 @@ int launch_contig_real(fft_args const &a, Launcher &L){
 
 constexpr int real_pow2_min = 2 * pow2_min;   // real lengths served by the fast real kernels
 constexpr int real_pow2_max = 4096;
+// real lengths n = 2m served by the real-data kernels: powers of two 32 ... 4096 and twice the mixed c2c lengths
+constexpr bool is_fast_real_length(long long n){
+    return (is_pow2(n) && n >= real_pow2_min && n <= real_pow2_max) || (n % 2 == 0 && is_mixed_fast_length(n / 2));
+}
+
+template<typename T, typename RL, int TPL, int LPB, int MINB, int KIND, bool SCATTER, typename Launcher>
+int launch_contig_real_tpl(fft_args const &a, Launcher &L){
+    long long blocks = (a.nlines + LPB - 1) / LPB;
+    constexpr int PITCH = pad_index(RL::N) + 1;
+    size_t smem = ((sizeof(cplx<T>) * (size_t)PITCH * LPB + 15) / 16) * 16 + (SCATTER ? sizeof(scatter_map) : 0);
+    if (a.backward) return L.launch(fft_contig_real_kernel<T, RL, LPB, MINB, KIND, true, SCATTER, TPL>, blocks, TPL * LPB, smem, a);
+    return L.launch(fft_contig_real_kernel<T, RL, LPB, MINB, KIND, false, SCATTER, TPL>, blocks, TPL * LPB, smem, a);
+}
 
 template<typename T, int KIND, bool SCATTER, typename Launcher>
 int dispatch_contig_real_kind(int m, fft_args const &a, Launcher &L){
@@ -149,6 +162,22 @@ int dispatch_contig_real_kind(int m, fft_args const &a, Launcher &L){
         case 512:  return launch_contig_real<T, radix_list<8, 8, 8, 1>,    1, 12, KIND, SCATTER>(a, L);
         case 1024: return launch_contig_real<T, radix_list<16, 8, 8, 1>,   1, 4, KIND, SCATTER>(a, L);
         case 2048: return launch_contig_real<T, radix_list<8, 8, 8, 4>,    1, 2, KIND, SCATTER>(a, L);
+        // m with factors 3 and 5 (real lengths 160 ... 4000); the first radix is even: the sine kinds flip the upper half there
+        case 96:   return launch_contig_real_tpl<T, radix_list<12, 8, 1, 1>,    4, 16, 4, KIND, SCATTER>(a, L);
+        case 192:  return launch_contig_real_tpl<T, radix_list<8, 8, 3, 1>,     8,  8, 4, KIND, SCATTER>(a, L);
+        case 384:  return launch_contig_real_tpl<T, radix_list<8, 8, 6, 1>,    16,  4, 4, KIND, SCATTER>(a, L);
+        case 768:  return launch_contig_real_tpl<T, radix_list<8, 8, 12, 1>,   32,  2, 4, KIND, SCATTER>(a, L);
+        case 1536: return launch_contig_real_tpl<T, radix_list<8, 8, 8, 3>,    64,  1, 4, KIND, SCATTER>(a, L);
+        case 80:   return launch_contig_real_tpl<T, radix_list<4, 4, 5, 1>,     4, 16, 4, KIND, SCATTER>(a, L);
+        case 160:  return launch_contig_real_tpl<T, radix_list<10, 4, 4, 1>,    8,  8, 4, KIND, SCATTER>(a, L);
+        case 320:  return launch_contig_real_tpl<T, radix_list<4, 4, 4, 5>,    16,  4, 4, KIND, SCATTER>(a, L);
+        case 640:  return launch_contig_real_tpl<T, radix_list<10, 4, 4, 4>,   32,  2, 4, KIND, SCATTER>(a, L);
+        case 1280: return launch_contig_real_tpl<T, radix_list<10, 8, 4, 4>,   32,  2, 2, KIND, SCATTER>(a, L);
+        case 200:  return launch_contig_real_tpl<T, radix_list<10, 10, 2, 1>,  10,  8, 4, KIND, SCATTER>(a, L);
+        case 400:  return launch_contig_real_tpl<T, radix_list<10, 10, 4, 1>,  20,  4, 4, KIND, SCATTER>(a, L);
+        case 500:  return launch_contig_real_tpl<T, radix_list<10, 10, 5, 1>,  25,  4, 4, KIND, SCATTER>(a, L);
+        case 1000: return launch_contig_real_tpl<T, radix_list<10, 10, 10, 1>, 50,  2, 2, KIND, SCATTER>(a, L);
+        case 2000: return launch_contig_real_tpl<T, radix_list<10, 10, 10, 2>, 100, 1, 2, KIND, SCATTER>(a, L);
         default: return -1;
     }
 }
@@ -174,6 +203,22 @@ int dispatch_strided_real_kind(int m, fft_args const &a, Launcher &L){
         case 512:  return launch_strided_real<T, radix_list<8, 8, 8, 1>,   32 / F, 16 * F, 1, KIND, SCATTER>(a, L);
         case 1024: return launch_strided_real<T, radix_list<16, 8, 8, 1>,  32 / F,  8 * F, 1, KIND, SCATTER>(a, L);
         case 2048: return launch_strided_real<T, radix_list<8, 8, 8, 4>,  128 / F,  4 * F, 1, KIND, SCATTER>(a, L);
+        // m with factors 3 and 5; even first radix (sine kinds); tiles of 40 ... 96 KB
+        case 96:   return launch_strided_real<T, radix_list<12, 8, 1, 1>,    4, 32 * F, 2, KIND, SCATTER>(a, L);
+        case 192:  return launch_strided_real<T, radix_list<8, 8, 3, 1>,     8, 16 * F, 2, KIND, SCATTER>(a, L);
+        case 384:  return launch_strided_real<T, radix_list<8, 8, 6, 1>,    16, 16 * F, 2, KIND, SCATTER>(a, L);
+        case 768:  return launch_strided_real<T, radix_list<8, 8, 12, 1>,   32,  8 * F, 1, KIND, SCATTER>(a, L);
+        case 1536: return launch_strided_real<T, radix_list<8, 8, 8, 3>,    64,  4 * F, 1, KIND, SCATTER>(a, L);
+        case 80:   return launch_strided_real<T, radix_list<4, 4, 5, 1>,     4, 32 * F, 2, KIND, SCATTER>(a, L);
+        case 160:  return launch_strided_real<T, radix_list<10, 4, 4, 1>,    8, 16 * F, 2, KIND, SCATTER>(a, L);
+        case 320:  return launch_strided_real<T, radix_list<4, 4, 4, 5>,    16, 16 * F, 2, KIND, SCATTER>(a, L);
+        case 640:  return launch_strided_real<T, radix_list<10, 4, 4, 4>,   32,  8 * F, 1, KIND, SCATTER>(a, L);
+        case 1280: return launch_strided_real<T, radix_list<10, 8, 4, 4>,   32,  4 * F, 1, KIND, SCATTER>(a, L);
+        case 200:  return launch_strided_real<T, radix_list<10, 10, 2, 1>,  10, 16 * F, 2, KIND, SCATTER>(a, L);
+        case 400:  return launch_strided_real<T, radix_list<10, 10, 4, 1>,  20,  8 * F, 2, KIND, SCATTER>(a, L);
+        case 500:  return launch_strided_real<T, radix_list<10, 10, 5, 1>,  25,  8 * F, 1, KIND, SCATTER>(a, L);
+        case 1000: return launch_strided_real<T, radix_list<10, 10, 10, 1>, 50,  4 * F, 1, KIND, SCATTER>(a, L);
+        case 2000: return launch_strided_real<T, radix_list<10, 10, 10, 2>, 100, 2 * F, 1, KIND, SCATTER>(a, L);
         default: return -1;
     }
 }

@@ -105,7 +105,7 @@ inline int make_host_plan(b200_fft1d_desc const &desc, host_plan &plan, const ch
     bool const real_kind_ok = (desc.kind == B200_R2C or desc.kind == B200_COS or desc.kind == B200_SIN);
     bool const real_contig = (desc.in.stride == 1 and desc.out.stride == 1);
     bool const real_strided = (desc.in.stride != 1 and desc.out.stride != 1 and desc.in.stride_a == 1 and desc.out.stride_a == 1);
-    if (real_kind_ok and is_pow2(n) and n >= real_pow2_min and n <= real_pow2_max and (real_contig or real_strided)){
+    if (real_kind_ok and is_fast_real_length(n) and (real_contig or real_strided)){
         plan.family = real_contig ? family_contig_real : family_strided_real;
         plan.real_kind = (desc.kind == B200_R2C) ? real_r2c : ((desc.kind == B200_COS) ? real_cos : real_sin);
         plan.table_extra_mod = 4LL * n; plan.table_extra = n + 1;      // W_{4n}^j, j = 0..n (the generic path reads j < n)

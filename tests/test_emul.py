@@ -151,3 +151,30 @@ def test_r2r_emulated(emul, prec, kind, name, n, order, dim):
     assert O.rel_l2(y, O.r2r_forward(x, box, dim, name)) < tol
     z, _ = _run(emul, kind, prec, box, dim, 1, x)
     assert O.rel_l2(z, O.r2r_backward(x, box, dim, name)) < tol
+
+
+@pytest.mark.parametrize("prec", [1, 0])
+@pytest.mark.parametrize("half", MIXED_LENGTHS)
+def test_real_mixed_radix_kernels_emulated(emul, prec, half):
+    """real transforms of length 2 * (a mixed c2c length): r2c / c2r / DCT / DST on the half-length mixed-radix engine"""
+    n = 2 * half
+    if prec == 0 and half not in (96, 160, 500, 2000):
+        pytest.skip("single precision: a sample of the lengths")
+    tol = 2e-5 if prec == 0 else 1e-12
+    for shape, dim, family in (((n, 3, 1), 0, "contig_real"), ((3, n, 1), 1, "strided_real")):
+        box = O.Box((0, 0, 0), tuple(v - 1 for v in shape))
+        rng = np.random.default_rng(half + dim)
+        x = rng.random(box.count())
+        cbox = box.r2c(dim)
+        y, fam = _run(emul, 1, prec, box, dim, 0, x, out_box=cbox)
+        assert FAMILY[fam] == family
+        ref = O.exec1d_r2c(x, box, dim)
+        assert O.rel_l2(y, ref) < tol
+        z, _ = _run(emul, 1, prec, box, dim, 1, ref, out_box=cbox)
+        assert O.rel_l2(z, O.exec1d_c2r(ref, box, dim)) < tol
+        for kind, name in ((2, "cos"), (3, "sin")):
+            f, fam = _run(emul, kind, prec, box, dim, 0, x)
+            assert FAMILY[fam] == family
+            assert O.rel_l2(f, O.r2r_forward(x, box, dim, name)) < 4 * tol
+            b, _ = _run(emul, kind, prec, box, dim, 1, x)
+            assert O.rel_l2(b, O.r2r_backward(x, box, dim, name)) < 4 * tol

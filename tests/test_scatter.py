@@ -94,6 +94,8 @@ def test_fft_with_fused_reshape(emul, prec, case):  # noqa: F811
     ((40, 128, 1), 1, (3, 1, 1), (2, 2, 1)),    # more lines than one tile row, ragged last tile
     ((32, 64, 4), 0, (1, 1, 1), (1, 2, 2)),     # contiguous real kernel, whole tiles per row: round-robin visit of nb = 2 ranges
     ((64, 32, 4), 1, (1, 1, 1), (2, 1, 2)),     # strided real kernel, whole tiles per row: round-robin visit of nb = 2 ranges
+    ((160, 4, 3), 0, (1, 2, 1), (2, 1, 3)),     # contiguous real kernel on the mixed-radix engine (m = 80 = 4 * 4 * 5)
+    ((6, 192, 2), 1, (2, 1, 1), (1, 3, 2)),     # strided real kernel on the mixed-radix engine (m = 96 = 12 * 8)
 ])
 @pytest.mark.parametrize("kind", ["r2c", "c2r", "cos", "sin", "cos_b", "sin_b"])
 def test_real_transforms_with_fused_reshape(emul, kind, n, dim, src_grid, dst_grid, prec):  # noqa: F811

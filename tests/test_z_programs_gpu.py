@@ -56,3 +56,31 @@ def test_c2c_mixed_radix_lengths(lib, prec, length):
         assert O.rel_l2(y, O.exec1d_c2c(x, box, dim)) <= TOL[prec], (shape, dim)
         yb, _ = _exec(lib, prec, 0, box, dim, 1, x, box.count(), ct, scale=0.5)
         assert O.rel_l2(yb, 0.5 * O.exec1d_c2c(x, box, dim, backward=True)) <= TOL[prec], (shape, dim)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("half", [96, 192, 384, 768, 1536, 80, 160, 320, 640, 1280, 200, 400, 500, 1000, 2000])
+def test_real_mixed_radix_lengths(lib, prec, half):
+    """real transforms of length 2 * (a mixed c2c length): r2c / c2r / DCT / DST on the half-length mixed-radix engine"""
+    import numpy as np
+    from oracle import heffte_oracle as O
+    from tests.helpers import TOL, seeded
+    from tests.test_gpu_fft1d import _exec
+    n = 2 * half
+    rt, ct = (np.float32, np.complex64) if prec == 0 else (np.float64, np.complex128)
+    for shape, dim, family in (((n, 3, 2), 0, "contig_real"), ((5, n, 2), 1, "strided_real")):
+        box = O.Box((0, 0, 0), tuple(v - 1 for v in shape))
+        x = seeded(box.count(), 29, False).astype(rt)
+        cbox = box.r2c(dim)
+        y, name = _exec(lib, prec, 1, box, dim, 0, x, cbox.count(), ct, cbox=cbox)
+        assert name == family
+        ref = O.exec1d_r2c(x, box, dim)
+        assert O.rel_l2(y, ref) <= TOL[prec]
+        back, _ = _exec(lib, prec, 1, box, dim, 1, ref.astype(ct), box.count(), rt, cbox=cbox)
+        assert O.rel_l2(back, O.exec1d_c2r(ref, box, dim)) <= TOL[prec]
+        for kid, kind in ((2, "cos"), (3, "sin")):
+            f, name = _exec(lib, prec, kid, box, dim, 0, x, box.count(), rt)
+            assert name == family
+            assert O.rel_l2(f, O.r2r_forward(x, box, dim, kind)) <= 4 * TOL[prec]
+            b, _ = _exec(lib, prec, kid, box, dim, 1, x, box.count(), rt)
+            assert O.rel_l2(b, O.r2r_backward(x, box, dim, kind)) <= 4 * TOL[prec]
