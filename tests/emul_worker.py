@@ -34,6 +34,11 @@ def main():
         if nranks in (1, 2, 8):
             todo.append((dict(kind=kind, n=(32, 32, 32), prec=prec, reorder=(kind in ("cos", "sin")), pencils=True, alg=0, gin=gin, gout=gout,
                               order_out=(0, 1, 2), **extra), 1))
+    # lengths with factors 3 and 5: the mixed-radix kernels inside whole plans (contiguous, strided, fused reshapes, real engine)
+    if nranks in (1, 2) and stride != 6:
+        todo.append((dict(kind="c2c", n=(96, 80, 6), prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 1))
+        todo.append((dict(kind="r2c", n=(160, 96, 4), prec=0, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2), r2c_dir=0), 1))
+        todo.append((dict(kind="cos", n=(160, 192, 4), prec=1, reorder=True, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 1))
     comms = hf.comm_threads(nranks)
     gate = threading.Barrier(nranks)
     failures = [None] * nranks
