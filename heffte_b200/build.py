@@ -72,6 +72,13 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("libheffte_b200.so: link failed:\n" + out.stdout + out.stderr)
     with open(stamp, "w") as f:
         f.write(fp)
+    # every source is recompiled whenever the fingerprint changes: the objects are of no further use, and the tree (objects
+    # included) is what travels to the GPU box
+    for obj in objects:
+        try:
+            os.remove(obj)
+        except OSError:
+            pass
     return library_path()
 
 
