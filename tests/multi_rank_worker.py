@@ -169,6 +169,7 @@ def run_config(hf, torch, comm, rank, c, batch=1, stream=None, expect_peer=None,
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--subcomm", action="store_true", help="also run the sub-communicator plans (test/test_subcomm.cpp)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -185,7 +186,7 @@ def main():
     done, worst = 0, 0.0
     failed = None
     gin, gout = grids_for(size)[0]
-    todo = [(c, 1) for c in configs(size, args.quick, subcomm=True)]
+    todo = [(c, 1) for c in configs(size, args.quick, subcomm=args.subcomm)]
     # batched transforms across ranks (test/test_fft3d.h:505-572)
     todo.append((dict(kind="c2c", n=(16, 18, 20), prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 3))
     flag = torch.zeros(1, device="cuda", dtype=torch.int32)

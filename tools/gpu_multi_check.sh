@@ -4,7 +4,7 @@ N=${1:-4}
 OUT=gpurun_out/multi_${N}gpu_check
 mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 420 $TR --master-port 29701 tests/multi_rank_worker.py --quick > $OUT/parity.log 2>&1; echo "parity rc=$?" | tee -a $OUT/parity.log
+timeout 420 $TR --master-port 29701 tests/multi_rank_worker.py --quick --subcomm > $OUT/parity.log 2>&1; echo "parity rc=$?" | tee -a $OUT/parity.log
 timeout 240 $TR --master-port 29702 bench.py --gpus $N --steps 10 --warmup 3 > $OUT/bench_c2c_f64_512.log 2>&1; echo "bench rc=$?"
 grep -h '"metric"' $OUT/bench_*.log | python -c "
 import sys, json
