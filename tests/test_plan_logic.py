@@ -232,3 +232,26 @@ def test_execution_plan_512_on_8_ranks(lib, monkeypatch):
     # a reorder request does not change the executed plan
     again, _, _ = H.execution_plan(boxes, boxes, use_reorder=True)
     assert again == got
+
+
+def _grids(shapes):
+    def grid_of(boxes):
+        return "x".join(str(len({(b[d], b[3 + d]) for b in boxes if all(b[3 + k] >= b[k] for k in range(3))})) for d in range(3))
+    return " -> ".join(grid_of(shapes[i]) for i in (0, 4, 5, 6, 7))
+
+
+def test_decomposition_chosen_for_the_headline_problem(lib):
+    """512^3 on the min-surface brick grids: the executed plan takes slabs on 4 and 8 ranks (fewer NVLink bytes at the busiest
+    GPU, measured 17.2 vs 16.3 TFlop/s on 8 GPUs) and leaves the 1- and 2-rank plans alone; with 12 ranks the slab plan would
+    need more than 8 cells per axis of a scatter map and is priced as an exchange-path plan"""
+    from heffte_b200 import heffte as H
+    world = O.world_box((512, 512, 512))
+    expect = {1: "1x1x1 -> 1x1x1 -> 1x1x1 -> 1x1x1 -> 1x1x1", 2: "1x1x2 -> 1x1x2 -> 1x1x2 -> 1x2x1 -> 1x1x2",
+              4: "1x2x2 -> 1x2x2 -> 4x1x1 -> 4x1x1 -> 1x2x2", 8: "2x2x2 -> 1x1x8 -> 1x1x8 -> 2x4x1 -> 2x2x2"}
+    for nranks, grids in expect.items():
+        boxes = [to_h(b) for b in bricks(world, tuple(H.proc_setup_min_surface(to_h(world), nranks)))]
+        shapes, _, _ = H.execution_plan(boxes, boxes)
+        assert _grids(shapes) == grids, (nranks, _grids(shapes))
+    boxes = [to_h(b) for b in bricks(world, tuple(H.proc_setup_min_surface(to_h(world), 12)))]
+    shapes, _, _ = H.execution_plan(boxes, boxes)
+    assert "1x1x12" not in _grids(shapes)
