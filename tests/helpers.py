@@ -40,3 +40,34 @@ def line_geometry(box, dim):
     if dim == o[1]:
         return (box.osize(0), 1, box.osize(0) * box.osize(1)), box.osize(0), box.osize(2)
     return (box.osize(0) * box.osize(1), 1, 0), box.osize(0) * box.osize(1), 1
+
+
+def host_ranks(limit=16):
+    """power-of-two number of thread-ranks for the compiled reference: as many as the host has cores, at most `limit`"""
+    import os
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    r = 1
+    while r * 2 <= min(cores, limit):
+        r *= 2
+    return r
+
+
+def reference_world_forward(ref, kind, prec, n, x, scaling="none", r2c_dir=0, ranks=None):
+    """
+    The WHOLE transform of the world array x (flat, order (0,1,2)) by the compiled reference (oracle/_ref, stock backend)
+    spread over thread-ranks as slabs of the slowest axis -- the test-suite pattern of the reference itself
+    (test/test_fft3d.h:124-214: world array -> sub-boxes -> fft3d -> compare).  Returns the flat world output.
+    """
+    ranks = ranks or host_ranks()
+    ranks = max(1, min(ranks, n[2]))
+    world = O.world_box(n)
+    out_world = world.r2c(r2c_dir) if kind == "r2c" else world
+    inboxes, outboxes = bricks(world, (1, 1, ranks)), bricks(out_world, (1, 1, ranks))
+    plane_in, plane_out = world.size[0] * world.size[1], out_world.size[0] * out_world.size[1]
+    inputs = [x[b.low[2] * plane_in:(b.high[2] + 1) * plane_in] for b in inboxes]
+    outs, _ = ref.fft3d(kind, prec, inboxes, outboxes, inputs, scaling=scaling, r2c_dir=r2c_dir)
+    assert all(o.size == b.count() for o, b in zip(outs, outboxes)) and plane_out > 0
+    return np.concatenate(outs)

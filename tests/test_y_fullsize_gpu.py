@@ -1,7 +1,9 @@
 """
-The BASELINE problem sizes on one GPU, checked through size-independent properties (the oracle finishes 512^3 in minutes,
-not seconds): Parseval, linearity, the closed-form spectrum of a shifted delta, the round trip with scale::full, and the
-agreement between the r2c plan and the complex plan on the half spectrum.  Sizes: 512^3 fp64 (bench line, r2c, DCT) and
+The BASELINE problem sizes on one GPU.  First against the reference itself: oracle/_ref (the unmodified reference, stock
+backend, thread-ranks) transforms the same seeded world array in a few seconds and the outputs are compared in relative L2
+(<= 1e-12 fp64, <= 1e-5 fp32) -- the pattern of the reference's own test/test_fft3d.h:124-214.  Then through
+size-independent properties: Parseval, linearity, the closed-form spectrum of a shifted delta, the round trip with
+scale::full, and the agreement between the r2c plan and the complex plan on the half spectrum.  Sizes: 512^3 fp64 (bench line, r2c, DCT) and
 256^3 fp32 (speed3d_c2c single 256^3 of BASELINE.json).  The file sorts late on purpose: it is the heaviest of the GPU suite.
 """
 import math
@@ -10,7 +12,7 @@ import numpy as np
 import pytest
 
 from oracle import heffte_oracle as O
-from tests.helpers import TOL, to_h
+from tests.helpers import TOL, reference_world_forward, to_h
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -26,7 +28,7 @@ def _plan(kind, n, hf):
     world = O.world_box(n)
     if kind == "r2c":
         return hf.fft3d_r2c(hf.backend.b200, to_h(world), to_h(world.r2c(0)), 0, hf.comm_self())
-    tag = hf.backend.b200_cos if kind == "cos" else hf.backend.b200
+    tag = {"c2c": hf.backend.b200, "cos": hf.backend.b200_cos, "sin": hf.backend.b200_sin}[kind]
     return hf.fft3d(tag, to_h(world), to_h(world), hf.comm_self())
 
 
@@ -119,3 +121,35 @@ def test_dct_properties_at_512(lib):
     fft.forward(x1, y1, hf.scale.full)
     fft.backward(y1, back)
     assert _rel(back, x1) <= 4 * TOL[1]
+
+
+# ---- the BASELINE sizes against the compiled reference (oracle/_ref) ------------------------------------------------------
+@pytest.mark.parametrize("kind,n,prec", [("c2c", (512, 512, 512), 1), ("r2c", (512, 512, 512), 1), ("cos", (512, 512, 512), 1),
+                                         ("c2c", (256, 256, 256), 0), ("sin", (256, 256, 256), 1), ("r2c", (256, 256, 256), 0)])
+def test_full_size_against_the_compiled_reference(lib, reference, kind, n, prec):
+    """forward(scale::full) of the seeded world array: b200 on the GPU vs heffte::fft3d<stock> (fp64) on the host cores"""
+    import heffte_b200 as hf
+    count = n[0] * n[1] * n[2]
+    rng = np.random.default_rng(4242)
+    rt, ct = (np.float32, np.complex64) if prec == 0 else (np.float64, np.complex128)
+    real_in = kind != "c2c"
+    x = rng.random(count).astype(rt)
+    if not real_in:
+        x = (x + 1j * rng.random(count).astype(rt)).astype(ct)
+    # the fp32 truth is the fp64 reference result of the same (fp32-representable) input, SURVEY 8(c)
+    expect = reference_world_forward(reference, kind, 1, n, x.astype(np.float64 if real_in else np.complex128), scaling="full")
+    fft = _plan(kind, n, hf)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.empty(fft.size_outbox(), dtype=torch.from_numpy(np.zeros(1, dtype=rt if kind in ("cos", "sin") else ct)).dtype, device="cuda")
+    fft.forward(dx, dy, hf.scale.full)
+    got = dy.cpu().numpy()
+    del dy, dx
+    assert got.shape == expect.shape
+    err = float(np.linalg.norm(got.astype(expect.dtype) - expect) / np.linalg.norm(expect))
+    tol = TOL[prec] * (4 if kind in ("cos", "sin") else 1)
+    assert err <= tol, (kind, n, prec, err)
+    if prec == 0 and kind == "c2c":
+        # for the record: the distance of the reference's own fp32 (stock) result from the same truth
+        stock32 = reference_world_forward(reference, kind, 0, n, x, scaling="full")
+        print("fp32 %s %s: b200 %.3e, stock fp32 %.3e (both vs the fp64 reference)" % (
+            kind, n, err, float(np.linalg.norm(stock32.astype(expect.dtype) - expect) / np.linalg.norm(expect))))

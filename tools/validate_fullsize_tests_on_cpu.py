@@ -38,3 +38,6 @@ T.test_c2c_properties_at_full_size(None, (32, 32, 32), 1); print("c2c fp64 ok")
 T.test_c2c_properties_at_full_size(None, (32, 16, 64), 0); print("c2c fp32 ok")
 T.test_r2c_matches_the_complex_plan_at_512(None); print("r2c ok")
 T.test_dct_properties_at_512(None); print("dct ok")
+from oracle import ref_lib
+for kind, n, prec in [("c2c", (32, 16, 64), 1), ("r2c", (32, 32, 32), 1), ("cos", (32, 32, 32), 1), ("c2c", (32, 32, 32), 0), ("sin", (32, 64, 32), 1), ("r2c", (64, 32, 32), 0)]:
+    T.test_full_size_against_the_compiled_reference(None, ref_lib, kind, n, prec); print("reference parity", kind, n, prec, "ok")
