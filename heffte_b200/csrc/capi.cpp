@@ -47,8 +47,10 @@ transform_kind kind_of(int backend, bool r2c){
     }
 }
 
-box3 box_from(int const low[3], int const high[3], int const *order){
-    box3 b({{low[0], low[1], low[2]}}, {{high[0], high[1], high[2]}});
+template<typename index>
+box3 box_from(index const low[3], index const high[3], int const *order){
+    box3 b({{static_cast<idx>(low[0]), static_cast<idx>(low[1]), static_cast<idx>(low[2])}},
+           {{static_cast<idx>(high[0]), static_cast<idx>(high[1]), static_cast<idx>(high[2])}});
     if (order != nullptr) b.order = {{order[0], order[1], order[2]}};
     return b;
 }
@@ -69,8 +71,9 @@ plan_options options_from(int backend, heffte_plan_options const *o){
     return p;
 }
 
-int create_plan(int backend, void *stream, int const inbox_low[3], int const inbox_high[3], int const *inbox_order,
-                int const outbox_low[3], int const outbox_high[3], int const *outbox_order,
+template<typename index>
+int create_plan(int backend, void *stream, index const inbox_low[3], index const inbox_high[3], int const *inbox_order,
+                index const outbox_low[3], index const outbox_high[3], int const *outbox_order,
                 int r2c_direction, bool r2c, heffte_comm const comm, heffte_plan_options const *options, heffte_plan *plan, int subranks = -1){
     if (plan == nullptr) return 2;
     *plan = nullptr;
@@ -215,6 +218,13 @@ int heffte_plan_create_stream(int backend, void *cuda_stream, int const inbox_lo
 int heffte_plan_create_subcomm(int backend, void *cuda_stream, int const inbox_low[3], int const inbox_high[3], int const *inbox_order,
                                int const outbox_low[3], int const outbox_high[3], int const *outbox_order,
                                int r2c_direction, heffte_comm const comm, heffte_plan_options const *options, int num_subranks, heffte_plan *plan){
+    return create_plan(backend, cuda_stream, inbox_low, inbox_high, inbox_order, outbox_low, outbox_high, outbox_order,
+                       r2c_direction, r2c_direction >= 0, comm, options, plan, (num_subranks > 0) ? num_subranks : -1);
+}
+
+int heffte_plan_create64(int backend, void *cuda_stream, long long const inbox_low[3], long long const inbox_high[3], int const *inbox_order,
+                         long long const outbox_low[3], long long const outbox_high[3], int const *outbox_order,
+                         int r2c_direction, heffte_comm const comm, heffte_plan_options const *options, int num_subranks, heffte_plan *plan){
     return create_plan(backend, cuda_stream, inbox_low, inbox_high, inbox_order, outbox_low, outbox_high, outbox_order,
                        r2c_direction, r2c_direction >= 0, comm, options, plan, (num_subranks > 0) ? num_subranks : -1);
 }

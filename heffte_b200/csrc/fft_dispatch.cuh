@@ -96,8 +96,10 @@ int dispatch_contig(int n, fft_args const &a, Launcher &L){
         case 32:   return launch_contig<T, radix_list<8, 4, 1, 1>,   32, 6, SCATTER>(a, L);
         case 64:   return launch_contig<T, radix_list<8, 8, 1, 1>,   16, 6, SCATTER>(a, L);
         case 128:  return launch_contig<T, radix_list<8, 4, 4, 1>,    8, 6, SCATTER>(a, L);
-        case 256:  return launch_contig<T, radix_list<8, 8, 4, 1>,    4, 6, SCATTER>(a, L);
-        case 512:  return launch_contig<T, radix_list<8, 8, 8, 1>,    1, 12, SCATTER>(a, L);
+        // tools/kbench_c2c.cu on B200 (profiles/r02_single/kbench_variants_a.log): 256-point fp32 <16,16> 6.2 vs 5.0 TB/s for <8,8,4>;
+        // 512-point fp64 <4,8,16> with two lines per CTA 6.95 vs 6.25 TB/s for <8,8,8> with one
+        case 256:  return launch_contig<T, radix_list<16, 16, 1, 1>,  4, 6, SCATTER>(a, L);
+        case 512:  return launch_contig<T, radix_list<4, 8, 16, 1>,   2, 8, SCATTER>(a, L);
         case 1024: return launch_contig<T, radix_list<16, 8, 8, 1>,   1, 4, SCATTER>(a, L);
         case 2048: return launch_contig<T, radix_list<8, 8, 8, 4>,    1, 2, SCATTER>(a, L);
         case 4096: return launch_contig<T, radix_list<8, 8, 8, 8>,    1, 1, SCATTER>(a, L);

@@ -100,6 +100,11 @@ int heffte_plan_create_subcomm(int backend, void *cuda_stream, int const inbox_l
                                int const outbox_low[3], int const outbox_high[3], int const *outbox_order,
                                int r2c_direction /* -1 unless r2c */, heffte_comm const comm, heffte_plan_options const *options,
                                int num_subranks, heffte_plan *plan);
+/* same with 64-bit box coordinates (C++ API: box3d<long long>, test/test_longlong.cpp): nothing is truncated on the way in */
+int heffte_plan_create64(int backend, void *cuda_stream, long long const inbox_low[3], long long const inbox_high[3], int const *inbox_order,
+                         long long const outbox_low[3], long long const outbox_high[3], int const *outbox_order,
+                         int r2c_direction /* -1 unless r2c */, heffte_comm const comm, heffte_plan_options const *options,
+                         int num_subranks, heffte_plan *plan);
 /* heffte_c.h:87  */ int heffte_plan_destroy(heffte_plan plan);
 /* heffte_c.h:93  */ int heffte_size_inbox(heffte_plan const plan);
 /* heffte_c.h:98  */ int heffte_size_outbox(heffte_plan const plan);

@@ -19,7 +19,8 @@
  *   - errors of the C layer become std::runtime_error (the reference throws from cuda::check_error,
  *     include/heffte_backend_cuda.h:49-60).
  * A program written against the reference compiles against this header after replacing the backend tag and the
- * communicator argument; tests/cpp/ holds such programs.
+ * communicator argument; tests/cpp/ holds such programs.  Everything lives in namespace heffte_b200; `heffte` is an alias of
+ * it unless the reference's heffte.h has been included before (see the end of this file), so both can share a translation unit.
  */
 #ifndef HEFFTE_B200_HPP
 #define HEFFTE_B200_HPP
@@ -35,7 +36,7 @@
 
 #include "heffte_b200.h"
 
-namespace heffte {
+namespace heffte_b200 {
 
 // ---- geometry: include/heffte_geometry.h:67-133 ----------------------------------------------------------------------
 template<typename index = int>
@@ -249,13 +250,14 @@ namespace b200_detail {
     protected:
         plan_base(int backend_id, void *stream, box3d<index> const &inbox, box3d<index> const &outbox, int r2c_direction, comm const &c, plan_options const &o)
             : plan(nullptr), cstream(stream){
-            int const lo_in[3] = {static_cast<int>(inbox.low[0]), static_cast<int>(inbox.low[1]), static_cast<int>(inbox.low[2])};
-            int const hi_in[3] = {static_cast<int>(inbox.high[0]), static_cast<int>(inbox.high[1]), static_cast<int>(inbox.high[2])};
-            int const lo_out[3] = {static_cast<int>(outbox.low[0]), static_cast<int>(outbox.low[1]), static_cast<int>(outbox.low[2])};
-            int const hi_out[3] = {static_cast<int>(outbox.high[0]), static_cast<int>(outbox.high[1]), static_cast<int>(outbox.high[2])};
+            // 64-bit coordinates all the way down (box3d<long long>, reference test/test_longlong.cpp)
+            long long const lo_in[3] = {static_cast<long long>(inbox.low[0]), static_cast<long long>(inbox.low[1]), static_cast<long long>(inbox.low[2])};
+            long long const hi_in[3] = {static_cast<long long>(inbox.high[0]), static_cast<long long>(inbox.high[1]), static_cast<long long>(inbox.high[2])};
+            long long const lo_out[3] = {static_cast<long long>(outbox.low[0]), static_cast<long long>(outbox.low[1]), static_cast<long long>(outbox.low[2])};
+            long long const hi_out[3] = {static_cast<long long>(outbox.high[0]), static_cast<long long>(outbox.high[1]), static_cast<long long>(outbox.high[2])};
             heffte_plan_options opts{o.use_reorder ? 1 : 0, static_cast<int>(o.algorithm), o.use_pencils ? 1 : 0, o.use_gpu_aware ? 1 : 0};
-            int const code = heffte_plan_create_subcomm(backend_id, stream, lo_in, hi_in, inbox.order.data(), lo_out, hi_out, outbox.order.data(),
-                                                        r2c_direction, c.get(), &opts, o.get_subranks(), &plan);
+            int const code = heffte_plan_create64(backend_id, stream, lo_in, hi_in, inbox.order.data(), lo_out, hi_out, outbox.order.data(),
+                                                  r2c_direction, c.get(), &opts, o.get_subranks(), &plan);
             if (code != 0) throw std::runtime_error(std::string("heffte::fft3d (b200) plan creation failed: ") + heffte_last_error());
         }
         void execute(int precision, int direction, int batch, void const *input, void *output, void *workspace, scale scaling) const {
@@ -341,6 +343,26 @@ public:
         backward(input.data(), output.data(), scaling);
         return output;
     }
+    //! std::vector variants (include/heffte_fft3d.h:417-447, 517-542): HOST data, staged through device vectors (H2D, transform, D2H)
+    template<typename T> std::vector<typename std::conditional<is_fft, std::complex<typename b200_detail::real_of<T>::type>, T>::type>
+    forward(std::vector<T> const &input, scale scaling = scale::none) const {
+        if (input.size() < this->size_inbox()) throw std::invalid_argument("The input vector is smaller than size_inbox(), i.e., not enough entries provided to fill the inbox.");
+        return gpu::transfer::unload(this->stream(), forward(gpu::transfer::load(this->stream(), input), scaling));
+    }
+    template<typename T> std::vector<T> backward(std::vector<T> const &input, scale scaling = scale::none) const {
+        if (input.size() < this->size_outbox()) throw std::invalid_argument("The input vector is smaller than size_outbox(), i.e., not enough entries provided to fill the outbox.");
+        return gpu::transfer::unload(this->stream(), backward(gpu::transfer::load(this->stream(), input), scaling));
+    }
+    //! complex spectrum back to a REAL field (include/heffte_fft3d.h:534-542)
+    template<typename real> gpu::vector<real> backward_real(gpu::vector<std::complex<real>> const &input, scale scaling = scale::none) const {
+        if (input.size() < this->size_outbox()) throw std::invalid_argument("The input vector is smaller than size_outbox(), i.e., not enough entries provided to fill the outbox.");
+        gpu::vector<real> output(this->size_inbox());
+        backward(input.data(), output.data(), scaling);
+        return output;
+    }
+    template<typename real> std::vector<real> backward_real(std::vector<std::complex<real>> const &input, scale scaling = scale::none) const {
+        return gpu::transfer::unload(this->stream(), backward_real(gpu::transfer::load(this->stream(), input), scaling));
+    }
 private:
     template<typename spatial_type, typename spectral_type> static void check_types(){
         using real = typename b200_detail::real_of<spectral_type>::type;
@@ -396,12 +418,39 @@ public:
         backward(input.data(), output.data(), scaling);
         return output;
     }
+    //! std::vector variants: HOST data, staged through device vectors
+    template<typename real> std::vector<std::complex<real>> forward(std::vector<real> const &input, scale scaling = scale::none) const {
+        if (input.size() < this->size_inbox()) throw std::invalid_argument("The input vector is smaller than size_inbox(), i.e., not enough entries provided to fill the inbox.");
+        return gpu::transfer::unload(this->stream(), forward(gpu::transfer::load(this->stream(), input), scaling));
+    }
+    template<typename real> std::vector<real> backward(std::vector<std::complex<real>> const &input, scale scaling = scale::none) const {
+        if (input.size() < this->size_outbox()) throw std::invalid_argument("The input vector is smaller than size_outbox(), i.e., not enough entries provided to fill the outbox.");
+        return gpu::transfer::unload(this->stream(), backward(gpu::transfer::load(this->stream(), input), scaling));
+    }
 private:
     static int checked(int r2c_direction){
         if (r2c_direction < 0 or r2c_direction > 2) throw std::runtime_error("fft3d_r2c: r2c_direction must be 0, 1 or 2");
         return r2c_direction;
     }
 };
+
+// ---- aliases and factories of include/heffte_fft3d.h:703-763, include/heffte_fft3d_r2c.h:383-420 -----------------------------
+//! two-dimensional transforms are three-dimensional plans on boxes of extent 1 along the third axis
+template<typename backend_tag, typename index = int> using fft2d = fft3d<backend_tag, index>;
+template<typename backend_tag, typename index = int> using fft2d_r2c = fft3d_r2c<backend_tag, index>;
+//! real-to-real transforms: the cosine / sine tags
+template<typename backend_tag, typename index = int> using rtransform = fft3d<backend_tag, index>;
+template<typename backend_tag, typename index>
+fft3d<backend_tag, index> make_fft3d(box3d<index> const inbox, box3d<index> const outbox, comm const &c, plan_options const options = default_options<backend_tag>()){
+    static_assert(backend::is_enabled<backend_tag>::value, "the requested backend is not enabled");
+    return fft3d<backend_tag, index>(inbox, outbox, c, options);
+}
+template<typename backend_tag, typename index>
+fft3d_r2c<backend_tag, index> make_fft3d_r2c(box3d<index> const inbox, box3d<index> const outbox, int r2c_direction, comm const &c,
+                                             plan_options const options = default_options<backend_tag>()){
+    static_assert(backend::is_enabled<backend_tag>::value, "the requested backend is not enabled");
+    return fft3d_r2c<backend_tag, index>(inbox, outbox, r2c_direction, c, options);
+}
 
 //! include/heffte_geometry.h:643-691 / 409-436 through the library (same answers as the reference, tests/test_plan_logic.py)
 inline std::array<int, 3> proc_setup_min_surface(box3d<> const &world, int num_procs){
@@ -423,6 +472,16 @@ inline std::vector<box3d<>> split_world(box3d<> const &world, std::array<int, 3>
     return out;
 }
 
-} // namespace heffte
+} // namespace heffte_b200
+
+/*
+ * Stand-alone use: the classes answer to the reference's spelling, heffte::fft3d<heffte::backend::b200>.
+ * Next to the reference's own heffte.h (include it FIRST) the alias is left out and this front-end stays in its own
+ * namespace: heffte_b200::fft3d<heffte_b200::backend::b200> is the plan-level (fused reshapes over NVLink) entry point,
+ * while heffte::fft3d<heffte::backend::b200> is the reference's template over include/heffte_backend_b200.h.
+ */
+#if !defined(HEFFTE_H) && !defined(HEFFTE_COMMON_H) && !defined(HEFFTE_B200_NO_ALIAS)
+namespace heffte = heffte_b200;
+#endif
 
 #endif

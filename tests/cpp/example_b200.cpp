@@ -96,6 +96,34 @@ int main(){
         double const expect0 = std::sqrt(double(world.count()));         // constant field: all energy in the zero mode
         if (std::abs(y[0] - std::complex<float>(float(expect0), 0.0f)) > 1e-3 or std::abs(y[1]) > 1e-3){ std::printf("single rank: wrong spectrum\n"); failures++; }
     }
+    // factories, aliases, 64-bit boxes and the std::vector overloads (include/heffte_fft3d.h:417-447, 703-763; test/test_longlong.cpp)
+    {
+        heffte::comm self = heffte::comm::self();
+        heffte::box3d<long long> const world = {{0, 0, 0}, {7, 5, 11}};
+        auto fft = heffte::make_fft3d<backend_tag>(world, world, self);
+        std::vector<std::complex<double>> x(fft.size_inbox());
+        for(size_t i=0; i<x.size(); i++) x[i] = {double(i % 7), double(i % 3)};
+        std::vector<std::complex<double>> y = fft.forward(x);                       // host vectors in, host vectors out
+        std::vector<std::complex<double>> back = fft.backward(y, heffte::scale::full);
+        double err = 0.0;
+        for(size_t i=0; i<x.size(); i++) err = std::max(err, std::abs(back[i] - x[i]));
+        std::complex<double> sum = 0.0;
+        for(auto const &v : x) sum += v;
+        err = std::max(err, std::abs(y[0] - sum));
+        heffte::rtransform<heffte::backend::b200_sin, long long> dst(world, world, self);
+        std::vector<double> r(dst.size_inbox());
+        std::iota(r.begin(), r.end(), 1.0);
+        std::vector<double> rb = dst.backward(dst.forward(r, heffte::scale::full));
+        for(size_t i=0; i<r.size(); i++) err = std::max(err, std::abs(rb[i] - r[i]));
+        heffte::box3d<> const plane = {{0, 0, 0}, {15, 11, 0}};
+        heffte::fft2d<backend_tag> fft2(plane, plane, self);
+        std::vector<std::complex<float>> p(fft2.size_inbox(), {1.0f, 0.0f});
+        std::vector<std::complex<float>> q = fft2.forward(p);
+        err = std::max(err, double(std::abs(q[0] - std::complex<float>(192.0f, 0.0f))) + double(std::abs(q[5])));
+        std::vector<float> preal = fft2.backward_real(q, heffte::scale::full);
+        err = std::max(err, double(std::abs(preal[7] - 1.0f)));
+        if (not (err < 1e-4)){ std::printf("factories / vectors / 64-bit boxes: error %.3e\n", err); failures++; }
+    }
     std::printf(failures == 0 ? "example_b200: ok\n" : "example_b200: FAILED\n");
     return failures == 0 ? 0 : 1;
 }

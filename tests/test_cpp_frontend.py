@@ -52,3 +52,18 @@ def test_c_program_runs_on_the_emulated_library():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "test_c_b200: ok" in r.stdout
+
+
+def test_front_end_coexists_with_the_reference_headers():
+    """include/heffte_b200.hpp lives in namespace heffte_b200 and can share a translation unit with the reference's heffte.h"""
+    if not os.path.exists("/root/reference/include/heffte.h"):
+        pytest.skip("the reference tree is not present on this host")
+    source = os.path.join(OUT, "coexist.cpp")
+    os.makedirs(OUT, exist_ok=True)
+    with open(source, "w") as f:
+        f.write('#include "heffte.h"\n#include "heffte_b200.hpp"\n'
+                'int main(){ heffte::box3d<> a({0,0,0},{3,3,3}); heffte_b200::box3d<long long> b({0,0,0},{3,3,3});\n'
+                '  heffte_b200::plan_options o(heffte_b200::backend::b200{}); (void) o; return (a.count() == b.count()) ? 0 : 1; }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "oracle", "config"), "-I", os.path.join(ROOT, "oracle", "mpi_shim"),
+                        "-I", "/root/reference/include", "-I", os.path.join(ROOT, "include"), source], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
