@@ -46,7 +46,8 @@ def parse_args():
     ap.add_argument("--kind", default="c2c", choices=["c2c", "r2c", "r2r", "conv"],
                     help="r2r = DCT-II / DCT-III (speed3d_r2r ... cos); conv = benchmarks/convolution.cpp: forward(scale full), x *= x, backward, c2c in place")
     ap.add_argument("--reorder", action="store_true")
-    ap.add_argument("--slabs", action="store_true")
+    ap.add_argument("--slabs", action="store_true", help="speed3d -slabs: the slab decomposition is executed (default: the planner picks)")
+    ap.add_argument("--pencils", action="store_true", help="speed3d -pencils: the pencil decomposition is executed")
     ap.add_argument("--io-pencils", action="store_true", help="pencil-shaped in/out boxes (speed3d -io_pencils)")
     ap.add_argument("--batch", type=int, default=1, help="speed3d -batch: transforms per call")
     ap.add_argument("--flush-l2", action="store_true", help="write a 512 MB buffer between timed steps (forced when the working set fits the L2)")
@@ -340,7 +341,7 @@ def flush_l2(ctx):
     ctx.flush.fill_(1.0)
 
 
-def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, reorder=False, slabs=False, io_pencils=False, batch=1,
+def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, reorder=False, slabs=False, pencils=False, io_pencils=False, batch=1,
                  force_flush=False, parity=True, e2e_wanted=True, cpu_wanted=True):
     torch, hf, lib, dist = ctx.torch, ctx.hf, ctx.lib, ctx.dist
     rank, world_size, distributed = ctx.rank, ctx.world_size, ctx.distributed
@@ -361,7 +362,8 @@ def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, re
     outbox = hf.heffte.split_world(cworld if r2c else world, out_grid)[rank]
 
     tag = hf.backend.b200_cos if r2r else hf.backend.b200
-    options = hf.plan_options(tag, use_reorder=reorder, use_pencils=not slabs)
+    decomposition = False if slabs else (True if pencils else None)       # None: the planner picks the cheaper one
+    options = hf.plan_options(tag, use_reorder=reorder, use_pencils=decomposition)
     fft = hf.fft3d_r2c(tag, inbox, outbox, 0, ctx.comm, options) if r2c else hf.fft3d(tag, inbox, outbox, ctx.comm, options)
 
     # the plan that runs (pure host planning, csrc/plan_logic.h): process grids of input, the three transform stages, output
@@ -369,7 +371,7 @@ def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, re
         world_boxes_in = hf.heffte.split_world(world, in_grid)
         world_boxes_out = hf.heffte.split_world(cworld if r2c else world, out_grid)
         shapes, _, swaps = hf.heffte.execution_plan(world_boxes_in, world_boxes_out, r2c_direction=0 if r2c else -1,
-                                                    use_reorder=bool(reorder or r2r), use_pencils=not slabs)
+                                                    use_reorder=bool(reorder or r2r), use_pencils=decomposition)
 
         def grid_of(boxes):
             return "x".join(str(len({(b[d], b[3 + d]) for b in boxes if all(b[3 + k] >= b[k] for k in range(3))})) for d in range(3))
@@ -698,7 +700,7 @@ def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, re
             "vs_baseline": None, "dtype": "f64" if prec == 1 else "f32", "data": "synthetic",
             "config": {"workload": workload_name(kind, precision, n),
                        "layout": "bricks %s%s, %s, %s, in-place, step = forward(scale full)+backward" % (
-                           grid, " (pencil-shaped in/out)" if io_pencils else "", "reorder" if reorder else "no-reorder", "slabs" if slabs else "pencils"),
+                           grid, " (pencil-shaped in/out)" if io_pencils else "", "reorder" if reorder else "no-reorder", "slabs" if slabs else ("pencils" if pencils else "decomposition chosen by the planner")),
                        "batch": batch,
                        "l2": ("working set %.0f MB per GPU exceeds the 126 MB L2" % working_set_mb) if not flush else
                              ("working set %.0f MB per GPU: a 512 MB buffer is overwritten between the timed steps (flush time not counted)" % working_set_mb),
@@ -729,7 +731,9 @@ def secondary_list(args, world_size):
     if world_size == 1:
         items.append(dict(kind="c2c", size=(256, 256, 256), precision="float", force_flush=True))
     if world_size >= 8:
-        items.append(dict(kind="c2c", size=(1024, 1024, 1024), precision="float", reorder=True))
+        # BASELINE cfg4: speed3d_c2c single 1024^3 -reorder, slabs against pencils
+        items.append(dict(kind="c2c", size=(1024, 1024, 1024), precision="float", reorder=True, slabs=True))
+        items.append(dict(kind="c2c", size=(1024, 1024, 1024), precision="float", reorder=True, pencils=True))
         items.append(dict(kind="c2c", size=(512, 512, 512), precision="double", io_pencils=True))
     return items
 
@@ -739,15 +743,16 @@ def b200_arm(args):
         os.environ["HEFFTE_B200_L2_SLAB_MB"] = str(args.l2_slab_mb)
     ctx = make_context(args)
     line = run_workload(ctx, args, args.kind, args.size, args.precision, args.steps, args.warmup, primary=True,
-                        reorder=args.reorder, slabs=args.slabs, io_pencils=args.io_pencils, batch=args.batch)
+                        reorder=args.reorder, slabs=args.slabs, pencils=args.pencils, io_pencils=args.io_pencils, batch=args.batch)
     default_workload = (args.kind == "c2c" and tuple(args.size) == (512, 512, 512) and args.precision == "double" and args.batch == 1
-                        and not (args.reorder or args.slabs or args.io_pencils))
+                        and not (args.reorder or args.slabs or args.pencils or args.io_pencils))
     if default_workload and not args.no_secondary:
         secondary = []
         for item in secondary_list(args, ctx.world_size):
             try:
                 r = run_workload(ctx, args, item["kind"], item["size"], item["precision"], max(3, min(args.steps, 5)), 3, primary=False,
                                  reorder=item.get("reorder", False), io_pencils=item.get("io_pencils", False),
+                                 slabs=item.get("slabs", False), pencils=item.get("pencils", False),
                                  force_flush=item.get("force_flush", False), e2e_wanted=False, cpu_wanted=False)
             except Exception as e:  # noqa: BLE001  (a secondary configuration must not take the headline down)
                 r = {"config": {"workload": workload_name(item["kind"], item["precision"], item["size"])}, "error": repr(e)} if ctx.rank == 0 else None

@@ -65,7 +65,10 @@ plan_options options_from(int backend, heffte_plan_options const *o){
     if (o != nullptr){
         p.use_reorder = (o->use_reorder != 0);
         p.algorithm = o->algorithm;
+        // 0 slabs / 1 pencils: the caller's choice, executed as given; 2 (Heffte_B200_DECOMPOSITION_AUTO): the planner picks the
+        // decomposition that moves less over NVLink (the reported sizes are those of the pencil plan, the reference's default)
         p.use_pencils = (o->use_pencils != 0);
+        p.explicit_decomposition = (o->use_pencils == 0 or o->use_pencils == 1);
         p.use_gpu_aware = (o->use_gpu_aware != 0);
     }
     return p;
@@ -139,10 +142,15 @@ void run_real_side(heffte_plan const plan, int precision, int direction, void co
 
 // communicator whose allgather answers from a fixed table: lets the real plan constructor run without any transport
 struct table_context { std::vector<long long> table; };
-int table_gather(void *context, const void*, void *all, size_t bytes){
+int table_gather(void *context, const void *mine, void *all, size_t bytes){
     auto *t = static_cast<table_context*>(context);
-    (void) bytes;
-    std::memcpy(all, t->table.data(), t->table.size() * sizeof(long long));
+    if (bytes == 18 * sizeof(long long)){        // the boxes of every rank
+        std::memcpy(all, t->table.data(), t->table.size() * sizeof(long long));
+        return 0;
+    }
+    // anything else (the plan signature): every rank of the table is this process
+    size_t const ranks = t->table.size() / 18;
+    for(size_t r=0; r<ranks; r++) std::memcpy(static_cast<char*>(all) + r * bytes, mine, bytes);
     return 0;
 }
 
@@ -350,7 +358,7 @@ int heffte_b200_logic_plan(int nranks, int const *inboxes, int const *outboxes, 
         shape ins, outs;
         for(int r=0; r<nranks; r++){ ins.push_back(box_from9(inboxes + 9 * r)); outs.push_back(box_from9(outboxes + 9 * r)); }
         plan_options o;
-        o.use_reorder = use_reorder != 0; o.algorithm = algorithm; o.use_pencils = use_pencils != 0; o.subranks = subranks;
+        o.use_reorder = use_reorder != 0; o.algorithm = algorithm; o.use_pencils = use_pencils != 0; o.explicit_decomposition = (use_pencils == 0 or use_pencils == 1); o.subranks = subranks;
         logic_plan lp = make_logic_plan(ins, outs, r2c_direction, o, rank);
         for(int s=0; s<4; s++)
             for(int r=0; r<nranks; r++){
@@ -372,7 +380,7 @@ int heffte_b200_execution_plan(int nranks, int const *inboxes, int const *outbox
         shape ins, outs;
         for(int r=0; r<nranks; r++){ ins.push_back(box_from9(inboxes + 9 * r)); outs.push_back(box_from9(outboxes + 9 * r)); }
         plan_options o;
-        o.use_reorder = use_reorder != 0; o.algorithm = algorithm; o.use_pencils = use_pencils != 0; o.subranks = subranks;
+        o.use_reorder = use_reorder != 0; o.algorithm = algorithm; o.use_pencils = use_pencils != 0; o.explicit_decomposition = (use_pencils == 0 or use_pencils == 1); o.subranks = subranks;
         logic_plan lp = make_execution_plan(ins, outs, r2c_direction, o, rank, swaps);
         for(int s=0; s<4; s++)
             for(int r=0; r<nranks; r++){
@@ -429,7 +437,7 @@ int heffte_b200_plan_sizes(int kind, int nranks, int const *inboxes, int const *
         }
         std::unique_ptr<communicator> comm(make_callback_communicator(rank, nranks, table_gather, nullptr, &context));
         plan_options o;
-        o.use_reorder = use_reorder != 0; o.algorithm = algorithm; o.use_pencils = use_pencils != 0; o.subranks = subranks;
+        o.use_reorder = use_reorder != 0; o.algorithm = algorithm; o.use_pencils = use_pencils != 0; o.explicit_decomposition = (use_pencils == 0 or use_pencils == 1); o.subranks = subranks;
         transform3d fft(static_cast<transform_kind>(kind), box_from9(inboxes + 9 * rank), box_from9(outboxes + 9 * rank), r2c_direction,
                         comm.get(), o, nullptr);
         *size_inbox = fft.size_inbox(); *size_outbox = fft.size_outbox(); *size_workspace = fft.size_workspace();

@@ -418,12 +418,13 @@ __device__ __forceinline__ void strided_pass(cplx<T> *sm, unsigned t, unsigned j
     }
 }
 
-template<typename T, typename RL, int TPL, int LPB, int MINB, bool BWD, bool SCATTER>
-__global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a){
-    B200_DYN_SMEM(smem_raw);
-    cplx<T> *sm = reinterpret_cast<cplx<T>*>(smem_raw);
+// One tile of the strided kernel: LPB adjacent lines starting at line tile * LPB (after the destination round-robin of the
+// scatter variants).  `smap` is the scatter map ALREADY staged in shared memory by the caller (null for plain stores).
+// Every thread of the CTA takes part; the caller separates two tiles that share the buffer by a __syncthreads().
+template<typename T, typename RL, int TPL, int LPB, bool BWD, bool SCATTER>
+__device__ __forceinline__ void strided_tile(cplx<T> *sm, const scatter_map *smap, fft_args const &a, unsigned tile){
     const unsigned t = threadIdx.x % LPB, j = threadIdx.x / LPB;
-    const unsigned line = (SCATTER ? scatter_tile_order<LPB>(a, blockIdx.x) : blockIdx.x) * LPB + t;
+    const unsigned line = (SCATTER ? scatter_tile_order<LPB>(a, tile) : tile) * LPB + t;
     const bool valid = line < a.nlines;
     const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
     const T scale = static_cast<T>(a.scale);
@@ -444,8 +445,6 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a
     cplx<T> *gout = nullptr;
     scatter_ctx sc{nullptr, 0, 0, 0};
     if constexpr (SCATTER){
-        scatter_map *smap = reinterpret_cast<scatter_map*>(sm + static_cast<size_t>(RL::N) * LPB);   // behind the tile
-        scatter_stage(smap, a.smap);
         sc.map = smap;
         sc.b = static_cast<int>(line / static_cast<unsigned>(a.count_a));
         sc.a = static_cast<int>(line - static_cast<unsigned>(sc.b) * static_cast<unsigned>(a.count_a));
@@ -468,6 +467,27 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a
     if constexpr (P > 3){
         __syncthreads();
         strided_pass<T, RL, 3, TPL, LPB, BWD, SCATTER>(sm, t, j, valid, gout, a.og.stride, tw, scale, do_scale, sc);
+    }
+}
+
+// number of tiles of a launch
+template<int LPB> __host__ __device__ inline unsigned tile_count(fft_args const &a){ return static_cast<unsigned>((a.nlines + LPB - 1) / LPB); }
+
+// The kernel walks the tiles grid-stride: one tile per CTA when the grid covers the box (the usual launch), several when the
+// grid is kept thin on purpose so that another kernel can share the SMs (NVLink-bound stages of a multi-GPU plan).
+template<typename T, typename RL, int TPL, int LPB, int MINB, bool BWD, bool SCATTER>
+__global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a){
+    B200_DYN_SMEM(smem_raw);
+    cplx<T> *sm = reinterpret_cast<cplx<T>*>(smem_raw);
+    scatter_map *smap = nullptr;
+    if constexpr (SCATTER){
+        smap = reinterpret_cast<scatter_map*>(sm + static_cast<size_t>(RL::N) * LPB);   // behind the tile
+        scatter_stage(smap, a.smap);      // visible after the first barrier inside strided_tile
+    }
+    const unsigned ntiles = tile_count<LPB>(a);
+    for(unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
+        strided_tile<T, RL, TPL, LPB, BWD, SCATTER>(sm, smap, a, tile);
+        if (tile + gridDim.x < ntiles) __syncthreads();
     }
 }
 
@@ -552,22 +572,19 @@ __device__ __forceinline__ void contig_pass(cplx<T> *row, unsigned j, bool valid
     }
 }
 
-// TPL threads share a line; it must divide N / R for every radix R of the schedule (power-of-two schedules: N / rmax)
-template<typename T, typename RL, int LPB, int MINB, bool BWD, bool SCATTER, int TPL = RL::N / RL::rmax>
-__global__ void __launch_bounds__(TPL * LPB, MINB) fft_contig_kernel(fft_args a){
-    B200_DYN_SMEM(smem_raw);
+// One tile of the contiguous kernel: LPB lines starting at line tile * LPB.  TPL threads share a line; it must divide N / R
+// for every radix R of the schedule (power-of-two schedules: N / rmax).  `smap`: scatter map already staged in shared memory.
+template<typename T, typename RL, int LPB, bool BWD, bool SCATTER, int TPL>
+__device__ __forceinline__ void contig_tile(unsigned char *smem_raw, const scatter_map *smap, fft_args const &a, unsigned tile){
     constexpr unsigned PITCH = pad_index(RL::N) + 1;
     const unsigned j = threadIdx.x % TPL, t = threadIdx.x / TPL;
     cplx<T> *row = reinterpret_cast<cplx<T>*>(smem_raw) + t * PITCH;
-    const unsigned line = (SCATTER ? scatter_tile_order<LPB>(a, blockIdx.x) : blockIdx.x) * LPB + t;
+    const unsigned line = (SCATTER ? scatter_tile_order<LPB>(a, tile) : tile) * LPB + t;
     const bool valid = line < a.nlines;
     const cplx<T> *gin = reinterpret_cast<const cplx<T>*>(a.in) + (valid ? tile_line_offset(a.ig, a.count_a, line) : 0);
     cplx<T> *gout = nullptr;
     scatter_ctx sc{nullptr, 0, 0, 0};
     if constexpr (SCATTER){
-        scatter_map *smap = reinterpret_cast<scatter_map*>(smem_raw + ((sizeof(cplx<T>) * PITCH * LPB + 15) / 16) * 16);
-        scatter_stage(smap, a.smap);
-        __syncthreads();
         sc.map = smap;
         sc.b = static_cast<int>(line / static_cast<unsigned>(a.count_a));
         sc.a = static_cast<int>(line - static_cast<unsigned>(sc.b) * static_cast<unsigned>(a.count_a));
@@ -593,6 +610,107 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_contig_kernel(fft_args a)
     if constexpr (P > 3){
         __syncthreads();
         contig_pass<T, RL, 3, N3, TPL, BWD, SCATTER>(row, j, valid, gin, gout, a.ig.stride, a.og.stride, tw, scale, do_scale, sc);
+    }
+}
+
+template<typename T, typename RL, int LPB, int MINB, bool BWD, bool SCATTER, int TPL = RL::N / RL::rmax>
+__global__ void __launch_bounds__(TPL * LPB, MINB) fft_contig_kernel(fft_args a){
+    B200_DYN_SMEM(smem_raw);
+    constexpr unsigned PITCH = pad_index(RL::N) + 1;
+    scatter_map *smap = nullptr;
+    if constexpr (SCATTER){
+        smap = reinterpret_cast<scatter_map*>(smem_raw + ((sizeof(cplx<T>) * PITCH * LPB + 15) / 16) * 16);
+        scatter_stage(smap, a.smap);
+        __syncthreads();
+    }
+    const unsigned ntiles = tile_count<LPB>(a);
+    for(unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
+        contig_tile<T, RL, LPB, BWD, SCATTER, TPL>(smem_raw, smap, a, tile);
+        if (tile + gridDim.x < ntiles) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// paired kernel: TWO consecutive transforms of the same box -- along the contiguous axis (A) and along the middle axis (B)
+// -- in ONE persistent launch, plane by plane, so that B finds the output of A in the L2 cache (126 MB on B200) instead of
+// HBM and overwrites it in place before it is ever written back: the pair costs one read and one write of HBM instead of
+// two of each (SURVEY 8d counts 2 x 2 x D algorithmic bytes for it).
+// The CTAs of the grid (as many as fit the GPU at once) walk a list of tickets dealt round-robin; tickets come
+// in groups: the A tiles of plane g, then the B tiles of plane g - lag.  A B tile waits (acquire spin on a per-plane
+// counter) until every A tile of its plane has been stored; with a lag of a few planes the wait is never taken, and the
+// planes in flight (lag x plane bytes) stay far below the L2 capacity.  No deadlock: a B ticket only waits for A tickets
+// with smaller numbers, which are held by running CTAs that wait for nothing.
+// B may be a SCATTER variant: the first local pass of a multi-GPU stage then hides behind the NVLink-bound fused stage.
+// ---------------------------------------------------------------------------------------------------------
+struct pair_args {
+    fft_args a, b;                 // A: lines along the contiguous axis, B: lines along the middle axis, both over the whole box
+    unsigned planes;               // extent of the slowest axis
+    unsigned tiles_a, tiles_b;     // tiles per plane of A and of B
+    unsigned lag;                  // planes between the A and the B front
+    unsigned *done;                // [planes], zeroed before the launch: tiles of the first transform stored, per plane
+};
+
+#ifndef B200_HOST_EMULATION
+__device__ __forceinline__ unsigned load_acquire(const unsigned *p){
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ticket_take(unsigned *p){ return atomicAdd(p, 1u); }
+__device__ __forceinline__ void count_release(unsigned *p){ __threadfence(); atomicAdd(p, 1u); }
+#else
+inline unsigned load_acquire(const unsigned *p){ return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline unsigned ticket_take(unsigned *p){ return __atomic_fetch_add(p, 1u, __ATOMIC_ACQ_REL); }
+inline void count_release(unsigned *p){ __atomic_fetch_add(p, 1u, __ATOMIC_ACQ_REL); }
+#endif
+
+// shared memory of the paired kernel: the larger of the two tiles, then (scatter variants) the staged map, then the ticket
+template<typename T, typename RLA, int LPBA, typename RLB, int LPBB>
+__host__ __device__ constexpr size_t pair_tile_bytes(){
+    constexpr size_t tile_a = ((sizeof(cplx<T>) * (pad_index(RLA::N) + 1) * LPBA + 15) / 16) * 16;
+    constexpr size_t tile_b = sizeof(cplx<T>) * static_cast<size_t>(RLB::N) * LPBB;
+    return tile_a > tile_b ? tile_a : tile_b;
+}
+template<typename T, typename RLA, int LPBA, typename RLB, int LPBB, bool SCATTER>
+__host__ __device__ constexpr size_t pair_smem_bytes(){
+    return pair_tile_bytes<T, RLA, LPBA, RLB, LPBB>() + (SCATTER ? sizeof(scatter_map) : 0);
+}
+
+// CONTIG_FIRST: the contiguous-axis transform runs ahead (forward order of a box), else the middle-axis one (backward order).
+// SCATTER applies to the transform that runs second.  p.a always describes the contiguous-axis transform, p.b the middle-axis one.
+template<typename T, typename RLA, int LPBA, int TPLA, typename RLB, int TPLB, int LPBB, int MINB, bool BWD, bool SCATTER, bool CONTIG_FIRST>
+__global__ void __launch_bounds__(TPLB * LPBB, MINB) fft_pair_kernel(pair_args p){
+    static_assert(TPLA * LPBA == TPLB * LPBB, "both phases use the whole CTA");
+    B200_DYN_SMEM(smem_raw);
+    constexpr size_t tile_bytes = pair_tile_bytes<T, RLA, LPBA, RLB, LPBB>();
+    scatter_map *smap = nullptr;
+    if constexpr (SCATTER){
+        smap = reinterpret_cast<scatter_map*>(smem_raw + tile_bytes);
+        scatter_stage(smap, CONTIG_FIRST ? p.b.smap : p.a.smap);
+    }
+    const unsigned tiles_first = CONTIG_FIRST ? p.tiles_a : p.tiles_b, tiles_second = CONTIG_FIRST ? p.tiles_b : p.tiles_a;
+    const unsigned group = tiles_first + tiles_second;
+    const unsigned total = (p.planes + p.lag) * group;
+    // tickets are dealt round-robin: CTA b takes b, b + gridDim.x, ...  (a shared atomic ticket counter serialises at one L2
+    // address: tools/kbench_pair.cu).  Still free of deadlock as long as the whole grid is resident (the host sizes it by
+    // occupancy): the CTA that holds the smallest unfinished ticket never waits for anything unfinished.
+    for(unsigned ticket = blockIdx.x; ticket < total; ticket += gridDim.x){
+        if (ticket != blockIdx.x) __syncthreads();      // the previous tile is done with shared memory
+        const unsigned g = ticket / group, r = ticket - g * group;
+        if (r < tiles_first){
+            if (g >= p.planes) continue;       // the first front has left the box: only tiles of the second transform remain
+            if constexpr (CONTIG_FIRST) contig_tile<T, RLA, LPBA, BWD, false, TPLA>(smem_raw, nullptr, p.a, g * p.tiles_a + r);
+            else strided_tile<T, RLB, TPLB, LPBB, BWD, false>(reinterpret_cast<cplx<T>*>(smem_raw), nullptr, p.b, g * p.tiles_b + r);
+            __syncthreads();                   // every thread has issued its stores
+            if (threadIdx.x == 0) count_release(p.done + g);
+        }else{
+            if (g < p.lag) continue;           // the second front has not entered the box yet
+            const unsigned plane = g - p.lag;
+            if (threadIdx.x == 0){ while(load_acquire(p.done + plane) < tiles_first){} }
+            __syncthreads();
+            if constexpr (CONTIG_FIRST) strided_tile<T, RLB, TPLB, LPBB, BWD, SCATTER>(reinterpret_cast<cplx<T>*>(smem_raw), smap, p.b, plane * p.tiles_b + (r - tiles_first));
+            else contig_tile<T, RLA, LPBA, BWD, SCATTER, TPLA>(smem_raw, smap, p.a, plane * p.tiles_a + (r - tiles_first));
+        }
     }
 }
 
@@ -794,6 +912,184 @@ __global__ void __launch_bounds__(TPL_ * LPB, MINB) fft_contig_real_kernel(fft_a
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DCT / DST along contiguous lines, second generation (plain stores only): the Makhoul permutation never touches shared
+// memory.  With z_e = v_2e + i v_2e+1 and v = (x_0, x_2, ..., x_3, x_1), FOUR consecutive reals x_4i .. x_4i+3 are exactly
+//      z_i = (x_4i, x_4i+2)          and          z_{M-1-i} = (x_4i+3, x_4i+1)                     (i < M/2)
+// and in a Stockham pass whose legs are q + r NB the mirror index M-1-(q + r NB) is leg R-1-r of butterfly NB-1-q.  A thread
+// that owns the butterflies q and NB-1-q therefore moves whole 32-byte (fp64) / 16-byte (fp32) pieces of the line between
+// global memory and its registers: the forward transform loads its first pass that way, the backward transform stores its
+// last pass that way.  No 8-byte asynchronous copies, no bank conflicts, one shared-memory round trip less than
+// fft_contig_real_kernel.  Needs an even number of butterflies per thread in that pass and 16-byte aligned lines.
+// ---------------------------------------------------------------------------------------------------------
+template<typename T> struct quad { T c[4]; };
+template<typename T> __device__ __forceinline__ quad<T> load_quad(const T *p);
+template<> __device__ __forceinline__ quad<double> load_quad<double>(const double *p){
+    const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+    return quad<double>{{a.x, a.y, b.x, b.y}};
+}
+template<> __device__ __forceinline__ quad<float> load_quad<float>(const float *p){
+    const float4 a = reinterpret_cast<const float4*>(p)[0];
+    return quad<float>{{a.x, a.y, a.z, a.w}};
+}
+template<typename T> __device__ __forceinline__ void store_quad(T *p, T c0, T c1, T c2, T c3);
+template<> __device__ __forceinline__ void store_quad<double>(double *p, double c0, double c1, double c2, double c3){
+    double2 a; a.x = c0; a.y = c1; double2 b; b.x = c2; b.y = c3;
+    reinterpret_cast<double2*>(p)[0] = a; reinterpret_cast<double2*>(p)[1] = b;
+}
+template<> __device__ __forceinline__ void store_quad<float>(float *p, float c0, float c1, float c2, float c3){
+    float4 a; a.x = c0; a.y = c1; a.z = c2; a.w = c3;
+    reinterpret_cast<float4*>(p)[0] = a;
+}
+
+template<typename T, typename RL, int LPB, int MINB, int KIND, bool BWD, int TPL_>
+__global__ void __launch_bounds__(TPL_ * LPB, MINB) fft_contig_dct_kernel(fft_args a){
+    B200_DYN_SMEM(smem_raw);
+    static_assert(KIND == real_cos || KIND == real_sin, "cosine / sine transforms only");
+    static_assert(RL::passes >= 2, "needs at least two passes");
+    constexpr unsigned M = RL::N, NR = 2 * RL::N;
+    constexpr int TPL = TPL_;
+    constexpr int P = RL::passes;
+    constexpr unsigned PITCH = pad_index(RL::N) + 1;
+    constexpr int N1 = RL::radix(0), N2 = N1 * RL::radix(1), N3 = N2 * RL::radix(2);
+    const unsigned j = threadIdx.x % TPL, t = threadIdx.x / TPL;
+    cplx<T> *row = reinterpret_cast<cplx<T>*>(smem_raw) + t * PITCH;
+    const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
+    const cplx<T> *tx = reinterpret_cast<const cplx<T>*>(a.twiddle2);
+    const T scale = static_cast<T>(a.scale);
+    const bool do_scale = a.scale != 1.0;
+    const scatter_ctx sc{nullptr, 0, 0, 0};
+    const unsigned ntiles = tile_count<LPB>(a);
+    for(unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
+        const unsigned line = tile * LPB + t;
+        const bool valid = line < a.nlines;
+        const T *rin = reinterpret_cast<const T*>(a.in) + (valid ? tile_line_offset(a.ig, a.count_a, line) : 0);
+        T *rout = reinterpret_cast<T*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, line) : 0);
+
+        if constexpr (!BWD){
+            // ---- first pass: butterflies q and NB-1-q, inputs straight from global memory in pieces of four reals ------------
+            {
+                constexpr unsigned R = RL::radix(0), NB = M / R, BPT = NB / TPL, H = BPT / 2;
+                static_assert(BPT % 2 == 0 && R % 2 == 0, "the forward transform pairs the butterflies of its first pass");
+                cplx<T> v[BPT][R];
+                #pragma unroll
+                for(unsigned u=0; u<H; u++){
+                    const unsigned q = j + u * TPL;
+                    #pragma unroll
+                    for(unsigned r=0; r<R/2; r++){
+                        quad<T> c, d;
+                        if (valid){ c = load_quad<T>(rin + 4 * (q + r * NB)); d = load_quad<T>(rin + 4 * ((NB - 1 - q) + r * NB)); }
+                        else{ c = quad<T>{{0, 0, 0, 0}}; d = c; }
+                        if (KIND == real_sin){ c.c[1] = -c.c[1]; c.c[3] = -c.c[3]; d.c[1] = -d.c[1]; d.c[3] = -d.c[3]; }
+                        v[u][r] = mk<T>(c.c[0], c.c[2]);       v[u + H][R - 1 - r] = mk<T>(c.c[3], c.c[1]);
+                        v[u + H][r] = mk<T>(d.c[0], d.c[2]);   v[u][R - 1 - r] = mk<T>(d.c[3], d.c[1]);
+                    }
+                }
+                #pragma unroll
+                for(unsigned u=0; u<BPT; u++){
+                    const unsigned q = (u < H) ? (j + u * TPL) : (NB - 1 - (j + (u - H) * TPL));
+                    butterfly<T, R>::run(v[u]);
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++) row[pad_index(q * R + r)] = v[u][r];
+                }
+            }
+            __syncthreads();
+            contig_pass<T, RL, 1, N1, TPL, false, false, false, (P == 2)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc);
+            if constexpr (P > 2){
+                __syncthreads();
+                contig_pass<T, RL, 2, N2, TPL, false, false, false, (P == 3)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc);
+            }
+            if constexpr (P > 3){
+                __syncthreads();
+                contig_pass<T, RL, 3, N3, TPL, false, false, false, true>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc);
+            }
+            __syncthreads();
+            // ---- epilogue: spectrum of the real sequence from the pair (k, M-k), then the quarter-wave twiddle ------------------
+            if (valid){
+                const T half = static_cast<T>(0.5);
+                for(unsigned k = j; k <= M / 2; k += TPL){
+                    const cplx<T> zk = row[pad_index(k)], zm = row[pad_index((M - k) % M)];
+                    const cplx<T> E = mk<T>((zk.x + zm.x) * half, (zk.y - zm.y) * half);
+                    const cplx<T> O = mk<T>((zk.y + zm.y) * half, (zm.x - zk.x) * half);
+                    const cplx<T> Pk = cmul(ldg_c<T>(tx + 4 * k), O);
+                    const cplx<T> vk = mk<T>(E.x + Pk.x, E.y + Pk.y), vm = mk<T>(E.x - Pk.x, -(E.y - Pk.y));
+                    const cplx<T> a1 = cmul(ldg_c<T>(tx + k), vk), a2 = cmul(ldg_c<T>(tx + (M - k)), vm);
+                    const T s2 = do_scale ? T(2) * scale : T(2);
+                    auto put_y = [&](unsigned p, T value){ rout[(KIND == real_sin) ? NR - 1 - p : p] = value; };
+                    put_y(k, s2 * a1.x);
+                    if (k > 0) put_y(NR - k, -s2 * a1.y);
+                    put_y(M - k, s2 * a2.x);
+                    if (k > 0) put_y(M + k, -s2 * a2.y);
+                }
+            }
+        }else{
+            // ---- prologue: Z_k and Z_{M-k} from four reals fetched straight from global memory, written swapped ------------------
+            if (valid){
+                for(unsigned k = j; k <= M / 2; k += TPL){
+                    T yk, ynk, ymk, ypk;
+                    if constexpr (KIND == real_cos){
+                        yk = rin[k]; ynk = (k == 0) ? T(0) : rin[NR - k]; ymk = rin[M - k]; ypk = rin[M + k];
+                    }else{
+                        yk = rin[NR - 1 - k]; ynk = (k == 0) ? T(0) : rin[k - 1]; ymk = rin[M - 1 + k]; ypk = rin[M - 1 - k];
+                    }
+                    const cplx<T> wk = ldg_c<T>(tx + k), wm = ldg_c<T>(tx + (M - k));
+                    const cplx<T> vk = cmul(mk<T>(yk, -ynk), mk<T>(wk.x, -wk.y));
+                    const cplx<T> vm = cmul(mk<T>(ymk, -ypk), mk<T>(wm.x, -wm.y));
+                    const cplx<T> A = mk<T>(vk.x + vm.x, vk.y - vm.y), B = mk<T>(vk.x - vm.x, vk.y + vm.y);
+                    const cplx<T> w = ldg_c<T>(tx + 4 * k);
+                    const cplx<T> wb = cmul(mk<T>(w.x, -w.y), B);
+                    const cplx<T> C = mk<T>(-wb.y, wb.x);
+                    row[pad_index(k)] = mk<T>(A.y + C.y, A.x + C.x);
+                    if (k > 0) row[pad_index(M - k)] = mk<T>(-(A.y - C.y), A.x - C.x);
+                }
+            }
+            __syncthreads();
+            contig_pass<T, RL, 0, 1, TPL, true, false, true, false>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc);
+            if constexpr (P > 2){
+                __syncthreads();
+                contig_pass<T, RL, 1, N1, TPL, true, false, false, false>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc);
+            }
+            if constexpr (P > 3){
+                __syncthreads();
+                contig_pass<T, RL, 2, N2, TPL, true, false, false, false>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc);
+            }
+            __syncthreads();
+            // ---- last pass: butterflies q and NB-1-q, four reals per store straight from the registers ------------------------------
+            {
+                constexpr unsigned S = P - 1;
+                constexpr unsigned R = RL::radix(S), NB = M / R, BPT = NB / TPL, H = BPT / 2;
+                static_assert(BPT % 2 == 0 && R % 2 == 0, "the backward transform pairs the butterflies of its last pass");
+                cplx<T> v[BPT][R];
+                #pragma unroll
+                for(unsigned u=0; u<BPT; u++){
+                    const unsigned q = (u < H) ? (j + u * TPL) : (NB - 1 - (j + (u - H) * TPL));
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++) v[u][r] = row[pad_index(q + r * NB)];
+                    apply_twiddles<T, R, true>(v[u], tw, q);          // NS = NB in the last pass: W_N^(q r)
+                    butterfly<T, R>::run(v[u]);
+                }
+                if (valid){
+                    const T two = do_scale ? T(2) * scale : T(2);
+                    const T odd = (KIND == real_sin) ? -two : two;
+                    #pragma unroll
+                    for(unsigned u=0; u<H; u++){
+                        const unsigned q = j + u * TPL;
+                        #pragma unroll
+                        for(unsigned r=0; r<R/2; r++){
+                            // the engine ran forward on swapped data: (.x, .y) = (Im z, Re z);  z_i = v[u][r], z_{M-1-i} = v[u+H][R-1-r]
+                            const cplx<T> zi = v[u][r], zm = v[u + H][R - 1 - r];
+                            store_quad<T>(rout + 4 * (q + r * NB), two * zi.y, odd * zm.x, two * zi.x, odd * zm.y);
+                            const cplx<T> wi = v[u + H][r], wm = v[u][R - 1 - r];
+                            store_quad<T>(rout + 4 * ((NB - 1 - q) + r * NB), two * wi.y, odd * wm.x, two * wi.x, odd * wm.y);
+                        }
+                    }
+                }
+            }
+        }
+        if (tile + gridDim.x < ntiles) __syncthreads();
     }
 }
 

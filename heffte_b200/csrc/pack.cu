@@ -1,5 +1,6 @@
 // C ABI of the packers, scaling and real<->complex conversion (see include/heffte_b200_kernels.h).
 #include "pack_host.h"
+#include <cstdlib>
 #include "runtime.h"
 
 using namespace b200;
@@ -61,12 +62,44 @@ int b200_scatter_copy(int elem_bytes, long long nfast, long long nmid, long long
     return (rc == B200_ERR_INVALID) ? fail(rc, "element size must be 4, 8 or 16 bytes") : rc;
 }
 
+// Limit of a wait for a peer, from HEFFTE_B200_BARRIER_TIMEOUT_S (seconds, fractions allowed).  Default 0: no limit -- a rank that
+// is late entering forward() / backward() (host I/O between steps, a debugger, load imbalance) is simply waited for, as MPI does.
+unsigned long long b200_peer_timeout_ns(void){
+    static unsigned long long value = []{
+        const char *e = std::getenv("HEFFTE_B200_BARRIER_TIMEOUT_S");
+        double const seconds = (e != nullptr) ? std::atof(e) : 0.0;
+        return (seconds > 0.0) ? static_cast<unsigned long long>(seconds * 1e9) : 0ULL;
+    }();
+    return value;
+}
+// One word of mapped, portable host memory per process: written by a device-side wait that expired.
+unsigned long long* b200_peer_timeout_word(void){
+#ifdef B200_HOST_EMULATION
+    static unsigned long long word = 0;
+    return &word;
+#else
+    static unsigned long long *word = []() -> unsigned long long* {
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess){ cudaGetLastError(); return nullptr; }
+        *static_cast<volatile unsigned long long*>(p) = 0;
+        return static_cast<unsigned long long*>(p);
+    }();
+    return word;
+#endif
+}
+unsigned long long b200_peer_timed_out(void){
+    unsigned long long *w = b200_peer_timeout_word();
+    return (w != nullptr) ? *static_cast<volatile unsigned long long*>(w) : 0ULL;
+}
+
 int b200_peer_barrier(int nranks, int me, void *const *remote_slots, void *local_flags, unsigned long long epoch, void *stream){
     if (nranks < 1 or nranks > barrier_max_ranks or me < 0 or me >= nranks) return fail(B200_ERR_INVALID, "bad rank count for the peer barrier");
     peer_barrier_args a{};
     for(int p=0; p<nranks; p++) a.remote[p] = static_cast<unsigned long long*>(remote_slots[p]);
     a.local = static_cast<unsigned long long*>(local_flags);
     a.epoch = epoch; a.nranks = nranks; a.me = me;
+    a.timeout_ns = b200_peer_timeout_ns();
+    a.timeout_word = b200_peer_timeout_word();
 #ifdef B200_HOST_EMULATION
     return B200_SUCCESS;   // tests/emul: streams are synchronous and the thread-ranks rendezvous in after_peer_barrier()
 #else

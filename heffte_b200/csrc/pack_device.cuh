@@ -66,23 +66,39 @@ struct peer_barrier_args {
     unsigned long long *remote[barrier_max_ranks];   // remote[p]: address of slot `me` in the flag array of rank p
     unsigned long long *local;                       // my flag array (slot p is written by rank p)
     unsigned long long epoch;
+    unsigned long long timeout_ns;                   // 0: wait for ever, like the MPI calls of the reference
+    unsigned long long *timeout_word;                // mapped host memory: receives (epoch << 8 | peer + 1) when a wait expires
     int nranks, me;
 };
 
 #ifndef B200_HOST_EMULATION
+// Spin until *flag >= target (system-scope acquire).  A late peer is NOT an error: by default the wait has no limit, exactly like
+// a rank blocked in MPI_Alltoallv.  With a limit (HEFFTE_B200_BARRIER_TIMEOUT_S) an expired wait records itself in mapped host
+// memory and gives up WITHOUT trapping -- a trap would poison the CUDA context of the whole job; the next transform call on this
+// rank returns B200_ERR_PEER instead.
+__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long target, unsigned long long timeout_ns,
+                                           unsigned long long *timeout_word, unsigned long long tag){
+    unsigned long long seen = 0, start = 0, now;
+    if (timeout_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
+    for(;;){
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+        if (seen >= target) return true;
+        if (timeout_ns){
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - start > timeout_ns){
+                if (timeout_word) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(timeout_word), "l"(tag) : "memory");
+                return false;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(barrier_max_ranks) peer_barrier_kernel(peer_barrier_args a){
     const int p = threadIdx.x;
     if (p >= a.nranks || p == a.me) return;
     __threadfence_system();
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(a.remote[p]), "l"(a.epoch) : "memory");
-    unsigned long long seen = 0, start, now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
-    for(;;){
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.local + p) : "memory");
-        if (seen >= a.epoch) break;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (now - start > 20000000000ULL) __trap();     // 20 s: a peer died; fail instead of hanging the GPU
-    }
+    spin_until(a.local + p, a.epoch, a.timeout_ns, a.timeout_word, (a.epoch << 8) | static_cast<unsigned long long>(p + 1));
 }
 #endif
 

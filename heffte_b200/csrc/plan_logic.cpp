@@ -405,7 +405,7 @@ logic_plan make_execution_plan(shape const &inboxes, shape const &outboxes, int 
         if (forced != nullptr and (forced[0] == 'p' or forced[0] == 's')){
             if (attempt == 1) break;
             exec_options.use_pencils = (forced[0] == 'p');
-        }
+        }else if (options.explicit_decomposition and attempt == 1) break;      // the caller's choice runs
         if (attempt == 1 and options.subranks > 0) break;     // sub-communicator plans keep the caller's decomposition
         try{
             logic_plan plan = make_logic_plan(inboxes, outboxes, r2c_direction, exec_options, rank);

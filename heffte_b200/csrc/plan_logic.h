@@ -16,6 +16,7 @@ struct plan_options {
     bool use_reorder = false;       // default of the GPU backends (reference include/heffte_backend_cuda.h:854-857)
     int algorithm = alg_alltoallv;
     bool use_pencils = true;
+    bool explicit_decomposition = false;   // the caller chose pencils / slabs: the executed plan keeps it (else the cheaper one runs)
     bool use_gpu_aware = true;
     int subranks = -1;
 };
@@ -44,7 +45,8 @@ int balance_traffic(logic_plan &plan, int r2c_direction);
 // any result -- (1) no reorder of the intermediate boxes: the strided kernels run at the same HBM rate as the contiguous
 // ones, and without a transposition every store of a fused reshape stays a full 128-byte row on the far side of NVLink;
 // (2) balance_traffic(); (3) the decomposition -- pencils or slabs -- that moves the least over NVLink at the busiest GPU
-// (execution_cost(); the caller's use_pencils decides ties; HEFFTE_B200_DECOMPOSITION=pencils|slabs forces one).
+// (execution_cost(); a caller that sets use_pencils explicitly -- plan_options::explicit_decomposition -- gets exactly that
+// decomposition; HEFFTE_B200_DECOMPOSITION=pencils|slabs forces one for experiments).
 // HEFFTE_B200_REFERENCE_PLAN=1 in the environment returns the reference's plan unchanged.
 // The sizes a plan REPORTS (size_workspace) always come from the reference's plan.
 double execution_cost(logic_plan const &plan, int r2c_direction);

@@ -191,6 +191,19 @@ transform3d::transform3d(transform_kind kind, box3 const &inbox, box3 const &out
     // (2) the plan that is executed (plan_logic.h: no reorder of the intermediate boxes, traffic balancing)
     lp = make_execution_plan(ins, outs, r2c_dir, effective, me, &balanced_swaps);
 
+    {   // the executed plan depends on per-process switches (HEFFTE_B200_REFERENCE_PLAN, HEFFTE_B200_DECOMPOSITION): every rank
+        // must have arrived at the same boxes, or the fused stores would land at wrong addresses
+        unsigned long long h = 1469598103934665603ULL;
+        auto mix = [&](long long v){ h ^= static_cast<unsigned long long>(v); h *= 1099511628211ULL; };
+        for(int s=0; s<4; s++)
+            for(shape const *sh : {&lp.in_shape[s], &lp.out_shape[s]})
+                for(box3 const &b : *sh) for(int d=0; d<3; d++){ mix(b.low[d]); mix(b.high[d]); mix(b.order[d]); }
+        for(int d=0; d<3; d++) mix(lp.fft_direction[d]);
+        std::vector<unsigned long long> all_hashes(static_cast<size_t>(n));
+        if (comm->allgather(&h, all_hashes.data(), sizeof(h)) != 0) throw std::runtime_error("allgather of the plan signature failed");
+        for(unsigned long long v : all_hashes)
+            if (v != h) throw std::runtime_error("the ranks planned different transforms (do HEFFTE_B200_REFERENCE_PLAN / HEFFTE_B200_DECOMPOSITION differ between the ranks?)");
+    }
     inbox_count = lp.in_shape[0][me].count();
     outbox_count = lp.out_shape[3][me].count();
     base_scale = 1.0 / static_cast<double>(lp.index_count);
@@ -495,11 +508,13 @@ int transform3d::run_peer(int precision, bool is_backward, const void *in, void 
             if (X[e]){
                 rc = b200_fft1d_execute(X[e], direction, cur, dst, stage_scale, cstream);
                 if (rc) return rc;
+            }
+            {   // the mark is emitted on every rank, also with an empty box: all ranks report the same list of stages
                 char label[40];
                 std::snprintf(label, sizeof(label), "fft%d (local)", e);
-                long long const count = lp.out_shape[e][me].count();
-                long long const out_count = (tkind == kind_r2c and e == 0) ? (is_backward ? count : lp.in_shape[1][me].count()) : count;
-                long long const in_count = (tkind == kind_r2c and e == 0 and is_backward) ? lp.in_shape[1][me].count() : count;
+                long long const count = X[e] ? lp.out_shape[e][me].count() : 0;
+                long long const out_count = (tkind == kind_r2c and e == 0) ? (is_backward ? count : (X[e] ? lp.in_shape[1][me].count() : 0)) : count;
+                long long const in_count = (tkind == kind_r2c and e == 0 and is_backward) ? (X[e] ? lp.in_shape[1][me].count() : 0) : count;
                 mark(label, in_count * bytes_of(e, false) + out_count * bytes_of(e, true), 0);
             }
             cur = dst; cur_buffer = dst_buffer;     // also without a transform (empty box): every rank follows the same buffers
@@ -596,6 +611,7 @@ void* transform3d::ensure_workspace(int precision, int batch){
 
 int transform3d::forward(int precision, int batch, const void *in, void *out, void *workspace, int scaling){
     if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
+    if (ccomm->size() > 1 and b200_peer_timed_out()) return fail(B200_ERR_PEER, "a peer GPU did not reach a barrier within HEFFTE_B200_BARRIER_TIMEOUT_S");
     int rc = ensure_executors(precision);
     if (rc) return rc;
     bool const through_peers = ensure_peer(precision);
@@ -617,6 +633,7 @@ int transform3d::forward(int precision, int batch, const void *in, void *out, vo
 
 int transform3d::backward(int precision, int batch, const void *in, void *out, void *workspace, int scaling){
     if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
+    if (ccomm->size() > 1 and b200_peer_timed_out()) return fail(B200_ERR_PEER, "a peer GPU did not reach a barrier within HEFFTE_B200_BARRIER_TIMEOUT_S");
     int rc = ensure_executors(precision);
     if (rc) return rc;
     bool const through_peers = ensure_peer(precision);

@@ -80,10 +80,11 @@ class box3d:
 class plan_options:
     """reference include/heffte_plan_logic.h:131-176"""
 
-    def __init__(self, backend_tag=backend.b200, use_reorder=None, algorithm=reshape_algorithm.alltoallv, use_pencils=True, use_gpu_aware=True):
+    def __init__(self, backend_tag=backend.b200, use_reorder=None, algorithm=reshape_algorithm.alltoallv, use_pencils=None, use_gpu_aware=True):
         self.use_reorder = (backend_tag != backend.b200) if use_reorder is None else bool(use_reorder)
         self.algorithm = algorithm
-        self.use_pencils = bool(use_pencils)
+        # True / False: that decomposition is executed, as in the reference; None: the planner picks the one that moves less over NVLink
+        self.use_pencils = None if use_pencils is None else bool(use_pencils)
         self.use_gpu_aware = bool(use_gpu_aware)
         self.num_subranks = -1
 
@@ -92,7 +93,7 @@ class plan_options:
         self.num_subranks = int(num_subranks)
 
     def as_struct(self):
-        return heffte_plan_options(int(self.use_reorder), int(self.algorithm), int(self.use_pencils), int(self.use_gpu_aware))
+        return heffte_plan_options(int(self.use_reorder), int(self.algorithm), 2 if self.use_pencils is None else int(self.use_pencils), int(self.use_gpu_aware))
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -319,12 +320,42 @@ class heffte_fft_plan:
             raise heffte_input_error(("forward" if forward else "backward") + "() called with invalid array size")
         if _is_torch(inarray) != _is_torch(outarray):
             raise heffte_input_error("input and output must both be torch CUDA tensors or both be numpy arrays")
+        # raw pointers are handed to the library: the arrays must be dense (the numpy input is copied if it is not)
+        if _is_torch(inarray):
+            if not inarray.is_contiguous() or not outarray.is_contiguous():
+                raise heffte_input_error("torch tensors must be contiguous")
+        elif not outarray.flags["C_CONTIGUOUS"]:
+            raise heffte_input_error("the output numpy array must be C-contiguous")
         return pin, cin, cout
+
+    def _check_workspace(self, workspace, outarray, forward, batch):
+        """reference python/heffte.py: the workspace holds size_workspace() entries of the complex (r2r: real) type"""
+        if workspace is None:
+            return
+        if _is_torch(workspace):
+            if not workspace.is_cuda:
+                raise heffte_input_error("a torch workspace must live on the GPU")
+            if not workspace.is_contiguous():
+                raise heffte_input_error("the workspace must be contiguous")
+        elif not workspace.flags["C_CONTIGUOUS"]:
+            raise heffte_input_error("the workspace must be contiguous")
+        if _dtype_name(workspace) not in _DTYPE_INFO:
+            raise heffte_input_error("use float32, float64, complex64, or complex128 arrays")
+        wprec, wcomplex = _DTYPE_INFO[_dtype_name(workspace)]
+        spectral = outarray if forward else None
+        need_complex = self.backend_tag == backend.b200
+        if wcomplex != need_complex:
+            raise heffte_input_error("the workspace must be %s" % ("complex" if need_complex else "real"))
+        if spectral is not None and wprec != _DTYPE_INFO[_dtype_name(spectral)][0]:
+            raise heffte_input_error("the workspace must have the precision of the transform")
+        if _numel(workspace) < batch * self.size_workspace():
+            raise heffte_input_error("the workspace is smaller than size_workspace()")
 
     def _run(self, forward, inarray, outarray, workspace, scaling, batch):
         if scaling not in (0, 1, 2):
             raise heffte_input_error(("forward" if forward else "backward") + "() called with invalid scaling")
         precision, cin, cout = self._check(inarray, outarray, forward, batch)
+        self._check_workspace(workspace, outarray, forward, batch)
         lib = _lib.load()
         direction = 0 if forward else 1
         if _is_torch(inarray):
@@ -416,7 +447,7 @@ def logic_plan(inboxes, outboxes, r2c_direction=-1, use_reorder=False, algorithm
     return shapes.reshape(8, n, 9).tolist(), fdir.tolist(), count.value
 
 
-def execution_plan(inboxes, outboxes, r2c_direction=-1, use_reorder=False, algorithm=0, use_pencils=True, subranks=-1, rank=0):
+def execution_plan(inboxes, outboxes, r2c_direction=-1, use_reorder=False, algorithm=0, use_pencils=None, subranks=-1, rank=0):
     """Pure host planning: the plan a b200 transform executes (no reorder, traffic-balanced): (shapes[8][nranks][9], fft_direction, swaps)."""
     lib = _lib.load()
     n = len(inboxes)
@@ -425,7 +456,7 @@ def execution_plan(inboxes, outboxes, r2c_direction=-1, use_reorder=False, algor
     shapes = np.zeros(8 * n * 9, dtype=np.int32)
     fdir = np.zeros(3, dtype=np.int32)
     swaps = np.zeros(1, dtype=np.int32)
-    rc = lib.heffte_b200_execution_plan(n, _iptr(ib), _iptr(ob), r2c_direction, int(use_reorder), algorithm, int(use_pencils), subranks, rank,
+    rc = lib.heffte_b200_execution_plan(n, _iptr(ib), _iptr(ob), r2c_direction, int(use_reorder), algorithm, 2 if use_pencils is None else int(use_pencils), subranks, rank,
                                         _iptr(shapes), _iptr(fdir), _iptr(swaps))
     if rc != 0:
         raise heffte_input_error(_lib.last_error())

@@ -82,6 +82,9 @@ int heffte_comm_size(heffte_comm comm);
 int heffte_comm_destroy(heffte_comm comm);
 
 /* ---- the reference C API (include/heffte_c.h) ----------------------------------------------------------------------- */
+/* heffte_plan_options::use_pencils: 0 (slabs) and 1 (pencils) are executed as given, like the reference; this value lets the planner
+ * pick the decomposition that moves the fewest bytes over NVLink at the busiest GPU (also what a NULL options pointer means) */
+#define Heffte_B200_DECOMPOSITION_AUTO 2
 /* heffte_c.h:33  */ int heffte_set_default_options(int backend, heffte_plan_options *options);
 /* heffte_c.h:67  */ int heffte_plan_create(int backend, int const inbox_low[3], int const inbox_high[3], int const *inbox_order,
                                             int const outbox_low[3], int const outbox_high[3], int const *outbox_order,

@@ -105,14 +105,24 @@ namespace backend {
 //! reference include/heffte_backend_cuda.h:854-877: the FFT backend does not reorder by default, the r2r ones do
 template<typename backend_tag> struct default_plan_options { static const bool use_reorder = not std::is_same<backend_tag, backend::b200>::value; };
 
+//! use_pencils of plan_options: reads and assigns like the reference's bool; an ASSIGNED value is executed as given (pencils or
+//! slabs), an untouched one lets the planner pick the decomposition that moves the fewest bytes over NVLink
+struct decomposition_choice {
+    decomposition_choice(bool pencils = true, bool chosen_by_caller = false) : value(pencils), chosen(chosen_by_caller) {}
+    decomposition_choice& operator = (bool pencils){ value = pencils; chosen = true; return *this; }
+    operator bool () const { return value; }
+    int c_value() const { return chosen ? (value ? 1 : 0) : Heffte_B200_DECOMPOSITION_AUTO; }
+    bool value, chosen;
+};
+
 // include/heffte_plan_logic.h:131-176
 struct plan_options {
     template<typename backend_tag> plan_options(backend_tag const)
         : use_reorder(default_plan_options<backend_tag>::use_reorder), algorithm(reshape_algorithm::alltoallv), use_pencils(true), use_gpu_aware(true) {}
-    plan_options(bool reorder, reshape_algorithm alg, bool pencils) : use_reorder(reorder), algorithm(alg), use_pencils(pencils), use_gpu_aware(true) {}
+    plan_options(bool reorder, reshape_algorithm alg, bool pencils) : use_reorder(reorder), algorithm(alg), use_pencils(pencils, true), use_gpu_aware(true) {}
     bool use_reorder;
     reshape_algorithm algorithm;
-    bool use_pencils;
+    decomposition_choice use_pencils;
     bool use_gpu_aware;
     //! include/heffte_plan_logic.h:100-129: hold the intermediate stages on the first num_subranks ranks only
     void use_subcomm(int num_subranks){ num_sub = num_subranks; }
@@ -255,7 +265,7 @@ namespace b200_detail {
             long long const hi_in[3] = {static_cast<long long>(inbox.high[0]), static_cast<long long>(inbox.high[1]), static_cast<long long>(inbox.high[2])};
             long long const lo_out[3] = {static_cast<long long>(outbox.low[0]), static_cast<long long>(outbox.low[1]), static_cast<long long>(outbox.low[2])};
             long long const hi_out[3] = {static_cast<long long>(outbox.high[0]), static_cast<long long>(outbox.high[1]), static_cast<long long>(outbox.high[2])};
-            heffte_plan_options opts{o.use_reorder ? 1 : 0, static_cast<int>(o.algorithm), o.use_pencils ? 1 : 0, o.use_gpu_aware ? 1 : 0};
+            heffte_plan_options opts{o.use_reorder ? 1 : 0, static_cast<int>(o.algorithm), o.use_pencils.c_value(), o.use_gpu_aware ? 1 : 0};
             int const code = heffte_plan_create64(backend_id, stream, lo_in, hi_in, inbox.order.data(), lo_out, hi_out, outbox.order.data(),
                                                   r2c_direction, c.get(), &opts, o.get_subranks(), &plan);
             if (code != 0) throw std::runtime_error(std::string("heffte::fft3d (b200) plan creation failed: ") + heffte_last_error());

@@ -38,6 +38,7 @@ extern "C" {
 #define B200_ERR_CUDA           3
 #define B200_ERR_NCCL           4
 #define B200_ERR_NO_DEVICE      5
+#define B200_ERR_PEER           6   /* a peer GPU did not arrive within HEFFTE_B200_BARRIER_TIMEOUT_S (default: no limit) */
 
 const char* b200_last_error(void);
 /* number of kernels launched by this library since load (used by bench.py for "gpu_launches") */
@@ -148,6 +149,12 @@ int b200_scatter_copy(int elem_bytes, long long nfast, long long nmid, long long
  * array, of the slot that belongs to rank `me`; local_flags is this rank's array; epoch increases by one per barrier.
  */
 int b200_peer_barrier(int nranks, int me, void *const *remote_slots, void *local_flags, unsigned long long epoch, void *stream);
+/* Waiting for a peer has NO time limit by default (a late rank is waited for, as the reference waits in MPI).  With
+ * HEFFTE_B200_BARRIER_TIMEOUT_S=<seconds> an expired wait gives up without trapping and records itself in mapped host memory:
+ * b200_peer_timed_out() then returns non-zero ((epoch << 8) | peer + 1) and every later transform call returns B200_ERR_PEER. */
+unsigned long long b200_peer_timeout_ns(void);
+unsigned long long* b200_peer_timeout_word(void);
+unsigned long long b200_peer_timed_out(void);
 /* Replaces heffte::cuda::scale_data (src/heffte_backend_cuda.cu:138-145, 471-478): data[i] *= factor over `count` reals. */
 int b200_scale(int precision, long long count, void *data, double factor, void *stream);
 /* Replaces heffte::cuda::convert (src/heffte_backend_cuda.cu:44-56, 352-361): real -> complex (zero imaginary) and complex -> real. */

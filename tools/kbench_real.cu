@@ -64,6 +64,59 @@ int main(){
             CV(R1616, 2, 12, "contig_real <16,16> LPB2 minb12 (32thr)")
         }
     }
+    // ---- second-generation contiguous DCT kernel (register-direct Makhoul permutation) ---------------------------------------
+    {
+        a.count_a = n * n; a.in = x; a.out = x; a.ig = a.og = line_geom{1, n, 0};
+        using R488 = radix_list<4,8,8,1>; using R884b = radix_list<8,8,4,1>; using R448 = radix_list<4,4,16,1>; using R1644 = radix_list<16,4,4,1>;
+        auto run_dct = [&](auto kernel, int threads, size_t smem, int lpb){
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
+            long long blocks = (a.nlines + lpb - 1) / lpb;
+            kernel<<<(unsigned)blocks, threads, smem>>>(a);
+        };
+        constexpr size_t pitch = (pad_index(256) + 1) * 16;
+        // correctness against the first-generation kernel, forward then backward
+        {
+            std::vector<double> h(elems), r1(elems), r2(elems);
+            for(long long i=0; i<elems; i++) h[i] = (double)((i * 2654435761u) % 1000) * 1e-3;
+            for(int backward=0; backward<2; backward++){
+                a.backward = backward;
+                CK(cudaMemcpy(x, h.data(), elems*8, cudaMemcpyHostToDevice));
+                launch_contig_real<double, R1616, 4, 6, real_cos, false>(a, l); CK(cudaDeviceSynchronize());
+                CK(cudaMemcpy(r1.data(), x, elems*8, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(x, h.data(), elems*8, cudaMemcpyHostToDevice));
+                if (backward) run_dct(fft_contig_dct_kernel<double, R884b, 4, 4, real_cos, true, 32>, 128, pitch * 4, 4);
+                else run_dct(fft_contig_dct_kernel<double, R488, 4, 4, real_cos, false, 32>, 128, pitch * 4, 4);
+                CK(cudaDeviceSynchronize());
+                CK(cudaMemcpy(r2.data(), x, elems*8, cudaMemcpyDeviceToHost));
+                double err = 0, nrm = 0; for(long long i=0; i<elems; i++){ err += (r1[i]-r2[i])*(r1[i]-r2[i]); nrm += r1[i]*r1[i]; }
+                printf("dct2 kernel vs first generation (%s): rel l2 %.3e\n", backward ? "backward" : "forward", sqrt(err / nrm));
+            }
+            CK(cudaMemset(x, 0, elems*8));
+        }
+        a.backward = 0;
+        printf("-- contig dct2 kernel, cos forward\n");
+#define DV(RL, LPB, MINB, TPL, label) report(label, gb_r2r, timeit([&]{ run_dct(fft_contig_dct_kernel<double, RL, LPB, MINB, real_cos, false, TPL>, TPL * LPB, pitch * LPB, LPB); }));
+        DV(R488, 4, 4, 32, "dct2 fwd <4,8,8> TPL32 LPB4 minb4 (128thr)")
+        DV(R488, 4, 6, 32, "dct2 fwd <4,8,8> TPL32 LPB4 minb6 (128thr)")
+        DV(R488, 2, 12, 32, "dct2 fwd <4,8,8> TPL32 LPB2 minb12 (64thr)")
+        DV(R488, 8, 3, 32, "dct2 fwd <4,8,8> TPL32 LPB8 minb3 (256thr)")
+        DV(R884b, 4, 6, 16, "dct2 fwd <8,8,4> TPL16 LPB4 minb6 (64thr)")
+        DV(R884b, 8, 4, 16, "dct2 fwd <8,8,4> TPL16 LPB8 minb4 (128thr)")
+        DV(R448, 4, 6, 16, "dct2 fwd <4,4,16> TPL16 LPB4 minb6 (64thr)")
+        DV(R448, 8, 4, 16, "dct2 fwd <4,4,16> TPL16 LPB8 minb4 (128thr)")
+        a.backward = 1;
+        printf("-- contig dct2 kernel, cos backward\n");
+#define DB(RL, LPB, MINB, TPL, label) report(label, gb_r2r, timeit([&]{ run_dct(fft_contig_dct_kernel<double, RL, LPB, MINB, real_cos, true, TPL>, TPL * LPB, pitch * LPB, LPB); }));
+        DB(R884b, 4, 4, 32, "dct2 bwd <8,8,4> TPL32 LPB4 minb4 (128thr)")
+        DB(R884b, 4, 6, 32, "dct2 bwd <8,8,4> TPL32 LPB4 minb6 (128thr)")
+        DB(R884b, 2, 12, 32, "dct2 bwd <8,8,4> TPL32 LPB2 minb12 (64thr)")
+        DB(R884b, 8, 3, 32, "dct2 bwd <8,8,4> TPL32 LPB8 minb3 (256thr)")
+        DB(R884b, 4, 6, 16, "dct2 bwd <8,8,4> TPL16 LPB4 minb6 (64thr)")
+        DB(R488, 4, 6, 16, "dct2 bwd <4,8,8> TPL16 LPB4 minb6 (64thr)")
+        DB(R1644, 4, 6, 16, "dct2 bwd <16,4,4> TPL16 LPB4 minb6 (64thr)")
+        DB(R1644, 8, 4, 16, "dct2 bwd <16,4,4> TPL16 LPB8 minb4 (128thr)")
+        a.backward = 0;
+    }
     // ---- middle axis (stride n, neighbours adjacent) ----------------------------------------------------------------------
     a.in = x; a.out = x; a.ig = a.og = line_geom{n, 1, (long long)n*n}; a.count_a = n;
     for(int backward=0; backward<2; backward++){
