@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--flush-l2", action="store_true", help="write a 512 MB buffer between timed steps (forced when the working set fits the L2)")
     ap.add_argument("--l2-slab-mb", type=float, default=None,
                     help="experimental: run pairs of local transforms slab by slab through the L2 cache (sets HEFFTE_B200_L2_SLAB_MB)")
+    ap.add_argument("--unfused-conv", action="store_true", help="--kind conv as three caller-side calls (forward, multiply, backward) instead of plan.convolve()")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the comparison with the compiled reference (oracle/_ref)")
@@ -391,14 +392,13 @@ def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, re
         xin = hashed_box_torch(torch, inbox, n, 0, rdtype)
         if not real_in:
             xin = torch.complex(xin, hashed_box_torch(torch, inbox, n, count, rdtype))
-        yout = torch.empty(nout, dtype=rdtype if r2r else cdtype, device="cuda")
-        fft.forward(xin, yout, hf.scale.full)
         if conv:
-            # the fused spectral product when the plan offers it, else the caller's multiply between two transforms
-            yout.mul_(yout)
-            back = torch.empty(nin, dtype=cdtype, device="cuda")
-            fft.backward(yout, back, hf.scale.none)
-            yout = back
+            # the fused spectral operator: forward(scale full), spectrum times itself, backward, one plan-level call
+            yout = torch.empty(nin, dtype=cdtype, device="cuda")
+            fft.convolve(xin, yout, None, hf.scale.full)
+        else:
+            yout = torch.empty(nout, dtype=rdtype if r2r else cdtype, device="cuda")
+            fft.forward(xin, yout, hf.scale.full)
         torch.cuda.synchronize()
         expect_dev, checker = None, None
         if too_big:
@@ -463,7 +463,7 @@ def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, re
         data_out = data_in
     reference_copy = data_in.clone()
 
-    fused_conv = conv and hasattr(fft, "convolve_buffered")
+    fused_conv = conv and not args.unfused_conv
 
     def step():
         if fused_conv:
@@ -546,14 +546,16 @@ def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, re
 
     # ---- multi-GPU: device time of every stage of one forward and one backward transform (CUDA events on the plan's stream) ----
     multi = None
-    if distributed and batch == 1 and not fused_conv:
+    if distributed and batch == 1:
         peer_mode = bool(fft.uses_peer_memory(prec))
         per_dir = []
         if peer_mode:
             fft.stage_timing(True)
-            for direction in ("forward", "backward"):
+            for direction in (("forward",) if fused_conv else ("forward", "backward")):
                 barrier(ctx)
-                if direction == "forward":
+                if fused_conv:
+                    fft.convolve_buffered(data_in, data_in, work, None, hf.scale.full)
+                elif direction == "forward":
                     fft.forward_buffered(data_in, data_out, work, hf.scale.full)
                 else:
                     fft.backward_buffered(data_out, data_in, work, hf.scale.none)

@@ -109,6 +109,22 @@ def load():
     sig("b200_peer_barrier", c_int, c_int, c_int, ctypes.POINTER(c_vp), c_vp, ctypes.c_ulonglong, c_vp)
     sig("heffte_execute", c_int, LP_plan, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int)
     sig("heffte_execute_host", c_int, LP_plan, c_int, c_int, c_int, c_vp, c_vp, c_int)
+    sig("heffte_convolve", c_int, LP_plan, c_int, c_vp, c_vp, c_vp, c_vp, c_int)
+    sig("heffte_convolve_box", c_int, LP_plan, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll), ip)
+    sig("heffte_b200_prepare", c_int, LP_plan, c_int, c_int)
+    sig("heffte_plan_create64", c_int, c_int, c_vp, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll), ip, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll), ip,
+        c_int, c_vp, ctypes.POINTER(heffte_plan_options), c_int, ctypes.POINTER(LP_plan))
+    sig("b200_fft1d_execute_batch", c_int, c_vp, c_int, c_vp, c_vp, c_dbl, c_vp, c_int, c_ll, c_ll)
+    sig("b200_fft1d_execute_scatter_batch", c_int, c_vp, c_int, c_vp, c_vp, c_dbl, c_vp, c_int, c_ll, c_ll, c_ll, c_ll)
+    sig("b200_fft1d_pairable", c_int, c_vp, c_vp)
+    sig("b200_fft1d_execute_pair", c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_dbl, c_vp, c_int, c_vp, c_int, c_ll, c_ll, c_ll, c_ll, c_ll)
+    sig("b200_fft1d_convolvable", c_int, c_vp)
+    sig("b200_fft1d_execute_convolve", c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_int, c_ll, c_ll, c_ll, c_ll, c_ll)
+    sig("b200_pointwise_multiply", c_int, c_int, c_ll, c_vp, c_vp, c_dbl, c_vp)
+    sig("b200_scatter_copy_batch", c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_ll, c_vp, c_vp, c_vp, c_int, c_ll, c_ll, c_ll, c_ll)
+    sig("b200_copy_subboxes", c_int, c_int, c_int, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll), ctypes.POINTER(c_ll), ctypes.POINTER(c_ll),
+        c_ll, c_ll, c_vp, c_vp, c_vp, c_int, c_ll, c_ll)
+    sig("b200_peer_timed_out", ctypes.c_ulonglong)
 
     sig("heffte_b200_logic_plan", c_int, c_int, ip, ip, c_int, c_int, c_int, c_int, c_int, c_int, ip, ip, ctypes.POINTER(c_ll))
     sig("heffte_b200_make_procgrid", None, c_int, ip)

@@ -15,7 +15,7 @@ LIBNAME = "libheffte_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
-CUDA_SOURCES = ["fft1d.cu", "pack.cu"] + ["fft_inst_%s_%s_%s.cu" % (f, t, m) for f in ("strided", "contig", "real", "sreal") for t in ("f32", "f64")
+CUDA_SOURCES = ["fft1d.cu", "pack.cu"] + ["fft_inst_%s_%s_%s.cu" % (f, t, m) for f in ("strided", "contig", "real", "sreal", "pair", "conv") for t in ("f32", "f64")
                                            for m in ("direct", "scatter")]
 HOST_SOURCES = ["plan_logic.cpp", "comm.cpp", "transform.cpp", "capi.cpp"]
 

@@ -294,6 +294,25 @@ int heffte_execute(heffte_plan const plan, int precision, int direction, int bat
     return s->fft->backward(precision, batch, input, output, workspace, scale);
 }
 
+int heffte_convolve(heffte_plan const plan, int precision, void const *input, void *output, void *workspace, void const *multiplier, int scale){
+    plan_state *s = state_of(plan);
+    if (s == nullptr) return fail(B200_ERR_INVALID, "invalid plan handle");
+    if (scale < 0 or scale > 2) return fail(B200_ERR_INVALID, "invalid scale");
+    return s->fft->convolve(precision, input, output, workspace, multiplier, scale);
+}
+int heffte_convolve_box(heffte_plan const plan, long long low[3], long long high[3], int order[3]){
+    plan_state *s = state_of(plan);
+    if (s == nullptr or low == nullptr or high == nullptr or order == nullptr) return fail(B200_ERR_INVALID, "invalid plan handle or null argument");
+    box3 const b = s->fft->convolve_box();
+    for(int d=0; d<3; d++){ low[d] = b.low[d]; high[d] = b.high[d]; order[d] = b.order[d]; }
+    return Heffte_SUCCESS;
+}
+int heffte_b200_prepare(heffte_plan const plan, int precision, int batch){
+    plan_state *s = state_of(plan);
+    if (s == nullptr) return fail(B200_ERR_INVALID, "invalid plan handle");
+    return s->fft->prepare(precision, batch);
+}
+
 int heffte_execute_host(heffte_plan const plan, int precision, int direction, int batch, void const *host_input, void *host_output, int scale){
     plan_state *s = state_of(plan);
     if (s == nullptr) return fail(B200_ERR_INVALID, "invalid plan handle");

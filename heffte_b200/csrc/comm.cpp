@@ -78,6 +78,7 @@ class nccl_communicator : public communicator {
 public:
     nccl_communicator(int rank, int size, nccl_comm_t c) : comm(c){ my_rank = rank; nranks = size; }
     ~nccl_communicator() override {
+        if (side) cudaStreamDestroy(side);
         if (scratch) cudaFree(scratch);
         if (comm) nccl().CommDestroy(comm);
     }
@@ -88,11 +89,14 @@ public:
             if (cudaMalloc(&scratch, need) != cudaSuccess){ scratch = nullptr; scratch_bytes = 0; return 1; }
             scratch_bytes = need;
         }
+        // on a stream of its own: the plan-time collectives never touch the legacy default stream (which would serialise with
+        // whatever the caller has in flight there)
+        if (side == nullptr and cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess){ side = nullptr; return 1; }
         char *send = static_cast<char*>(scratch), *recv = send + bytes;
-        if (cudaMemcpy(send, mine, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
-        if (nccl().AllGather(send, recv, bytes, nccl_int8, comm, nullptr) != nccl_success) return 2;
-        if (cudaStreamSynchronize(nullptr) != cudaSuccess) return 1;
-        if (cudaMemcpy(all, recv, bytes * nranks, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+        if (cudaMemcpyAsync(send, mine, bytes, cudaMemcpyHostToDevice, side) != cudaSuccess) return 1;
+        if (nccl().AllGather(send, recv, bytes, nccl_int8, comm, side) != nccl_success) return 2;
+        if (cudaMemcpyAsync(all, recv, bytes * nranks, cudaMemcpyDeviceToHost, side) != cudaSuccess) return 1;
+        if (cudaStreamSynchronize(side) != cudaSuccess) return 1;
         return 0;
     }
     int exchange(std::vector<transfer> const &sends, std::vector<transfer> const &recvs, cudaStream_t stream) override {
@@ -161,6 +165,7 @@ private:
     nccl_comm_t comm = nullptr;
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    cudaStream_t side = nullptr;     // plan-time collectives
 };
 
 class callback_communicator : public communicator {

@@ -58,6 +58,14 @@ int cuda_launcher::run_real(bool strided, bool is_float, bool scatter, int kind,
     if (is_float) return scatter ? run_real_f32_scatter(kind, m, a, *this) : run_real_f32_direct(kind, m, a, *this);
     return scatter ? run_real_f64_scatter(kind, m, a, *this) : run_real_f64_direct(kind, m, a, *this);
 }
+int run_conv_f32_direct(int n, fft_args const &a, cuda_launcher &L);
+int run_conv_f32_scatter(int n, fft_args const &a, cuda_launcher &L);
+int run_conv_f64_direct(int n, fft_args const &a, cuda_launcher &L);
+int run_conv_f64_scatter(int n, fft_args const &a, cuda_launcher &L);
+int run_pair_f32_direct(int n, bool contig_first, pair_args const &p, cuda_launcher &L);
+int run_pair_f32_scatter(int n, bool contig_first, pair_args const &p, cuda_launcher &L);
+int run_pair_f64_direct(int n, bool contig_first, pair_args const &p, cuda_launcher &L);
+int run_pair_f64_scatter(int n, bool contig_first, pair_args const &p, cuda_launcher &L);
 int cuda_launcher::run_generic(bool is_float, long long blocks, int threads, size_t smem, generic_args const &g){
     if (is_float) return launch(fft_generic_kernel<float>, blocks, threads, smem, g);
     return launch(fft_generic_kernel<double>, blocks, threads, smem, g);
@@ -172,10 +180,135 @@ int b200_fft1d_execute_range(b200_fft1d_plan plan, int direction, const void *in
     return rc;
 }
 
-int b200_fft1d_execute_scatter(b200_fft1d_plan plan, int direction, const void *in, const void *device_scatter_map, double scale, void *stream){
-    if (plan == nullptr or device_scatter_map == nullptr) return fail(B200_ERR_INVALID, "null plan or scatter map");
+// can the two plans run as one paired launch (fft_pair_kernel)?  One transform along the contiguous axis, one along the middle
+// axis of the same box, same power-of-two length with a pair shape, complex data.
+static bool pairable(host_plan const &x, host_plan const &y){
+    host_plan const &c = (x.family == family_contig) ? x : y, &s = (x.family == family_contig) ? y : x;
+    if (c.family != family_contig or s.family != family_strided) return false;
+    b200_fft1d_desc const &dc = c.desc, &ds = s.desc;
+    if (dc.kind != B200_C2C or ds.kind != B200_C2C or dc.precision != ds.precision) return false;
+    if (dc.n != ds.n or not is_pair_length(dc.n)) return false;
+    if (dc.in.stride != 1 or dc.out.stride != 1 or ds.in.stride_a != 1 or ds.out.stride_a != 1) return false;
+    if (dc.in.stride_a != dc.n or ds.in.stride != dc.n or dc.count_a != ds.n or ds.count_a != dc.n) return false;
+    if (dc.count_b != ds.count_b or dc.in.stride_b != ds.in.stride_b or dc.in.stride_b != dc.n * ds.n) return false;
+    auto same = [](b200_line_geom const &p, b200_line_geom const &q){ return p.stride == q.stride and p.stride_a == q.stride_a and p.stride_b == q.stride_b; };
+    return same(dc.in, dc.out) and same(ds.in, ds.out);
+}
+
+int b200_fft1d_pairable(b200_fft1d_plan first, b200_fft1d_plan second){
+    return (first != nullptr and second != nullptr and pairable(first->host, second->host)) ? 1 : 0;
+}
+
+int b200_fft1d_execute_pair(b200_fft1d_plan first, b200_fft1d_plan second, int direction, const void *in, void *mid,
+                            const void *device_scatter_map, double scale, void *counters, int lag, void *stream,
+                            int batch, long long in_step, long long mid_step, long long scatter_step, long long local_shift, long long local_step){
+    if (first == nullptr or second == nullptr or mid == nullptr or counters == nullptr) return fail(B200_ERR_INVALID, "null argument");
+    if (batch < 1) return fail(B200_ERR_INVALID, "batch must be positive");
+    if (not pairable(first->host, second->host)) return B200_ERR_UNSUPPORTED;
+    bool const contig_first = (first->host.family == family_contig);
+    bool const backward = (direction == B200_BACKWARD);
+    auto fill = [&](b200_fft1d_plan plan, const void *src, void *dst, long long src_step, long long dst_step, double factor){
+        b200_fft1d_desc const &d = plan->host.desc;
+        fft_args a{};
+        a.in = src; a.out = dst; a.twiddle = plan->twiddle; a.twiddle2 = nullptr;
+        a.ig = to_geom(d.in); a.og = to_geom(d.out);
+        a.nlines = d.count_a * d.count_b;
+        a.count_a = static_cast<int>(d.count_a);
+        a.backward = backward ? 1 : 0;
+        a.scale = factor;
+        a.smap = nullptr;
+        a.in_step = src_step; a.out_step = dst_step;
+        return a;
+    };
+    fft_args one = fill(first, in, mid, in_step, mid_step, 1.0);
+    fft_args two = fill(second, mid, mid, mid_step, mid_step, scale);
+    if (device_scatter_map != nullptr){
+        two.out = nullptr; two.out_step = 0;
+        two.smap = static_cast<const scatter_map*>(device_scatter_map);
+        two.scatter_step = scatter_step; two.local_shift = local_shift; two.local_step = local_step;
+    }
+    pair_args p{};
+    p.a = contig_first ? one : two;
+    p.b = contig_first ? two : one;
+    p.planes = static_cast<unsigned>(first->host.desc.count_b);
+    {   // the planes between the two fronts hold about 16 MB: far below the 126 MB of the L2 cache, far above what is in flight
+        // (tools/kbench_pair.cu: 4 planes of 512 x 512 complex doubles, 32 planes of 256 x 256 complex floats)
+        double const plane_bytes = static_cast<double>(first->host.desc.n) * static_cast<double>(second->host.desc.n) *
+                                   ((first->host.desc.precision == B200_PREC_FLOAT) ? 8.0 : 16.0);
+        long long automatic = static_cast<long long>(16.0 * 1024 * 1024 / plane_bytes);
+        automatic = std::max<long long>(1, std::min<long long>(automatic, 64));
+        p.lag = static_cast<unsigned>(lag > 0 ? lag : automatic);
+    }
+    p.done = static_cast<unsigned*>(counters);
+    cudaStream_t const s = static_cast<cudaStream_t>(stream);
+    int rc = check_cuda(cudaMemsetAsync(counters, 0, sizeof(unsigned) * static_cast<size_t>(p.planes) * batch, s), "cudaMemsetAsync(pair counters)");
+    if (rc) return rc;
+    cuda_launcher L{s};
+    L.batch = batch;
+    int const n = static_cast<int>(first->host.desc.n);
+    bool const is_float = (first->host.desc.precision == B200_PREC_FLOAT);
+    if (device_scatter_map != nullptr) rc = is_float ? run_pair_f32_scatter(n, contig_first, p, L) : run_pair_f64_scatter(n, contig_first, p, L);
+    else rc = is_float ? run_pair_f32_direct(n, contig_first, p, L) : run_pair_f64_direct(n, contig_first, p, L);
+    return (rc == -1) ? B200_ERR_UNSUPPORTED : rc;
+}
+
+int b200_fft1d_convolvable(b200_fft1d_plan plan){
+    if (plan == nullptr) return 0;
+    b200_fft1d_desc const &d = plan->host.desc;
+    auto same = [](b200_line_geom const &p, b200_line_geom const &q){ return p.stride == q.stride and p.stride_a == q.stride_a and p.stride_b == q.stride_b; };
+    return (plan->host.family == family_strided and d.kind == B200_C2C and is_conv_length(d.n) and same(d.in, d.out)) ? 1 : 0;
+}
+
+int b200_fft1d_execute_convolve(b200_fft1d_plan plan, const void *in, void *out, const void *device_scatter_map, const void *multiplier,
+                                double scale, void *stream, int batch, long long in_step, long long out_step,
+                                long long scatter_step, long long local_shift, long long local_step){
+    if (plan == nullptr) return fail(B200_ERR_INVALID, "null plan");
+    if (batch < 1) return fail(B200_ERR_INVALID, "batch must be positive");
+    if (not b200_fft1d_convolvable(plan)) return B200_ERR_UNSUPPORTED;
+    if (out == nullptr and device_scatter_map == nullptr) return fail(B200_ERR_INVALID, "no destination");
+    b200_fft1d_desc const &d = plan->host.desc;
+    fft_args a{};
+    a.in = in; a.out = out; a.twiddle = plan->twiddle; a.twiddle2 = nullptr;
+    a.ig = to_geom(d.in); a.og = to_geom(d.out);
+    a.nlines = d.count_a * d.count_b;
+    a.count_a = static_cast<int>(d.count_a);
+    a.backward = 0;
+    a.scale = scale;
+    a.smap = static_cast<const scatter_map*>(device_scatter_map);
+    a.in_step = in_step; a.out_step = out_step; a.scatter_step = scatter_step; a.local_shift = local_shift; a.local_step = local_step;
+    a.multiplier = multiplier;
+    if (a.nlines == 0) return B200_SUCCESS;
     cuda_launcher L{static_cast<cudaStream_t>(stream)};
-    int rc = run_host_plan(plan->host, plan->twiddle, direction, in, nullptr, scale, L, device_scatter_map);
+    L.batch = batch;
+    bool const is_float = (d.precision == B200_PREC_FLOAT);
+    int rc;
+    if (device_scatter_map != nullptr) rc = is_float ? run_conv_f32_scatter(static_cast<int>(d.n), a, L) : run_conv_f64_scatter(static_cast<int>(d.n), a, L);
+    else rc = is_float ? run_conv_f32_direct(static_cast<int>(d.n), a, L) : run_conv_f64_direct(static_cast<int>(d.n), a, L);
+    return (rc == -1) ? B200_ERR_UNSUPPORTED : rc;
+}
+
+int b200_fft1d_execute_scatter(b200_fft1d_plan plan, int direction, const void *in, const void *device_scatter_map, double scale, void *stream){
+    return b200_fft1d_execute_scatter_batch(plan, direction, in, device_scatter_map, scale, stream, 1, 0, 0, 0, 0);
+}
+
+int b200_fft1d_execute_batch(b200_fft1d_plan plan, int direction, const void *in, void *out, double scale, void *stream,
+                             int batch, long long in_step, long long out_step){
+    if (plan == nullptr) return fail(B200_ERR_INVALID, "null plan");
+    if (batch < 1) return fail(B200_ERR_INVALID, "batch must be positive");
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    batch_steps steps; steps.batch = batch; steps.in_step = in_step; steps.out_step = out_step;
+    int rc = run_host_plan(plan->host, plan->twiddle, direction, in, out, scale, L, nullptr, 0, -1, steps);
+    if (rc == -1) return fail(B200_ERR_UNSUPPORTED, "no kernel for this length");
+    return rc;
+}
+
+int b200_fft1d_execute_scatter_batch(b200_fft1d_plan plan, int direction, const void *in, const void *device_scatter_map, double scale, void *stream,
+                                     int batch, long long in_step, long long scatter_step, long long local_shift, long long local_step){
+    if (plan == nullptr or device_scatter_map == nullptr) return fail(B200_ERR_INVALID, "null plan or scatter map");
+    if (batch < 1) return fail(B200_ERR_INVALID, "batch must be positive");
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    batch_steps steps; steps.batch = batch; steps.in_step = in_step; steps.scatter_step = scatter_step; steps.local_shift = local_shift; steps.local_step = local_step;
+    int rc = run_host_plan(plan->host, plan->twiddle, direction, in, nullptr, scale, L, device_scatter_map, 0, -1, steps);
     if (rc == -1) return fail(B200_ERR_UNSUPPORTED, "no kernel for this length");
     return rc;
 }

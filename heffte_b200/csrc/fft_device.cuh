@@ -231,7 +231,23 @@ struct fft_args {
     int backward;          // 0 forward, 1 backward
     double scale;          // applied on the final store
     const scatter_map *smap;   // device pointer; non-null selects the scatter variants (og is ignored)
+    // batched transforms (reference include/heffte_fft3d.h:391-414): entry e = blockIdx.y works on in + e * in_step and
+    // out + e * out_step (bytes).  Fused stores add e * scatter_step to every destination, and local_shift + e * local_step to
+    // the destinations that lie in this rank's own memory (scatter_map::local_mask): that is how the last stage of a plan lands
+    // its own part in the caller's array without a per-call copy of the map.
+    long long in_step, out_step, scatter_step, local_shift, local_step;
+    const void *multiplier;    // fused spectral operator (fft_strided_conv_kernel): null = the spectrum times itself
 };
+struct batch_shift { long long all, local; };
+// the arguments of batch entry blockIdx.y
+__device__ __forceinline__ fft_args batch_entry(fft_args a, batch_shift &shift){
+    const long long e = blockIdx.y;
+    a.in = static_cast<const char*>(a.in) + e * a.in_step;
+    if (a.out != nullptr) a.out = static_cast<char*>(a.out) + e * a.out_step;
+    shift.all = e * a.scatter_step;
+    shift.local = a.local_shift + e * a.local_step;
+    return a;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // scatter map: where the output of a batched transform goes when the following reshape is fused into the store.
@@ -256,12 +272,34 @@ __device__ __forceinline__ V* scatter_address(const scatter_map *m, int row, int
     const scatter_cell &c = m->cell[ck * (m->na * m->nb) + row];
     return reinterpret_cast<V*>(c.base) + (k * c.sk + a * c.sa + b * c.sb);
 }
-// every thread of the CTA takes part; the caller synchronises before the map is used
-__device__ __forceinline__ void scatter_stage(scatter_map *dst, const scatter_map *src){
+// every thread of the CTA takes part; the caller synchronises before the map is used.  The destination addresses are
+// re-based on the way: shift.all for every cell, shift.local on top for the cells that stay in this rank's memory.
+__device__ __forceinline__ void scatter_stage(scatter_map *dst, const scatter_map *src, batch_shift shift = batch_shift{0, 0}){
     const int words = (scatter_header_bytes + static_cast<int>(sizeof(scatter_cell)) * src->ncells) / 16;
+    const unsigned long long mask = src->local_mask;
     const int4 *g = reinterpret_cast<const int4*>(src);
     int4 *s = reinterpret_cast<int4*>(dst);
-    for(int i = threadIdx.x; i < words; i += blockDim.x) s[i] = g[i];
+    constexpr int header_words = scatter_header_bytes / 16;
+    for(int i = threadIdx.x; i < words; i += blockDim.x){
+        int4 v = g[i];
+        const int w = i - header_words;
+        if (w >= 0 && (w & 1) == 0){          // first half of a cell: the 64-bit base address sits in (x, y)
+            long long base = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(v.y)) << 32) | static_cast<unsigned>(v.x));
+            base += shift.all + (((mask >> (w >> 1)) & 1ULL) ? shift.local : 0);
+            v.x = static_cast<int>(static_cast<unsigned long long>(base) & 0xffffffffULL);
+            v.y = static_cast<int>(static_cast<unsigned long long>(base) >> 32);
+        }
+        s[i] = v;
+    }
+}
+// the same resolution for kernels that read the map from global memory (generic kernel)
+template<typename V>
+__device__ __forceinline__ V* scatter_address_shifted(const scatter_map *m, int row, int k, int a, int b, batch_shift shift){
+    const int ck = scatter_find(m->cut_k, m->nk, k);
+    const int index = ck * (m->na * m->nb) + row;
+    const scatter_cell &c = m->cell[index];
+    const long long base = c.base + shift.all + (((m->local_mask >> index) & 1ULL) ? shift.local : 0);
+    return reinterpret_cast<V*>(base) + (k * c.sk + a * c.sa + b * c.sb);
 }
 
 __device__ __forceinline__ long long line_offset(line_geom const &g, int count_a, long long line){
@@ -476,17 +514,187 @@ template<int LPB> __host__ __device__ inline unsigned tile_count(fft_args const 
 // The kernel walks the tiles grid-stride: one tile per CTA when the grid covers the box (the usual launch), several when the
 // grid is kept thin on purpose so that another kernel can share the SMs (NVLink-bound stages of a multi-GPU plan).
 template<typename T, typename RL, int TPL, int LPB, int MINB, bool BWD, bool SCATTER>
-__global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a){
+__global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a0){
     B200_DYN_SMEM(smem_raw);
+    batch_shift shift;
+    const fft_args a = batch_entry(a0, shift);
     cplx<T> *sm = reinterpret_cast<cplx<T>*>(smem_raw);
     scatter_map *smap = nullptr;
     if constexpr (SCATTER){
         smap = reinterpret_cast<scatter_map*>(sm + static_cast<size_t>(RL::N) * LPB);   // behind the tile
-        scatter_stage(smap, a.smap);      // visible after the first barrier inside strided_tile
+        scatter_stage(smap, a.smap, shift);      // visible after the first barrier inside strided_tile
     }
     const unsigned ntiles = tile_count<LPB>(a);
     for(unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
         strided_tile<T, RL, TPL, LPB, BWD, SCATTER>(sm, smap, a, tile);
+        if (tile + gridDim.x < ntiles) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused spectral operator along a strided axis: forward transform, pointwise product, backward transform of every line in ONE
+// pass over memory (reference benchmarks/convolution.cpp:86-97 runs forward(scale::full), x[i] *= x[i], backward as three
+// sweeps plus the reshapes around them).  The forward part is the decimation-in-frequency kernel above, except that the last
+// pass leaves the spectrum in the tile (digit-reversed positions).  The product is applied there: times `scale`, then times
+// itself or times the caller's multiplier (same layout as the input box).  The backward part undoes the passes in reverse
+// order -- decimation in time: twiddle, then butterfly, on re/im-swapped data so that the forward butterflies and the forward
+// twiddle table serve (swap(z conj(w)) = swap(z) w, swap(conjDFT(z)) = DFT(swap(z))) -- and ends in natural order, stored
+// through the plain or the fused-reshape path like any backward transform.
+// ---------------------------------------------------------------------------------------------------------
+// forward pass S < P-1: butterfly, twiddle, back into the tile
+template<typename T, typename RL, int S, int TPL, int LPB>
+__device__ __forceinline__ void conv_forward_pass(cplx<T> *sm, unsigned t, unsigned j, const cplx<T> *tw){
+    constexpr unsigned R = RL::radix(S);
+    constexpr unsigned ST = RL::stride(S);
+    constexpr unsigned NB = RL::N / R;
+    static_assert(S < RL::passes - 1, "the last pass is the turn-around");
+    #pragma unroll 1
+    for(unsigned u=0; u<NB/TPL; u++){
+        const unsigned q = j + u * TPL;
+        const unsigned o = q % ST;
+        const unsigned p0 = (q / ST) * (ST * R) + o;
+        cplx<T> *cell = sm + p0 * LPB + t;
+        cplx<T> v[R];
+        #pragma unroll
+        for(unsigned r=0; r<R; r++) v[r] = cell[r * ST * LPB];
+        butterfly<T, R>::run(v);
+        apply_twiddles<T, R, true>(v, tw, o * (RL::N / (ST * R)));
+        #pragma unroll
+        for(unsigned r=0; r<R; r++) cell[r * ST * LPB] = v[r];
+    }
+}
+
+// turn-around, pass P-1 in both directions on the same R adjacent positions: last forward butterfly, the product (natural
+// index of leg r: k0 + r N/R), swap, first backward butterfly (no twiddle on either side of the product)
+template<typename T, typename RL, int TPL, int LPB, bool SCATTER>
+__device__ __forceinline__ void conv_turn_pass(cplx<T> *sm, unsigned t, unsigned j, bool valid, T scale, const cplx<T> *mult, long long mstride,
+                                                cplx<T> *gout, long long ostride, scatter_ctx const &sc){
+    constexpr unsigned S = RL::passes - 1;
+    constexpr unsigned R = RL::radix(S);
+    constexpr unsigned NB = RL::N / R;
+    #pragma unroll 1
+    for(unsigned u=0; u<NB/TPL; u++){
+        const unsigned q = j + u * TPL;
+        const unsigned p0 = q * R;
+        cplx<T> *cell = sm + p0 * LPB + t;
+        cplx<T> v[R];
+        #pragma unroll
+        for(unsigned r=0; r<R; r++) v[r] = cell[r * LPB];
+        butterfly<T, R>::run(v);
+        const unsigned k0 = dif_output_index<RL>(p0);
+        #pragma unroll
+        for(unsigned r=0; r<R; r++){
+            cplx<T> x = mk<T>(v[r].x * scale, v[r].y * scale);
+            cplx<T> m = x;
+            if (mult != nullptr) m = valid ? mult[static_cast<long long>(k0 + r * (RL::N / R)) * mstride] : mk<T>(0, 0);
+            v[r] = cswap(cmul(x, m));
+        }
+        butterfly<T, R>::run(v);
+        if constexpr (S > 0){
+            #pragma unroll
+            for(unsigned r=0; r<R; r++) cell[r * LPB] = v[r];
+        }else{
+            // a single pass: the turn-around is the whole transform
+            if (valid){
+                #pragma unroll
+                for(unsigned r=0; r<R; r++){
+                    const cplx<T> x = cswap(v[r]);
+                    if constexpr (SCATTER) *scatter_address<cplx<T>>(sc.map, sc.row, static_cast<int>(p0 + r), sc.a, sc.b) = x;
+                    else gout[static_cast<long long>(p0 + r) * ostride] = x;
+                }
+            }
+        }
+    }
+}
+
+// backward pass S < P-1 (decimation in time on swapped data): twiddle, butterfly; pass 0 stores the result
+template<typename T, typename RL, int S, int TPL, int LPB, bool SCATTER>
+__device__ __forceinline__ void conv_backward_pass(cplx<T> *sm, unsigned t, unsigned j, bool valid, cplx<T> *gout, long long ostride,
+                                                    const cplx<T> *tw, scatter_ctx const &sc){
+    constexpr unsigned R = RL::radix(S);
+    constexpr unsigned ST = RL::stride(S);
+    constexpr unsigned NB = RL::N / R;
+    static_assert(S < RL::passes - 1, "the last pass is the turn-around");
+    #pragma unroll 1
+    for(unsigned u=0; u<NB/TPL; u++){
+        const unsigned q = j + u * TPL;
+        const unsigned o = q % ST;
+        const unsigned p0 = (q / ST) * (ST * R) + o;
+        cplx<T> *cell = sm + p0 * LPB + t;
+        cplx<T> v[R];
+        #pragma unroll
+        for(unsigned r=0; r<R; r++) v[r] = cell[r * ST * LPB];
+        apply_twiddles<T, R, true>(v, tw, o * (RL::N / (ST * R)));
+        butterfly<T, R>::run(v);
+        if constexpr (S > 0){
+            #pragma unroll
+            for(unsigned r=0; r<R; r++) cell[r * ST * LPB] = v[r];
+        }else{
+            // pass 0 comes last: position p0 + r ST is the natural index
+            if (valid){
+                #pragma unroll
+                for(unsigned r=0; r<R; r++){
+                    const cplx<T> x = cswap(v[r]);
+                    if constexpr (SCATTER) *scatter_address<cplx<T>>(sc.map, sc.row, static_cast<int>(p0 + r * ST), sc.a, sc.b) = x;
+                    else gout[static_cast<long long>(p0 + r * ST) * ostride] = x;
+                }
+            }
+        }
+    }
+}
+
+template<typename T, typename RL, int TPL, int LPB, int MINB, bool SCATTER>
+__global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_conv_kernel(fft_args a0){
+    B200_DYN_SMEM(smem_raw);
+    batch_shift shift;
+    const fft_args a = batch_entry(a0, shift);
+    cplx<T> *sm = reinterpret_cast<cplx<T>*>(smem_raw);
+    scatter_map *smap = nullptr;
+    if constexpr (SCATTER){
+        smap = reinterpret_cast<scatter_map*>(sm + static_cast<size_t>(RL::N) * LPB);
+        scatter_stage(smap, a.smap, shift);
+    }
+    const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
+    const T scale = static_cast<T>(a.scale);
+    constexpr int P = RL::passes;
+    const unsigned t = threadIdx.x % LPB, j = threadIdx.x / LPB;
+    const unsigned ntiles = tile_count<LPB>(a);
+    for(unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
+        const unsigned line = (SCATTER ? scatter_tile_order<LPB>(a, tile) : tile) * LPB + t;
+        const bool valid = line < a.nlines;
+        const long long ioff = valid ? tile_line_offset(a.ig, a.count_a, line) : 0;
+        if (valid){
+            const cplx<T> *src = reinterpret_cast<const cplx<T>*>(a.in) + ioff + static_cast<long long>(j) * a.ig.stride;
+            const long long hop = static_cast<long long>(TPL) * a.ig.stride;
+            cplx<T> *dst = sm + j * LPB + t;
+            #pragma unroll 4
+            for(unsigned row = j; row < RL::N; row += TPL){
+                async_copy<sizeof(cplx<T>)>(dst, src);
+                src += hop;
+                dst += TPL * LPB;
+            }
+        }
+        const cplx<T> *mult = (a.multiplier != nullptr) ? reinterpret_cast<const cplx<T>*>(a.multiplier) + ioff : nullptr;
+        cplx<T> *gout = nullptr;
+        scatter_ctx sc{nullptr, 0, 0, 0};
+        if constexpr (SCATTER){
+            sc.map = smap;
+            sc.b = static_cast<int>(line / static_cast<unsigned>(a.count_a));
+            sc.a = static_cast<int>(line - static_cast<unsigned>(sc.b) * static_cast<unsigned>(a.count_a));
+        }else{
+            gout = reinterpret_cast<cplx<T>*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, line) : 0);
+        }
+        async_wait_all();
+        __syncthreads();
+        if constexpr (SCATTER) sc.row = valid ? scatter_row(sc.map, sc.a, sc.b) : 0;
+
+        if constexpr (P > 1){ conv_forward_pass<T, RL, 0, TPL, LPB>(sm, t, j, tw); __syncthreads(); }
+        if constexpr (P > 2){ conv_forward_pass<T, RL, 1, TPL, LPB>(sm, t, j, tw); __syncthreads(); }
+        if constexpr (P > 3){ conv_forward_pass<T, RL, 2, TPL, LPB>(sm, t, j, tw); __syncthreads(); }
+        conv_turn_pass<T, RL, TPL, LPB, SCATTER>(sm, t, j, valid, scale, mult, a.ig.stride, gout, a.og.stride, sc);
+        if constexpr (P > 3){ __syncthreads(); conv_backward_pass<T, RL, 2, TPL, LPB, SCATTER>(sm, t, j, valid, gout, a.og.stride, tw, sc); }
+        if constexpr (P > 2){ __syncthreads(); conv_backward_pass<T, RL, 1, TPL, LPB, SCATTER>(sm, t, j, valid, gout, a.og.stride, tw, sc); }
+        if constexpr (P > 1){ __syncthreads(); conv_backward_pass<T, RL, 0, TPL, LPB, SCATTER>(sm, t, j, valid, gout, a.og.stride, tw, sc); }
         if (tile + gridDim.x < ntiles) __syncthreads();
     }
 }
@@ -614,13 +822,15 @@ __device__ __forceinline__ void contig_tile(unsigned char *smem_raw, const scatt
 }
 
 template<typename T, typename RL, int LPB, int MINB, bool BWD, bool SCATTER, int TPL = RL::N / RL::rmax>
-__global__ void __launch_bounds__(TPL * LPB, MINB) fft_contig_kernel(fft_args a){
+__global__ void __launch_bounds__(TPL * LPB, MINB) fft_contig_kernel(fft_args a0){
     B200_DYN_SMEM(smem_raw);
+    batch_shift shift;
+    const fft_args a = batch_entry(a0, shift);
     constexpr unsigned PITCH = pad_index(RL::N) + 1;
     scatter_map *smap = nullptr;
     if constexpr (SCATTER){
         smap = reinterpret_cast<scatter_map*>(smem_raw + ((sizeof(cplx<T>) * PITCH * LPB + 15) / 16) * 16);
-        scatter_stage(smap, a.smap);
+        scatter_stage(smap, a.smap, shift);
         __syncthreads();
     }
     const unsigned ntiles = tile_count<LPB>(a);
@@ -682,11 +892,15 @@ template<typename T, typename RLA, int LPBA, int TPLA, typename RLB, int TPLB, i
 __global__ void __launch_bounds__(TPLB * LPBB, MINB) fft_pair_kernel(pair_args p){
     static_assert(TPLA * LPBA == TPLB * LPBB, "both phases use the whole CTA");
     B200_DYN_SMEM(smem_raw);
+    batch_shift shift_a, shift_b;
+    p.a = batch_entry(p.a, shift_a);
+    p.b = batch_entry(p.b, shift_b);
+    p.done += static_cast<size_t>(blockIdx.y) * p.planes;
     constexpr size_t tile_bytes = pair_tile_bytes<T, RLA, LPBA, RLB, LPBB>();
     scatter_map *smap = nullptr;
     if constexpr (SCATTER){
         smap = reinterpret_cast<scatter_map*>(smem_raw + tile_bytes);
-        scatter_stage(smap, CONTIG_FIRST ? p.b.smap : p.a.smap);
+        scatter_stage(smap, CONTIG_FIRST ? p.b.smap : p.a.smap, CONTIG_FIRST ? shift_b : shift_a);
     }
     const unsigned tiles_first = CONTIG_FIRST ? p.tiles_a : p.tiles_b, tiles_second = CONTIG_FIRST ? p.tiles_b : p.tiles_a;
     const unsigned group = tiles_first + tiles_second;
@@ -737,8 +951,10 @@ __host__ __device__ constexpr unsigned real_pos(unsigned p){ return 2 * pad_inde
 
 // (TPL_: threads per line, see fft_contig_kernel; the first radix of the schedule must be even for the sine kinds)
 template<typename T, typename RL, int LPB, int MINB, int KIND, bool BWD, bool SCATTER, int TPL_ = RL::N / RL::rmax>
-__global__ void __launch_bounds__(TPL_ * LPB, MINB) fft_contig_real_kernel(fft_args a){
+__global__ void __launch_bounds__(TPL_ * LPB, MINB) fft_contig_real_kernel(fft_args a0){
     B200_DYN_SMEM(smem_raw);
+    batch_shift shift;
+    const fft_args a = batch_entry(a0, shift);
     constexpr unsigned M = RL::N, NR = 2 * RL::N;
     constexpr int TPL = TPL_;
     constexpr unsigned PITCH = pad_index(RL::N) + 1;
@@ -758,7 +974,7 @@ __global__ void __launch_bounds__(TPL_ * LPB, MINB) fft_contig_real_kernel(fft_a
     scatter_ctx sc{nullptr, 0, 0, 0};
     if constexpr (SCATTER){
         scatter_map *smap = reinterpret_cast<scatter_map*>(smem_raw + ((sizeof(cplx<T>) * PITCH * LPB + 15) / 16) * 16);
-        scatter_stage(smap, a.smap);
+        scatter_stage(smap, a.smap, shift);
         __syncthreads();
         sc.map = smap;
         sc.b = static_cast<int>(line / static_cast<unsigned>(a.count_a));
@@ -946,8 +1162,10 @@ template<> __device__ __forceinline__ void store_quad<float>(float *p, float c0,
 }
 
 template<typename T, typename RL, int LPB, int MINB, int KIND, bool BWD, int TPL_>
-__global__ void __launch_bounds__(TPL_ * LPB, MINB) fft_contig_dct_kernel(fft_args a){
+__global__ void __launch_bounds__(TPL_ * LPB, MINB) fft_contig_dct_kernel(fft_args a0){
     B200_DYN_SMEM(smem_raw);
+    batch_shift shift;
+    const fft_args a = batch_entry(a0, shift);
     static_assert(KIND == real_cos || KIND == real_sin, "cosine / sine transforms only");
     static_assert(RL::passes >= 2, "needs at least two passes");
     constexpr unsigned M = RL::N, NR = 2 * RL::N;
@@ -1173,8 +1391,10 @@ __device__ __forceinline__ void strided_real_pass(cplx<T> *sm, unsigned t, unsig
 }
 
 template<typename T, typename RL, int TPL, int LPB, int MINB, int KIND, bool BWD, bool SCATTER>
-__global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_real_kernel(fft_args a){
+__global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_real_kernel(fft_args a0){
     B200_DYN_SMEM(smem_raw);
+    batch_shift shift;
+    const fft_args a = batch_entry(a0, shift);
     constexpr unsigned M = RL::N, NR = 2 * RL::N;
     constexpr bool R2C = (KIND == real_r2c);
     cplx<T> *sm = reinterpret_cast<cplx<T>*>(smem_raw);
@@ -1194,7 +1414,7 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_real_kernel(fft_a
     long long ooff = 0;
     if constexpr (SCATTER){
         scatter_map *smap = reinterpret_cast<scatter_map*>(sm + static_cast<size_t>(RL::N) * LPB);   // behind the tile
-        scatter_stage(smap, a.smap);
+        scatter_stage(smap, a.smap, shift);
         sc.map = smap;
         sc.b = static_cast<int>(line / static_cast<unsigned>(a.count_a));
         sc.a = static_cast<int>(line - static_cast<unsigned>(sc.b) * static_cast<unsigned>(a.count_a));
@@ -1340,6 +1560,7 @@ struct generic_args {
     int nfactors;
     int factors[24];
     const scatter_map *smap;   // device pointer or null: fused reshape on the store side (read from global memory, L1-resident)
+    long long in_step, out_step, scatter_step, local_shift, local_step;   // batched transforms, see fft_args
 };
 
 template<typename T>
@@ -1386,6 +1607,14 @@ __device__ __forceinline__ cplx<T> generic_load(generic_args const &a, const voi
 template<typename T>
 __global__ void fft_generic_kernel(generic_args a){
     B200_DYN_SMEM(smem_raw);
+    batch_shift shift;
+    {
+        const long long e = blockIdx.y;
+        a.in = static_cast<const char*>(a.in) + e * a.in_step;
+        if (a.out != nullptr) a.out = static_cast<char*>(a.out) + e * a.out_step;
+        shift.all = e * a.scatter_step;
+        shift.local = a.local_shift + e * a.local_step;
+    }
     const int m = a.m, n = a.n;
     const int lpb = a.lpb;
     cplx<T> *buf0 = reinterpret_cast<cplx<T>*>(smem_raw);
@@ -1481,8 +1710,8 @@ __global__ void fft_generic_kernel(generic_args a){
             if (a.smap != nullptr){
                 const int lb = static_cast<int>(line / a.count_a), la = static_cast<int>(line - static_cast<long long>(lb) * a.count_a);
                 const int row = scatter_row(a.smap, la, lb);
-                where = complex_out ? static_cast<void*>(scatter_address<cplx<T>>(a.smap, row, i, la, lb))
-                                    : static_cast<void*>(scatter_address<T>(a.smap, row, i, la, lb));
+                where = complex_out ? static_cast<void*>(scatter_address_shifted<cplx<T>>(a.smap, row, i, la, lb, shift))
+                                    : static_cast<void*>(scatter_address_shifted<T>(a.smap, row, i, la, lb, shift));
             }else{
                 const long long pos = line_offset(a.og, a.count_a, line) + (long long)i * a.og.stride;
                 where = complex_out ? static_cast<void*>(reinterpret_cast<cplx<T>*>(a.out) + pos) : static_cast<void*>(reinterpret_cast<T*>(a.out) + pos);

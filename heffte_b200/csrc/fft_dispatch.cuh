@@ -88,6 +88,31 @@ int dispatch_strided(int n, fft_args const &a, Launcher &L){
     }
 }
 
+// fused spectral operator along a strided axis (fft_strided_conv_kernel): the tile shapes of the strided kernel
+template<typename T, typename RL, int TPL, int LPB, int MINB, bool SCATTER, typename Launcher>
+int launch_strided_conv(fft_args const &a, Launcher &L){
+    long long blocks = (a.nlines + LPB - 1) / LPB;
+    size_t smem = sizeof(cplx<T>) * (size_t)RL::N * LPB + (SCATTER ? sizeof(scatter_map) : 0);
+    return L.launch(fft_strided_conv_kernel<T, RL, TPL, LPB, MINB, SCATTER>, blocks, TPL * LPB, smem, a);
+}
+constexpr bool is_conv_length(long long n){ return is_pow2(n) && n >= pow2_min && n <= pow2_max; }
+template<typename T, bool SCATTER, typename Launcher>
+int dispatch_strided_conv(int n, fft_args const &a, Launcher &L){
+    constexpr int M = row_lines<T>::value / 8;
+    switch(n){
+        case 16:   return launch_strided_conv<T, radix_list<4, 4, 1, 1>,   4 / M, 32 * M, 2, SCATTER>(a, L);
+        case 32:   return launch_strided_conv<T, radix_list<8, 4, 1, 1>,   4 / M, 32 * M, 2, SCATTER>(a, L);
+        case 64:   return launch_strided_conv<T, radix_list<8, 8, 1, 1>,   8 / M, 16 * M, 2, SCATTER>(a, L);
+        case 128:  return launch_strided_conv<T, radix_list<8, 4, 4, 1>,  16 / M,  8 * M, 2, SCATTER>(a, L);
+        case 256:  return launch_strided_conv<T, radix_list<8, 8, 4, 1>,  32 / M,  8 * M, 2, SCATTER>(a, L);
+        case 512:  return launch_strided_conv<T, radix_list<8, 8, 8, 1>,  32 / M,  8 * M, 3, SCATTER>(a, L);
+        case 1024: return launch_strided_conv<T, radix_list<16, 8, 8, 1>, 32 / M,  8 * M, 1, SCATTER>(a, L);
+        case 2048: return launch_strided_conv<T, radix_list<8, 8, 8, 4>, 128 / M,  4 * M, 1, SCATTER>(a, L);
+        case 4096: return launch_strided_conv<T, radix_list<8, 8, 8, 8>, 256 / M,  2 * M, 1, SCATTER>(a, L);
+        default: return -1;
+    }
+}
+
 template<typename T, bool SCATTER, typename Launcher>
 int dispatch_contig(int n, fft_args const &a, Launcher &L){
     // small CTAs (64-128 threads), many per SM: measured best on B200 (tools/kbench.cu, profiles/)
@@ -121,6 +146,52 @@ int dispatch_contig(int n, fft_args const &a, Launcher &L){
         case 500:  return launch_contig_tpl<T, radix_list<10, 10, 5, 1>,  25,  4, 4, SCATTER>(a, L);
         case 1000: return launch_contig_tpl<T, radix_list<10, 10, 10, 1>, 50,  2, 2, SCATTER>(a, L);
         case 2000: return launch_contig_tpl<T, radix_list<10, 10, 10, 2>, 100, 1, 2, SCATTER>(a, L);
+        default: return -1;
+    }
+}
+
+// ---- paired kernel (fft_pair_kernel): the contiguous-axis and the middle-axis transform of a box in one persistent launch ------
+// Shapes per length: both phases use the same number of threads; the larger tile decides the shared memory.
+// tools/kbench_pair.cu on B200: 256^3 fp32 0.097 ms against 0.119 ms for the two launches; 512^3 fp64 1.55 against 1.27 ms --
+// the L2 pays for the small planes only, so the plan uses the pair where the second transform is bound by NVLink anyway (the
+// local pass in front of a fused reshape hides behind the transfer) and, without a reshape, for single precision.
+template<typename T, int N> struct pair_shape;
+template<> struct pair_shape<double, 128>  { using A = radix_list<8, 4, 4, 1>;  using B = radix_list<8, 4, 4, 1>;  static constexpr int TPLA = 16, LPBA = 8,  TPLB = 16, LPBB = 8,  MINB = 4; };
+template<> struct pair_shape<double, 256>  { using A = radix_list<8, 8, 4, 1>;  using B = radix_list<8, 8, 4, 1>;  static constexpr int TPLA = 32, LPBA = 8,  TPLB = 32, LPBB = 8,  MINB = 3; };
+template<> struct pair_shape<double, 512>  { using A = radix_list<8, 8, 8, 1>;  using B = radix_list<8, 8, 8, 1>;  static constexpr int TPLA = 64, LPBA = 4,  TPLB = 32, LPBB = 8,  MINB = 3; };
+template<> struct pair_shape<double, 1024> { using A = radix_list<16, 8, 8, 1>; using B = radix_list<16, 8, 8, 1>; static constexpr int TPLA = 64, LPBA = 4,  TPLB = 32, LPBB = 8,  MINB = 1; };
+template<> struct pair_shape<float, 128>   { using A = radix_list<8, 4, 4, 1>;  using B = radix_list<8, 4, 4, 1>;  static constexpr int TPLA = 16, LPBA = 8,  TPLB = 8,  LPBB = 16, MINB = 4; };
+template<> struct pair_shape<float, 256>   { using A = radix_list<16, 16, 1, 1>; using B = radix_list<8, 8, 4, 1>; static constexpr int TPLA = 16, LPBA = 16, TPLB = 16, LPBB = 16, MINB = 4; };
+template<> struct pair_shape<float, 512>   { using A = radix_list<8, 8, 8, 1>;  using B = radix_list<8, 8, 8, 1>;  static constexpr int TPLA = 64, LPBA = 4,  TPLB = 16, LPBB = 16, MINB = 3; };
+template<> struct pair_shape<float, 1024>  { using A = radix_list<16, 8, 8, 1>; using B = radix_list<16, 8, 8, 1>; static constexpr int TPLA = 64, LPBA = 4,  TPLB = 16, LPBB = 16, MINB = 1; };
+
+constexpr bool is_pair_length(long long n){ return n == 128 || n == 256 || n == 512 || n == 1024; }
+
+// L.launch_pair(kernel, threads, smem, args) sizes the grid to what is resident at once (one CTA in the emulation)
+template<typename T, int N, bool SCATTER, typename Launcher>
+int launch_pair_n(bool contig_first, pair_args p, Launcher &L){
+    using S = pair_shape<T, N>;
+    constexpr int threads = S::TPLB * S::LPBB;
+    static_assert(S::TPLA * S::LPBA == threads, "pair shapes must agree on the block size");
+    size_t const smem = pair_smem_bytes<T, typename S::A, S::LPBA, typename S::B, S::LPBB, SCATTER>();
+    if (p.a.count_a % S::LPBA != 0 or p.b.count_a % S::LPBB != 0) return -1;     // tiles must not straddle planes
+    p.tiles_a = static_cast<unsigned>(p.a.count_a / S::LPBA);
+    p.tiles_b = static_cast<unsigned>(p.b.count_a / S::LPBB);
+    bool const bwd = p.a.backward != 0;
+    if (contig_first){
+        if (bwd) return L.launch_pair(fft_pair_kernel<T, typename S::A, S::LPBA, S::TPLA, typename S::B, S::TPLB, S::LPBB, S::MINB, true, SCATTER, true>, threads, smem, p);
+        return L.launch_pair(fft_pair_kernel<T, typename S::A, S::LPBA, S::TPLA, typename S::B, S::TPLB, S::LPBB, S::MINB, false, SCATTER, true>, threads, smem, p);
+    }
+    if (bwd) return L.launch_pair(fft_pair_kernel<T, typename S::A, S::LPBA, S::TPLA, typename S::B, S::TPLB, S::LPBB, S::MINB, true, SCATTER, false>, threads, smem, p);
+    return L.launch_pair(fft_pair_kernel<T, typename S::A, S::LPBA, S::TPLA, typename S::B, S::TPLB, S::LPBB, S::MINB, false, SCATTER, false>, threads, smem, p);
+}
+template<typename T, bool SCATTER, typename Launcher>
+int dispatch_pair(int n, bool contig_first, pair_args const &p, Launcher &L){
+    switch(n){
+        case 128:  return launch_pair_n<T, 128, SCATTER>(contig_first, p, L);
+        case 256:  return launch_pair_n<T, 256, SCATTER>(contig_first, p, L);
+        case 512:  return launch_pair_n<T, 512, SCATTER>(contig_first, p, L);
+        case 1024: return launch_pair_n<T, 1024, SCATTER>(contig_first, p, L);
         default: return -1;
     }
 }

@@ -116,12 +116,22 @@ inline int make_host_plan(b200_fft1d_desc const &desc, host_plan &plan, const ch
 
 inline line_geom to_geom(b200_line_geom const &g){ return line_geom{g.stride, g.stride_a, g.stride_b}; }
 
+// batched execution: `batch` entries, entry e works on in + e * in_step / out + e * out_step (bytes); fused stores: see fft_args
+struct batch_steps {
+    int batch = 1;
+    long long in_step = 0, out_step = 0, scatter_step = 0, local_shift = 0, local_step = 0;
+};
+template<typename args_t> inline void set_steps(args_t &a, batch_steps const &s){
+    a.in_step = s.in_step; a.out_step = s.out_step; a.scatter_step = s.scatter_step; a.local_shift = s.local_shift; a.local_step = s.local_step;
+}
+
 // runs the plan through a Launcher (CUDA stream launcher in the product, thread emulation in tests/emul)
 // `scatter` (device pointer to a scatter_map, or null) fuses the following reshape into the store of the transform
 // b_begin / b_count (b_count >= 0) restrict the launch to the lines with b in [b_begin, b_begin + b_count): a slab of the box
 template<typename Launcher>
 int run_host_plan(host_plan const &plan, const void *twiddle, int direction, const void *in, void *out, double scale, Launcher &L,
-                  const void *scatter = nullptr, long long b_begin = 0, long long b_count = -1){
+                  const void *scatter = nullptr, long long b_begin = 0, long long b_count = -1, batch_steps const &steps = batch_steps()){
+    L.batch = steps.batch;
     b200_fft1d_desc const &d = plan.desc;
     bool const backward = (direction == B200_BACKWARD);
     bool const is_float = (d.precision == B200_PREC_FLOAT);
@@ -161,6 +171,7 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
             a.backward = backward ? 1 : 0;
             a.scale = scale;
             a.smap = static_cast<const scatter_map*>(scatter);
+            set_steps(a, steps);
             return L.run_real(plan.family == family_strided_real, is_float, scatter != nullptr, plan.real_kind, static_cast<int>(d.n / 2), a);
         }
     }else if (plan.family != family_generic){
@@ -173,6 +184,7 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
         a.backward = backward ? 1 : 0;
         a.scale = scale;
         a.smap = static_cast<const scatter_map*>(scatter);
+        set_steps(a, steps);
         return L.run_pow2(plan.family == family_strided, is_float, scatter != nullptr, static_cast<int>(d.n), a);
     }
 
@@ -190,6 +202,7 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
     g.lines_fast = plan.lines_fast;
     g.nfactors = plan.nfactors;
     g.smap = static_cast<const scatter_map*>(scatter);
+    set_steps(g, steps);
     for(int i=0; i<24; i++) g.factors[i] = (i < plan.nfactors) ? plan.factors[i] : 1;
     switch(d.kind){
         case B200_C2C:  g.mode = mode_c2c; break;

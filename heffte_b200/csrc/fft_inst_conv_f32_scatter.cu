@@ -1,0 +1,7 @@
+// One slice of the fused spectral-operator kernel instantiations (float, fused reshape store); see fft_dispatch.cuh.
+#include "fft_dispatch.cuh"
+#include "runtime.h"
+
+namespace b200 {
+int run_conv_f32_scatter(int n, fft_args const &a, cuda_launcher &L){ return dispatch_strided_conv<float, true>(n, a, L); }
+}

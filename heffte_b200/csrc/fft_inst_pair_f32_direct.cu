@@ -1,0 +1,7 @@
+// One slice of the paired-kernel instantiations (float, plain store); see fft_dispatch.cuh.
+#include "fft_dispatch.cuh"
+#include "runtime.h"
+
+namespace b200 {
+int run_pair_f32_direct(int n, bool contig_first, pair_args const &p, cuda_launcher &L){ return dispatch_pair<float, false>(n, contig_first, p, L); }
+}

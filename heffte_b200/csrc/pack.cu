@@ -52,14 +52,43 @@ int b200_transpose_unpack(int elem_bytes, long long nfast, long long nmid, long 
     return rc;
 }
 
-int b200_scatter_copy(int elem_bytes, long long nfast, long long nmid, long long nslow, long long line_stride, long long plane_stride,
-                      const void *src, const void *device_scatter_map, void *stream){
+int b200_scatter_copy_batch(int elem_bytes, long long nfast, long long nmid, long long nslow, long long line_stride, long long plane_stride,
+                            const void *src, const void *device_scatter_map, void *stream,
+                            int batch, long long in_step, long long scatter_step, long long local_shift, long long local_step){
     if (device_scatter_map == nullptr) return fail(B200_ERR_INVALID, "null scatter map");
     if (nfast > 2147483647LL or nmid > 2147483647LL or nslow > 2147483647LL) return fail(B200_ERR_UNSUPPORTED, "box too large");
     cuda_launcher L{static_cast<cudaStream_t>(stream)};
-    scatter_copy_args a{src, static_cast<const scatter_map*>(device_scatter_map), (int) nfast, (int) nmid, (int) nslow, line_stride, plane_stride, 1};
+    L.batch = batch;
+    scatter_copy_args a{src, static_cast<const scatter_map*>(device_scatter_map), (int) nfast, (int) nmid, (int) nslow, line_stride, plane_stride, 1,
+                        in_step, scatter_step, local_shift, local_step};
     int rc = launch_scatter_copy(elem_bytes, a, L);
     return (rc == B200_ERR_INVALID) ? fail(rc, "element size must be 4, 8 or 16 bytes") : rc;
+}
+int b200_scatter_copy(int elem_bytes, long long nfast, long long nmid, long long nslow, long long line_stride, long long plane_stride,
+                      const void *src, const void *device_scatter_map, void *stream){
+    return b200_scatter_copy_batch(elem_bytes, nfast, nmid, nslow, line_stride, plane_stride, src, device_scatter_map, stream, 1, 0, 0, 0, 0);
+}
+
+int b200_copy_subboxes(int elem_bytes, int npieces, const long long *offsets, const long long *nfast, const long long *nmid, const long long *nslow,
+                       long long line_stride, long long plane_stride, const void *src, void *dst, void *stream,
+                       int batch, long long src_step, long long dst_step){
+    if (npieces < 0 or (npieces > 0 and (offsets == nullptr or nfast == nullptr or nmid == nullptr or nslow == nullptr))) return fail(B200_ERR_INVALID, "bad piece list");
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    for(int first = 0; first < npieces; first += multi_copy_max){
+        multi_copy_args a{};
+        a.src = src; a.dst = dst; a.line = line_stride; a.plane = plane_stride; a.src_step = src_step; a.dst_step = dst_step;
+        for(int i = first; i < npieces and a.npieces < multi_copy_max; i++){
+            if (nfast[i] <= 0 or nmid[i] <= 0 or nslow[i] <= 0) continue;
+            if (nfast[i] > 2147483647LL or nmid[i] > 2147483647LL or nslow[i] > 2147483647LL) return fail(B200_ERR_UNSUPPORTED, "box too large");
+            a.offset[a.npieces] = offsets[i];
+            a.nfast[a.npieces] = static_cast<int>(nfast[i]); a.nmid[a.npieces] = static_cast<int>(nmid[i]); a.nslow[a.npieces] = static_cast<int>(nslow[i]);
+            a.npieces++;
+        }
+        int rc = launch_multi_copy(elem_bytes, a, batch, L);
+        if (rc == B200_ERR_INVALID) return fail(rc, "element size must be 4, 8 or 16 bytes");
+        if (rc) return rc;
+    }
+    return B200_SUCCESS;
 }
 
 // Limit of a wait for a peer, from HEFFTE_B200_BARRIER_TIMEOUT_S (seconds, fractions allowed).  Default 0: no limit -- a rank that
@@ -106,6 +135,15 @@ int b200_peer_barrier(int nranks, int me, void *const *remote_slots, void *local
     cuda_launcher L{static_cast<cudaStream_t>(stream)};
     return L.launch(peer_barrier_kernel, 1, barrier_max_ranks, 0, a);
 #endif
+}
+
+int b200_pointwise_multiply(int precision, long long count, void *data, const void *multiplier, double factor, void *stream){
+    if (count <= 0) return B200_SUCCESS;
+    cuda_launcher L{static_cast<cudaStream_t>(stream)};
+    pointwise_args a{data, multiplier, count, factor};
+    long long const blocks = stream_blocks(count, 256);
+    if (precision == B200_PREC_FLOAT) return L.launch(pointwise_kernel<float2, float>, blocks, 256, 0, a);
+    return L.launch(pointwise_kernel<double2, double>, blocks, 256, 0, a);
 }
 
 int b200_scale(int precision, long long count, void *data, double factor, void *stream){

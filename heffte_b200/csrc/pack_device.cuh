@@ -21,15 +21,17 @@ struct scatter_copy_args {
     int nfast, nmid, nslow;
     long long line, plane;       // strides of my box
     int tf;                      // threads along the fast axis (power of two <= 256)
+    long long in_step, scatter_step, local_shift, local_step;   // batched transforms (bytes), see fft_args
 };
 
 template<typename V>
 __global__ void __launch_bounds__(256) scatter_copy_kernel(scatter_copy_args a){
     B200_DYN_SMEM(map_raw);
     scatter_map *smap = reinterpret_cast<scatter_map*>(map_raw);
-    scatter_stage(smap, a.smap);
+    const long long entry = blockIdx.y;
+    scatter_stage(smap, a.smap, batch_shift{entry * a.scatter_step, a.local_shift + entry * a.local_step});
     __syncthreads();
-    const V *src = reinterpret_cast<const V*>(a.src);
+    const V *src = reinterpret_cast<const V*>(static_cast<const char*>(a.src) + entry * a.in_step);
     const int tx = threadIdx.x & (a.tf - 1), ty = threadIdx.x / a.tf;
     const int rows = blockDim.x / a.tf;                         // lines handled side by side by one CTA
     const long long nlines = static_cast<long long>(a.nmid) * a.nslow;
@@ -101,6 +103,41 @@ __global__ void __launch_bounds__(barrier_max_ranks) peer_barrier_kernel(peer_ba
     spin_until(a.local + p, a.epoch, a.timeout_ns, a.timeout_word, (a.epoch << 8) | static_cast<unsigned long long>(p + 1));
 }
 #endif
+
+// ---------------------------------------------------------------------------------------------------------
+// sub-boxes of one box copied to the same positions of another array with the same layout: after the last fused reshape of a
+// plan the pieces received from the other GPUs move from the plan's arena into the caller's array.  One launch for all
+// pieces (blockIdx.y) and all batch entries (blockIdx.z); rows are moved in 16-byte words when the geometry allows.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int multi_copy_max = 16;
+struct multi_copy_args {
+    const void *src;
+    void *dst;
+    long long line, plane;                 // strides of the box, in elements
+    long long offset[multi_copy_max];      // first element of every piece
+    int nfast[multi_copy_max], nmid[multi_copy_max], nslow[multi_copy_max];
+    int npieces;
+    long long src_step, dst_step;          // bytes between batch entries
+};
+
+template<typename V, int RATIO>      // V: access type, RATIO: elements per access (geometry in elements of sizeof(V) / RATIO bytes)
+__global__ void __launch_bounds__(256) multi_copy_kernel(multi_copy_args a){
+    const int piece = blockIdx.y;
+    const long long entry = blockIdx.z;
+    const V *src = reinterpret_cast<const V*>(static_cast<const char*>(a.src) + entry * a.src_step);
+    V *dst = reinterpret_cast<V*>(static_cast<char*>(a.dst) + entry * a.dst_step);
+    const long long base = a.offset[piece] / RATIO, line = a.line / RATIO, plane = a.plane / RATIO;
+    const int nf = a.nfast[piece] / RATIO, nm = a.nmid[piece];
+    const long long rows = static_cast<long long>(nm) * a.nslow[piece];
+    // a CTA moves whole rows; short rows share a CTA pass
+    const int tf = (nf >= 256) ? 256 : ((nf >= 128) ? 128 : ((nf >= 64) ? 64 : 32));
+    const int tx = threadIdx.x % tf, ty = threadIdx.x / tf, side = 256 / tf;
+    for(long long row = static_cast<long long>(blockIdx.x) * side + ty; row < rows; row += static_cast<long long>(gridDim.x) * side){
+        const long long s = row / nm, m = row - s * nm;
+        const long long at = base + s * plane + m * line;
+        for(int f = tx; f < nf; f += tf) dst[at + f] = src[at + f];
+    }
+}
 
 struct copy3d_args {
     const void *src;
@@ -193,6 +230,24 @@ __global__ void __launch_bounds__(256) scale_kernel(scale_args a){
     const T factor = static_cast<T>(a.factor);
     const long long step = (long long)gridDim.x * blockDim.x;
     for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += step) data[i] *= factor;
+}
+
+struct pointwise_args { void *data; const void *multiplier; long long count; double factor; };
+
+// data[i] = data[i] * factor * M[i]  (M null: data[i] itself): the pointwise product of a spectral operator, unfused form
+template<typename C, typename T>
+__global__ void __launch_bounds__(256) pointwise_kernel(pointwise_args a){
+    C *data = reinterpret_cast<C*>(a.data);
+    const C *mult = reinterpret_cast<const C*>(a.multiplier);
+    const T factor = static_cast<T>(a.factor);
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += step){
+        C x = data[i];
+        x.x *= factor; x.y *= factor;
+        const C m = (mult != nullptr) ? mult[i] : x;
+        C r; r.x = x.x * m.x - x.y * m.y; r.y = x.x * m.y + x.y * m.x;
+        data[i] = r;
+    }
 }
 
 struct convert_args { const void *src; void *dst; long long count; };

@@ -3,6 +3,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cstdint>
 
 #include "../../include/heffte_b200_kernels.h"
 #include "pack_device.cuh"
@@ -25,6 +26,33 @@ int launch_copy3d(int elem_bytes, copy3d_args const &a, Launcher &L){
         case 4:  return L.launch(copy3d_kernel<float>,   blocks, 256, 0, a);
         case 8:  return L.launch(copy3d_kernel<double>,  blocks, 256, 0, a);
         case 16: return L.launch(copy3d_kernel<double2>, blocks, 256, 0, a);
+        default: return B200_ERR_INVALID;
+    }
+}
+
+// the pieces must not be empty; elem_bytes in {4, 8, 16}
+template<typename Launcher>
+int launch_multi_copy(int elem_bytes, multi_copy_args const &a, int batch, Launcher &L){
+    if (a.npieces <= 0 or batch <= 0) return B200_SUCCESS;
+    // widest access (16 bytes) that divides every row length, offset and stride
+    int ratio = 16 / elem_bytes;
+    auto fits = [&](int r){
+        if ((reinterpret_cast<uintptr_t>(a.src) | reinterpret_cast<uintptr_t>(a.dst)) % (static_cast<uintptr_t>(r) * elem_bytes)) return false;
+        if (a.line % r or a.plane % r or (a.src_step % (r * elem_bytes)) or (a.dst_step % (r * elem_bytes))) return false;
+        for(int i=0; i<a.npieces; i++) if (a.nfast[i] % r or a.offset[i] % r) return false;
+        return true;
+    };
+    while(ratio > 1 and not fits(ratio)) ratio /= 2;
+    long long most_rows = 1;
+    for(int i=0; i<a.npieces; i++) most_rows = std::max<long long>(most_rows, static_cast<long long>(a.nmid[i]) * a.nslow[i]);
+    long long const gx = std::max<long long>(1, std::min<long long>(most_rows, (long long) num_sms * 8 / std::max(1, a.npieces)));
+    int const bytes = elem_bytes * ratio;
+    switch(bytes){
+        case 4:  return L.launch3(multi_copy_kernel<float, 1>, gx, a.npieces, batch, 256, 0, a);
+        case 8:  return (ratio == 2) ? L.launch3(multi_copy_kernel<double, 2>, gx, a.npieces, batch, 256, 0, a) : L.launch3(multi_copy_kernel<double, 1>, gx, a.npieces, batch, 256, 0, a);
+        case 16: return (ratio == 4) ? L.launch3(multi_copy_kernel<double2, 4>, gx, a.npieces, batch, 256, 0, a)
+                                     : ((ratio == 2) ? L.launch3(multi_copy_kernel<double2, 2>, gx, a.npieces, batch, 256, 0, a)
+                                                     : L.launch3(multi_copy_kernel<double2, 1>, gx, a.npieces, batch, 256, 0, a));
         default: return B200_ERR_INVALID;
     }
 }

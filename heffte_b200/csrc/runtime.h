@@ -4,6 +4,7 @@
 
 #include "cuda_compat.h"
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -24,15 +25,35 @@ void allow_smem(const void *kernel, size_t bytes);
 
 struct cuda_launcher {
     cudaStream_t stream;
+    int batch = 1;          // grid.y: entries of a batched transform (the kernels read blockIdx.y)
     template<typename kernel_t, typename args_t>
     int launch(kernel_t kernel, long long blocks, int threads, size_t smem, args_t const &args){
-        if (blocks <= 0) return B200_SUCCESS;
-        if (blocks > 2147483647LL) return fail(B200_ERR_UNSUPPORTED, "grid too large");
+        if (blocks <= 0 or batch <= 0) return B200_SUCCESS;
+        if (blocks > 2147483647LL or batch > 65535) return fail(B200_ERR_UNSUPPORTED, "grid too large");
 #ifdef B200_HOST_EMULATION
-        emul::launch(kernel, dim3(static_cast<unsigned>(blocks)), dim3(static_cast<unsigned>(threads)), smem, args);   // tests/emul only
+        emul::launch(kernel, dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(batch)), dim3(static_cast<unsigned>(threads)), smem, args);   // tests/emul only
 #else
         if (smem > 48 * 1024) allow_smem(reinterpret_cast<const void*>(kernel), smem);
-        kernel<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(args);
+        kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(batch)), threads, smem, stream>>>(args);
+#endif
+        launch_counter.fetch_add(1, std::memory_order_relaxed);
+        return check_cuda(cudaPeekAtLastError(), "kernel launch");
+    }
+    // persistent launch of the paired kernel: the whole grid must be resident at once (its CTAs wait for one another), so it is
+    // sized by the occupancy of the kernel; grid.y = batch entries
+    template<typename kernel_t>
+    int launch_pair(kernel_t kernel, int threads, size_t smem, pair_args const &args){
+        if (batch <= 0) return B200_SUCCESS;
+#ifdef B200_HOST_EMULATION
+        emul::launch(kernel, dim3(1u, static_cast<unsigned>(batch)), dim3(static_cast<unsigned>(threads)), smem, args);   // blocks run one after the other
+#else
+        if (smem > 48 * 1024) allow_smem(reinterpret_cast<const void*>(kernel), smem);
+        int per_sm = 0, sms = 0, device = 0;
+        if (cudaGetDevice(&device) != cudaSuccess or cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess or
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess or per_sm < 1)
+            return check_cuda(cudaGetLastError(), "occupancy query of the paired kernel");
+        int const grid = std::max(1, (per_sm * sms) / batch);      // all entries share the GPU
+        kernel<<<dim3(static_cast<unsigned>(grid), static_cast<unsigned>(batch)), threads, smem, stream>>>(args);
 #endif
         launch_counter.fetch_add(1, std::memory_order_relaxed);
         return check_cuda(cudaPeekAtLastError(), "kernel launch");

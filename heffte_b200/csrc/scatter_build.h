@@ -27,8 +27,9 @@ inline idx box_stride(box3 const &box, int dim){
 // dest[r] / dest_base[r]: box of rank r after the reshape and the address (valid on THIS device) of its first element.
 // Returns false with a reason when the box cannot be expressed (too many cells, uncovered region).
 // owners (optional, scatter_max_cells entries): the rank every cell lands on
+// self_rank (optional): the rank that writes; the cells it keeps are flagged in map.local_mask
 inline bool build_scatter_map(box3 const &mine, int k_pos, std::vector<box3> const &dest, std::vector<void*> const &dest_base,
-                              int elem_bytes, scatter_map &map, std::string &why, int *owners = nullptr){
+                              int elem_bytes, scatter_map &map, std::string &why, int *owners = nullptr, int self_rank = -1){
     map = scatter_map{};
     map.nk = map.na = map.nb = 1;
     if (mine.empty()){ map.ncells = 0; return true; }
@@ -86,6 +87,7 @@ inline bool build_scatter_map(box3 const &mine, int k_pos, std::vector<box3> con
         box3 const &b = dest[owner];
         scatter_cell &cell = map.cell[(ck * counts[1] + ca) * counts[2] + cb];
         if (owners) owners[(ck * counts[1] + ca) * counts[2] + cb] = owner;
+        if (owner == self_rank) map.local_mask |= 1ULL << ((ck * counts[1] + ca) * counts[2] + cb);
         // destination element of local (k, a, b): sum_d (mine.low[d] + local_d - b.low[d]) * stride_b(d)
         idx shift = 0;
         for(int d=0; d<3; d++) shift += (mine.low[d] - b.low[d]) * box_stride(b, d);

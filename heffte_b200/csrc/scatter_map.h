@@ -12,9 +12,11 @@ constexpr int scatter_max_cells = 64;
 struct scatter_map {
     int nk, na, nb, ncells;
     int cut_k[scatter_max_cuts], cut_a[scatter_max_cuts], cut_b[scatter_max_cuts];   // first index of every cell (cut[0] = 0)
+    unsigned long long local_mask;   // bit c: cell c lands in the memory of the rank that writes it (may be re-based per call)
+    unsigned long long reserved;
     scatter_cell cell[scatter_max_cells];                                            // index (ck * na + ca) * nb + cb
 };
-constexpr int scatter_header_bytes = 16 + 3 * 4 * scatter_max_cuts;   // 112: multiple of 16
+constexpr int scatter_header_bytes = 16 + 3 * 4 * scatter_max_cuts + 16;   // 128: multiple of 16
 
 
 } // namespace b200

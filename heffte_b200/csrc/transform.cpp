@@ -247,32 +247,39 @@ idx transform3d::workspace_layout(logic_plan const &p, idx &comm_elements, idx &
     return comm_elements + temp_elements + last_chunk;
 }
 
-transform3d::~transform3d(){
-    for(int p=0; p<2; p++){
-        peer_state &P = peer[p];
-        if (P.arena){
-            cudaStreamSynchronize(cstream);
-            if (not P.arenas.empty()) ccomm->unmap_peers(P.arenas);
-            cudaFree(P.arena);
-        }
-        if (P.maps) cudaFree(P.maps);
+void transform3d::release_peer(int precision){
+    peer_state &P = peer[precision];
+    if (P.arena){
+        cudaStreamSynchronize(cstream);
+        if (not P.arenas.empty()) ccomm->unmap_peers(P.arenas);
+        cudaFree(P.arena);
+        P.arena = nullptr;
     }
+    P.arenas.clear();
+    if (P.maps){ cudaFree(P.maps); P.maps = nullptr; }
+    P.active = false;
+}
+
+transform3d::~transform3d(){
+    for(int p=0; p<2; p++) release_peer(p);
     for(int p=0; p<2; p++) for(int i=0; i<3; i++) if (exec[p][i]) b200_fft1d_destroy(exec[p][i]);
     if (own_workspace) cudaFree(own_workspace);
+    if (counters) cudaFree(counters);
     for(cudaEvent_t e : marks) cudaEventDestroy(e);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // peer-memory mode
 // ------------------------------------------------------------------------------------------------------------
-// Collective over the ranks of the plan (first transform of each precision): allocate and peer-map the arena, build the
-// scatter maps of every stage.  Any rank failing any step makes every rank fall back to the exchange() path.
-bool transform3d::ensure_peer(int precision){
+// Collective over the ranks of the plan (first transform of each precision, or prepare(); again when a larger batch arrives):
+// allocate and peer-map the arena -- three rotating buffers of `batch` entries -- and build the scatter maps of every stage.
+// Any rank failing any step makes every rank fall back to the exchange() path.
+bool transform3d::ensure_peer(int precision, int batch){
     peer_state &P = peer[precision];
-    if (P.tried) return P.active;
-    P.tried = true;
+    batch = std::max(batch, 1);
+    if (P.tried and (not P.active or batch <= P.capacity)) return P.active;
     int const n = ccomm->size();
-    if (n < 2 or n > 64) return false;
+    if (n < 2 or n > 64){ P.tried = true; return false; }
     int const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
     int const cplx_bytes = 2 * real_bytes;
     bool const complex_data = (tkind == kind_c2c or tkind == kind_r2c);
@@ -282,15 +289,21 @@ bool transform3d::ensure_peer(int precision){
         P.fused[1][s] = shapes_differ(lp.out_shape[3-s], lp.in_shape[3-s]);
         any = any or P.fused[0][s];
     }
-    if (not any) return false;
+    if (not any){ P.tried = true; return false; }
+    if (P.tried) release_peer(precision);          // a larger batch: every rank rebuilds (the call is collective)
+    P.tried = true;                                // the flags of a new arena start at zero on every rank: so does the epoch
+    P.epoch = 0;
+    P.next_buffer = 0;
 
-    // a buffer holds the largest box this rank ever owns, in the widest element type of the plan
-    // (the same size on every rank: buffer 1 of a peer sits at a known offset inside its arena)
+    // an entry holds the largest box any rank ever owns, in the widest element type of the plan (the same size on every
+    // rank: the buffers of a peer sit at known offsets inside its arena)
     idx largest = 1;
     for(int s=0; s<4; s++)
         for(int r=0; r<n; r++) largest = std::max(largest, std::max(lp.in_shape[s][r].count(), lp.out_shape[s][r].count()));
-    P.buffer_bytes = ((static_cast<size_t>(largest) * (complex_data ? cplx_bytes : real_bytes) + 255) / 256) * 256;
-    size_t const arena_bytes = 4096 + 2 * P.buffer_bytes;
+    P.entry_bytes = ((static_cast<size_t>(largest) * (complex_data ? cplx_bytes : real_bytes) + 255) / 256) * 256;
+    P.capacity = batch;
+    P.buffer_bytes = P.entry_bytes * static_cast<size_t>(batch);
+    size_t const arena_bytes = 4096 + 3 * P.buffer_bytes;
     int ok = 1;
     if (cudaMalloc(&P.arena, arena_bytes) != cudaSuccess){ P.arena = nullptr; cudaGetLastError(); ok = 0; }
     if (ok and (cudaMemset(P.arena, 0, 4096) != cudaSuccess or cudaDeviceSynchronize() != cudaSuccess)) ok = 0;
@@ -311,9 +324,8 @@ bool transform3d::ensure_peer(int precision){
     P.remote_slots.resize(n);
     for(int r=0; r<n; r++) P.remote_slots[r] = static_cast<char*>(arenas[r]) + sizeof(unsigned long long) * me;
 
-    // scatter maps: ((direction * 4 + stage) * 2 + buffer)
-    std::vector<scatter_map> maps(16);
-    std::vector<int> owners(16 * scatter_max_cells, -1);
+    // scatter maps: ((direction * 4 + stage) * 3 + buffer)
+    std::vector<scatter_map> maps(24);
     std::string why;
     int built = 1;
     for(int dir=0; dir<2 and built; dir++){
@@ -335,15 +347,14 @@ bool transform3d::ensure_peer(int precision){
             stage_elems[dir][st] = written.count();
             sent_elems[dir][st] = 0;
             for(int r=0; r<n; r++) if (r != me) sent_elems[dir][st] += written.overlap(dest[r]).count();
-            for(int w=0; w<2; w++){
+            for(int w=0; w<3; w++){
                 std::vector<void*> bases(n);
                 for(int r=0; r<n; r++) bases[r] = static_cast<char*>(arenas[r]) + 4096 + static_cast<size_t>(w) * P.buffer_bytes;
-                if (not build_scatter_map(written, k_pos, dest, bases, bytes, maps[(dir * 4 + st) * 2 + w], why,
-                                          owners.data() + static_cast<size_t>((dir * 4 + st) * 2 + w) * scatter_max_cells)){ built = 0; break; }
+                if (not build_scatter_map(written, k_pos, dest, bases, bytes, maps[(dir * 4 + st) * 3 + w], why, nullptr, me)){ built = 0; break; }
             }
         }
     }
-    if (built and cudaMalloc(&P.maps, (maps.size() + 2) * sizeof(scatter_map)) != cudaSuccess){ P.maps = nullptr; cudaGetLastError(); built = 0; }
+    if (built and cudaMalloc(&P.maps, maps.size() * sizeof(scatter_map)) != cudaSuccess){ P.maps = nullptr; cudaGetLastError(); built = 0; }
     if (built and cudaMemcpy(P.maps, maps.data(), maps.size() * sizeof(scatter_map), cudaMemcpyHostToDevice) != cudaSuccess) built = 0;
     {
         std::vector<int> votes(n);
@@ -351,16 +362,28 @@ bool transform3d::ensure_peer(int precision){
         for(int v : votes) if (not v) built = 0;
     }
     if (not built){
-        ccomm->unmap_peers(P.arenas);
-        P.arenas.clear();
-        cudaFree(P.arena); P.arena = nullptr;
-        if (P.maps){ cudaFree(P.maps); P.maps = nullptr; }
+        release_peer(precision);
         return false;
     }
-    P.host_maps = maps;
-    P.owners = owners;
     P.active = true;
     return true;
+}
+
+int transform3d::prepare(int precision, int batch){
+    if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
+    int rc = ensure_executors(precision);
+    if (rc) return rc;
+    ensure_peer(precision, batch);
+    return B200_SUCCESS;
+}
+
+void* transform3d::pair_counters(size_t count){
+    if (count > counters_count){
+        if (counters){ cudaStreamSynchronize(cstream); cudaFree(counters); counters = nullptr; counters_count = 0; }
+        if (cudaMalloc(&counters, count * sizeof(unsigned)) != cudaSuccess){ cudaGetLastError(); return nullptr; }
+        counters_count = count;
+    }
+    return counters;
 }
 
 void transform3d::mark(const char *name, long long local_bytes, long long sent_bytes){
@@ -400,151 +423,317 @@ int transform3d::peer_fence(int precision){
     return rc;
 }
 
-// One transform with every reshape fused into the store of the kernel in front of it.  Data alternates between the two
-// peer-mapped buffers; a fence follows every stage that writes into other ranks' memory.
-int transform3d::run_peer(int precision, bool is_backward, const void *in, void *out, double scale){
+// One transform (or one fused spectral operator) with every reshape fused into the store of the kernel in front of it, for
+// `batch` entries at once: every stage is ONE launch for all entries (grid.y) followed by ONE fence (reference: batch widens the
+// messages of every reshape, src/heffte_reshape3d.cpp:379-384, 401-419).
+// Data moves through three peer-mapped buffers that rotate: a stage that writes into other ranks' memory always targets the
+// buffer after the last one used, on every rank alike, and a fence follows it.  When a rank writes buffer w, every rank has
+// passed the fence of the previous remote stage, so it has finished all reads of what w held before (that was consumed two
+// remote stages ago at the latest) -- no fence is needed at the start of a transform.
+// A purely local transform in front of a fused one runs inside the same persistent kernel (fft_pair_kernel): its HBM traffic
+// hides behind the NVLink-bound stores.
+int transform3d::run_peer(int precision, int mode, int batch, const void *in, void *out, double scale, const void *multiplier){
     peer_state &P = peer[precision];
     int const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
     int const cplx_bytes = 2 * real_bytes;
     bool const complex_data = (tkind == kind_c2c or tkind == kind_r2c);
-    int const dir = is_backward ? 1 : 0;
-    int const direction = is_backward ? B200_BACKWARD : B200_FORWARD;
     b200_fft1d_plan const *X = exec[precision];
-    auto map_of = [&](int st, int w){ return static_cast<const char*>(P.maps) + sizeof(scatter_map) * static_cast<size_t>((dir * 4 + st) * 2 + w); };
+    static bool const allow_pair = (std::getenv("HEFFTE_B200_NO_PAIR") == nullptr);
+    static bool const allow_direct = (std::getenv("HEFFTE_B200_NO_DIRECT_OUTPUT") == nullptr);
+    static bool const trace = (std::getenv("HEFFTE_B200_TRACE") != nullptr);
 
-    // the scaling rides on the LAST transform stage of the plan -- a global choice: a rank whose box is empty in that stage
-    // must not scale earlier, its data would be scaled again by the ranks that receive it
-    int const last_fft = 3;
-
-    pending.clear();
-    mark("start", 0, 0);
-    // every peer has finished reading its buffers of the previous transform before anybody writes into them again
-    int rc = peer_fence(precision);
-    if (rc) return rc;
-    mark("fence", 0, 0);
-    unsigned touched = 0;            // buffers read or written locally since the last fence
-    auto bytes_of = [&](int e, bool output){     // element size on the input / output side of executor e in this direction
+    // the sequence of stages: (direction, stage); a convolution replaces the last forward stage and the first backward stage
+    // by the operator kernel, whose store is the reshape of backward stage 1
+    struct op { int dir, st; bool conv; };
+    std::vector<op> ops;
+    if (mode == mode_convolve){
+        ops = {{0, 0, false}, {0, 1, false}, {0, 2, false}, {1, 1, true}, {1, 2, false}, {1, 3, false}};
+    }else{
+        int const d = (mode == mode_backward) ? 1 : 0;
+        ops = {{d, 0, false}, {d, 1, false}, {d, 2, false}, {d, 3, false}};
+    }
+    auto executor_of = [](op const &o){ return (o.dir == 0) ? o.st - 1 : 3 - o.st; };
+    auto map_of = [&](op const &o, int w){ return static_cast<const char*>(P.maps) + sizeof(scatter_map) * static_cast<size_t>((o.dir * 4 + o.st) * 3 + w); };
+    // element size on the input / output side of executor e run in direction dir
+    auto bytes_of = [&](int e, int dir, bool output){
         if (tkind == kind_c2c) return cplx_bytes;
         if (tkind != kind_r2c) return real_bytes;
         if (e != 0) return cplx_bytes;
-        return (output != is_backward) ? cplx_bytes : real_bytes;   // r2c forward writes complex, c2r backward writes real
+        return (output != (dir == 1)) ? cplx_bytes : real_bytes;   // r2c forward writes complex, c2r backward writes real
     };
+    bool const last_is_backward = (ops.back().dir == 1);
+    int const in_unit = (mode == mode_backward) ? (complex_data ? cplx_bytes : real_bytes)
+                                                : ((tkind == kind_c2c) ? cplx_bytes : real_bytes);
+    bool const real_out = (tkind == kind_r2c and last_is_backward) or not complex_data;
+    int const out_unit = real_out ? real_bytes : cplx_bytes;
+    long long const in_entry = static_cast<long long>((mode == mode_backward) ? outbox_count : inbox_count) * in_unit;
+    long long const out_entry = static_cast<long long>(last_is_backward ? inbox_count : outbox_count) * out_unit;
+    long long const arena_entry = static_cast<long long>(P.entry_bytes);
 
-    // the last reshape can deliver my own part straight into the caller's array (not for the real output of a c2r transform
-    // that still has complex stages in the arena: there the arena element type differs only before stage 3, which is fine)
-    bool const direct_local = P.fused[dir][3] and std::getenv("HEFFTE_B200_NO_DIRECT_OUTPUT") == nullptr;
-    bool landed_direct = false;
+    pending.clear();
+    mark("start", 0, 0);
+    int rc = B200_SUCCESS;
     const void *cur = in;
+    long long cur_step = in_entry;
     int cur_buffer = -1;             // -1: caller memory
-    if (P.fused[dir][0]){
-        box3 const &box = is_backward ? lp.out_shape[3][me] : lp.in_shape[0][me];
-        int bytes = complex_data ? cplx_bytes : real_bytes;
-        if (tkind == kind_r2c and not is_backward) bytes = real_bytes;
-        if (not box.empty()){
-            rc = b200_scatter_copy(bytes, box.osize(0), box.osize(1), box.osize(2), box.osize(0), box.osize(0) * box.osize(1), cur, map_of(0, 0), cstream);
+    bool landed_direct = false;
+    int const last_fft_op = static_cast<int>(ops.size()) - 1;
+
+    for(size_t i=0; i<ops.size(); i++){
+        op const &o = ops[i];
+        bool const fused = P.fused[o.dir][o.st];
+        if (o.st == 0){
+            // ---- the first reshape of a transform: a scatter copy ------------------------------------------------------------
+            if (not fused) continue;
+            box3 const &box = (o.dir == 1) ? lp.out_shape[3][me] : lp.in_shape[0][me];
+            int bytes = complex_data ? cplx_bytes : real_bytes;
+            if (tkind == kind_r2c and o.dir == 0) bytes = real_bytes;
+            int const w = P.take();
+            if (not box.empty()){
+                rc = b200_scatter_copy_batch(bytes, box.osize(0), box.osize(1), box.osize(2), box.osize(0), box.osize(0) * box.osize(1), cur, map_of(o, w),
+                                             cstream, batch, cur_step, arena_entry, 0, 0);
+                if (rc) return rc;
+            }
+            mark("reshape0 (scatter copy)", batch * (2 * stage_elems[o.dir][0] - sent_elems[o.dir][0]) * bytes, batch * sent_elems[o.dir][0] * bytes);
+            rc = peer_fence(precision);
             if (rc) return rc;
+            mark("fence", 0, 0);
+            cur_buffer = w; cur = P.buffer(w); cur_step = arena_entry;
+            continue;
         }
-        mark("reshape0 (scatter copy)", (2 * stage_elems[dir][0] - sent_elems[dir][0]) * bytes, sent_elems[dir][0] * bytes);
-        rc = peer_fence(precision);
-        if (rc) return rc;
-        mark("fence", 0, 0);
-        cur_buffer = 0; cur = P.buffer(0);
-    }
-    for(int st=1; st<4; st++){
-        int const e = is_backward ? 3 - st : st - 1;
-        double const stage_scale = (st == last_fft) ? scale : 1.0;
+        int const e = executor_of(o);
+        int const direction = (o.dir == 1) ? B200_BACKWARD : B200_FORWARD;
+        // the scaling rides on ONE stage of the plan -- a global choice: a rank whose box is empty in that stage must not scale
+        // earlier, its data would be scaled again by the ranks that receive it.  Transforms: the last stage; operator: the product.
+        double const stage_scale = (mode == mode_convolve) ? (o.conv ? scale : 1.0) : ((static_cast<int>(i) == last_fft_op) ? scale : 1.0);
         bool const type_changes = (tkind == kind_r2c and e == 0);          // r2c / c2r cannot run in place
-        if (P.fused[dir][st]){
-            int const w = (cur_buffer < 0) ? 0 : (cur_buffer ^ 1);
-            if (touched & (1u << w)){ rc = peer_fence(precision); if (rc) return rc; touched = 0; }
-            const void *stage_map = map_of(st, w);
-            if (st == 3 and direct_local){
+        bool const is_last = (i + 1 == ops.size());
+        bool later_fused = false;
+        for(size_t t=i+1; t<ops.size(); t++) later_fused = later_fused or P.fused[ops[t].dir][ops[t].st];
+
+        if (fused){
+            int const w = P.take();
+            long long local_shift = 0, local_step = 0;
+            if (is_last and allow_direct){
                 // last stage: the part of my output that I produce myself goes straight into the caller's array (the cells of the
-                // map that point into my own arena are re-based); only what the other GPUs send lands in the arena
-                if (P.patched_out[dir] != out or P.patched_buffer[dir] != w){
-                    scatter_map patched = P.host_maps[(dir * 4 + 3) * 2 + w];
-                    long long const arena_base = static_cast<long long>(reinterpret_cast<intptr_t>(P.buffer(w)));
-                    const int *owner = P.owners.data() + static_cast<size_t>((dir * 4 + 3) * 2 + w) * scatter_max_cells;
-                    for(int c=0; c<patched.ncells; c++)
-                        if (owner[c] == me) patched.cell[c].base += static_cast<long long>(reinterpret_cast<intptr_t>(out)) - arena_base;
-                    char *slot = static_cast<char*>(P.maps) + sizeof(scatter_map) * static_cast<size_t>(16 + dir);
-                    if (cudaMemcpyAsync(slot, &patched, sizeof(scatter_map), cudaMemcpyHostToDevice, cstream) != cudaSuccess)
-                        return fail(B200_ERR_CUDA, "cudaMemcpyAsync failed (scatter map)");
-                    if (cudaStreamSynchronize(cstream) != cudaSuccess) return fail(B200_ERR_CUDA, "stream synchronisation failed");   // `patched` is a local
-                    P.patched_out[dir] = out; P.patched_buffer[dir] = w;
-                }
-                stage_map = static_cast<const char*>(P.maps) + sizeof(scatter_map) * static_cast<size_t>(16 + dir);
+                // map that stay in my own memory are re-based by the kernel); only what the other GPUs send lands in the arena
+                local_shift = static_cast<long long>(reinterpret_cast<intptr_t>(out)) - static_cast<long long>(reinterpret_cast<intptr_t>(P.buffer(w)));
+                local_step = out_entry - arena_entry;
                 landed_direct = true;
             }
+            if (trace) std::fprintf(stderr, "[b200 rank %d] stage (%d,%d) fused -> buffer %d\n", me, o.dir, o.st, w);
             if (X[e]){
-                rc = b200_fft1d_execute_scatter(X[e], direction, cur, stage_map, stage_scale, cstream);
+                if (o.conv){
+                    rc = b200_fft1d_execute_convolve(X[e], cur, nullptr, map_of(o, w), multiplier, stage_scale, cstream, batch, cur_step, 0, arena_entry, local_shift, local_step);
+                    if (rc == B200_ERR_UNSUPPORTED){
+                        // no operator kernel for this axis: transform in place, multiply, and let the backward kernel carry the reshape
+                        void *here = const_cast<void*>(cur);
+                        if (cur_buffer < 0) return fail(B200_ERR_UNSUPPORTED, "the fused spectral operator needs the plan's buffers");
+                        rc = b200_fft1d_execute_batch(X[e], B200_FORWARD, cur, here, 1.0, cstream, batch, cur_step, cur_step);
+                        for(int b=0; b<batch and rc == 0; b++)
+                            rc = b200_pointwise_multiply(precision, lp.out_shape[e][me].count(), static_cast<char*>(here) + b * cur_step, multiplier, stage_scale, cstream);
+                        if (rc == 0) rc = b200_fft1d_execute_scatter_batch(X[e], B200_BACKWARD, cur, map_of(o, w), 1.0, cstream, batch, cur_step, arena_entry, local_shift, local_step);
+                    }
+                }else{
+                    rc = b200_fft1d_execute_scatter_batch(X[e], direction, cur, map_of(o, w), stage_scale, cstream, batch, cur_step, arena_entry, local_shift, local_step);
+                }
                 if (rc) return rc;
             }
             {
                 char label[40];
-                std::snprintf(label, sizeof(label), "fft%d + reshape%d (fused)", e, is_backward ? st : st);
-                long long const read_bytes = X[e] ? static_cast<long long>(is_backward ? lp.out_shape[e][me].count() : lp.out_shape[e][me].count()) * bytes_of(e, false) : 0;
-                long long const wrote = stage_elems[dir][st] * bytes_of(e, true), sent = sent_elems[dir][st] * bytes_of(e, true);
-                mark(label, read_bytes + wrote - sent, sent);
+                std::snprintf(label, sizeof(label), o.conv ? "fft%d * ifft%d + reshape%d (fused)" : "fft%d + reshape%d (fused)", e, o.conv ? e : o.st, o.st);
+                long long const read_bytes = X[e] ? static_cast<long long>(lp.out_shape[e][me].count()) * bytes_of(e, o.dir, false) : 0;
+                long long const wrote = stage_elems[o.dir][o.st] * bytes_of(e, o.dir, true), sent = sent_elems[o.dir][o.st] * bytes_of(e, o.dir, true);
+                mark(label, batch * (read_bytes + wrote - sent), batch * sent);
             }
             rc = peer_fence(precision);
             if (rc) return rc;
             mark("fence", 0, 0);
-            touched = 0;
-            cur_buffer = w; cur = P.buffer(w);
-        }else{
-            bool later_fused = false;
-            for(int t=st+1; t<4; t++) later_fused = later_fused or P.fused[dir][t];
-            void *dst;
-            int dst_buffer;
-            // the caller's output can take the result once nothing moves any more -- except the complex intermediates of a
-            // complex-to-real transform, which do not fit the real output array
-            bool const fits_output = not (tkind == kind_r2c and is_backward and st < 3);
-            if (not later_fused and fits_output){ dst = out; dst_buffer = -1; }
-            else if (cur_buffer >= 0 and not type_changes){ dst = const_cast<void*>(cur); dst_buffer = cur_buffer; }
-            else{ dst_buffer = (cur_buffer < 0) ? 0 : (cur_buffer ^ 1); dst = P.buffer(dst_buffer); }
-            if (cur_buffer >= 0) touched |= 1u << cur_buffer;
-            if (dst_buffer >= 0) touched |= 1u << dst_buffer;
-            if (X[e]){
-                rc = b200_fft1d_execute(X[e], direction, cur, dst, stage_scale, cstream);
-                if (rc) return rc;
-            }
-            {   // the mark is emitted on every rank, also with an empty box: all ranks report the same list of stages
-                char label[40];
-                std::snprintf(label, sizeof(label), "fft%d (local)", e);
-                long long const count = X[e] ? lp.out_shape[e][me].count() : 0;
-                long long const out_count = (tkind == kind_r2c and e == 0) ? (is_backward ? count : (X[e] ? lp.in_shape[1][me].count() : 0)) : count;
-                long long const in_count = (tkind == kind_r2c and e == 0 and is_backward) ? (X[e] ? lp.in_shape[1][me].count() : 0) : count;
-                mark(label, in_count * bytes_of(e, false) + out_count * bytes_of(e, true), 0);
-            }
-            cur = dst; cur_buffer = dst_buffer;     // also without a transform (empty box): every rank follows the same buffers
+            cur_buffer = w; cur = P.buffer(w); cur_step = arena_entry;
+            continue;
         }
+
+        // ---- a stage without data movement --------------------------------------------------------------------------------------
+        void *dst;
+        int dst_buffer;
+        long long dst_step;
+        // the caller's output can take the result once nothing moves any more -- except the complex intermediates of a
+        // complex-to-real transform, which do not fit the real output array
+        bool const fits_output = not (tkind == kind_r2c and last_is_backward and not is_last);
+        if (not later_fused and fits_output){ dst = out; dst_buffer = -1; dst_step = out_entry; }
+        else if (cur_buffer >= 0 and not type_changes){ dst = const_cast<void*>(cur); dst_buffer = cur_buffer; dst_step = cur_step; }
+        else{ dst_buffer = P.take(); dst = P.buffer(dst_buffer); dst_step = arena_entry; }
+
+        // followed by a fused stage of the same box: both in one persistent launch, this one hidden behind the transfers of the next
+        bool paired = false;
+        if (allow_pair and not o.conv and i + 1 < ops.size() and tkind == kind_c2c and X[e]){
+            op const &next = ops[i + 1];
+            int const e2 = executor_of(next);
+            if (P.fused[next.dir][next.st] and not next.conv and next.dir == o.dir and X[e2] and b200_fft1d_pairable(X[e], X[e2])){
+                box3 const &box = lp.out_shape[e][me];
+                void *planes = pair_counters(static_cast<size_t>(box.osize(2)) * batch);
+                if (planes != nullptr){
+                    bool const next_last = (i + 2 == ops.size());
+                    int const w = P.take();
+                    long long local_shift = 0, local_step = 0;
+                    if (next_last and allow_direct){
+                        local_shift = static_cast<long long>(reinterpret_cast<intptr_t>(out)) - static_cast<long long>(reinterpret_cast<intptr_t>(P.buffer(w)));
+                        local_step = out_entry - arena_entry;
+                    }
+                    double const next_scale = (mode != mode_convolve and static_cast<int>(i + 1) == last_fft_op) ? scale : 1.0;
+                    rc = b200_fft1d_execute_pair(X[e], X[e2], direction, cur, dst, map_of(next, w), next_scale, planes, 0, cstream,
+                                                 batch, cur_step, dst_step, arena_entry, local_shift, local_step);
+                    if (rc == B200_SUCCESS){
+                        paired = true;
+                        if (next_last and allow_direct) landed_direct = true;
+                        char label[40];
+                        std::snprintf(label, sizeof(label), "fft%d + fft%d + reshape%d (paired)", e, e2, next.st);
+                        long long const count = box.count();
+                        long long const wrote = stage_elems[next.dir][next.st] * cplx_bytes, sent = sent_elems[next.dir][next.st] * cplx_bytes;
+                        mark(label, batch * (3 * count * cplx_bytes + wrote - sent), batch * sent);
+                        rc = peer_fence(precision);
+                        if (rc) return rc;
+                        mark("fence", 0, 0);
+                        cur_buffer = w; cur = P.buffer(w); cur_step = arena_entry;
+                        i++;                     // the fused stage is done
+                    }else if (rc != B200_ERR_UNSUPPORTED) return rc;
+                    else P.next_buffer = w;      // not taken after all: the rotation stays in step with the other ranks
+                }
+            }
+        }
+        if (paired) continue;
+
+        if (X[e]){
+            if (o.conv){
+                rc = b200_fft1d_execute_convolve(X[e], cur, dst, nullptr, multiplier, stage_scale, cstream, batch, cur_step, dst_step, 0, 0, 0);
+                if (rc == B200_ERR_UNSUPPORTED){
+                    rc = b200_fft1d_execute_batch(X[e], B200_FORWARD, cur, dst, 1.0, cstream, batch, cur_step, dst_step);
+                    for(int b=0; b<batch and rc == 0; b++)
+                        rc = b200_pointwise_multiply(precision, lp.out_shape[e][me].count(), static_cast<char*>(dst) + b * dst_step, multiplier, stage_scale, cstream);
+                    if (rc == 0) rc = b200_fft1d_execute_batch(X[e], B200_BACKWARD, dst, dst, 1.0, cstream, batch, dst_step, dst_step);
+                }
+            }else{
+                rc = b200_fft1d_execute_batch(X[e], direction, cur, dst, stage_scale, cstream, batch, cur_step, dst_step);
+            }
+            if (rc) return rc;
+        }
+        {   // the mark is emitted on every rank, also with an empty box: all ranks report the same list of stages
+            char label[40];
+            std::snprintf(label, sizeof(label), o.conv ? "fft%d * ifft%d (local)" : "fft%d (local)", e, e);
+            long long const count = X[e] ? lp.out_shape[e][me].count() : 0;
+            long long const half = X[e] ? lp.in_shape[1][me].count() : 0;
+            long long const out_count = (tkind == kind_r2c and e == 0) ? ((o.dir == 1) ? count : half) : count;
+            long long const in_count = (tkind == kind_r2c and e == 0 and o.dir == 1) ? half : count;
+            mark(label, batch * (in_count * bytes_of(e, o.dir, false) + out_count * bytes_of(e, o.dir, true)), 0);
+        }
+        cur = dst; cur_buffer = dst_buffer; cur_step = dst_step;     // also without a transform (empty box): every rank follows the same buffers
     }
+
     if (cur != out and landed_direct){
-        // what the other GPUs sent sits in the arena at its final position inside my box: move those sub-boxes only
-        bool const real_out = (tkind == kind_r2c and is_backward) or not complex_data;
-        int const elem = real_out ? real_bytes : cplx_bytes;
-        shape const &from = is_backward ? lp.out_shape[0] : lp.in_shape[3];
-        box3 const &mine = is_backward ? lp.in_shape[0][me] : lp.out_shape[3][me];
+        // what the other GPUs sent sits in the arena at its final position inside my box: move those sub-boxes only, all of
+        // them and all batch entries in one launch
+        shape const &from = last_is_backward ? lp.out_shape[0] : lp.in_shape[3];
+        box3 const &mine = last_is_backward ? lp.in_shape[0][me] : lp.out_shape[3][me];
+        std::vector<long long> offsets, nf, nm, ns;
         long long moved = 0;
         for(int r=0; r<ccomm->size() and not mine.empty(); r++){
             if (r == me) continue;
             box3 const piece = mine.overlap(from[r]);
             if (piece.empty()) continue;
-            idx const offset = mine.offset_of(piece.low);
-            rc = b200_copy_subbox(elem, piece.osize(0), piece.osize(1), piece.osize(2), mine.osize(0), mine.osize(0) * mine.osize(1),
-                                  mine.osize(0), mine.osize(0) * mine.osize(1), advance(cur, offset, elem), advance(out, offset, elem), cstream);
-            if (rc) return rc;
+            offsets.push_back(mine.offset_of(piece.low));
+            nf.push_back(piece.osize(0)); nm.push_back(piece.osize(1)); ns.push_back(piece.osize(2));
             moved += piece.count();
         }
-        mark("received sub-boxes to the caller's array", 2 * moved * elem, 0);
+        if (not offsets.empty()){
+            rc = b200_copy_subboxes(out_unit, static_cast<int>(offsets.size()), offsets.data(), nf.data(), nm.data(), ns.data(),
+                                    mine.osize(0), mine.osize(0) * mine.osize(1), cur, out, cstream, batch, cur_step, out_entry);
+            if (rc) return rc;
+        }
+        mark("received sub-boxes to the caller's array", batch * 2 * moved * out_unit, 0);
     }else if (cur != out){
-        idx const count = is_backward ? inbox_count : outbox_count;
-        bool const real_out = (tkind == kind_r2c and is_backward) or not complex_data;
-        size_t const bytes = static_cast<size_t>(count) * (real_out ? real_bytes : cplx_bytes);
-        if (count > 0 and cudaMemcpyAsync(out, cur, bytes, cudaMemcpyDeviceToDevice, cstream) != cudaSuccess)
-            return fail(B200_ERR_CUDA, "cudaMemcpyAsync failed");
-        mark("copy to the caller's array", 2 * static_cast<long long>(bytes), 0);
+        idx const count = last_is_backward ? inbox_count : outbox_count;
+        size_t const bytes = static_cast<size_t>(count) * out_unit;
+        for(int b=0; b<batch; b++)
+            if (count > 0 and cudaMemcpyAsync(static_cast<char*>(out) + b * out_entry, static_cast<const char*>(cur) + b * cur_step, bytes, cudaMemcpyDeviceToDevice, cstream) != cudaSuccess)
+                return fail(B200_ERR_CUDA, "cudaMemcpyAsync failed");
+        mark("copy to the caller's array", batch * 2 * static_cast<long long>(bytes), 0);
+    }
+    return B200_SUCCESS;
+}
+
+// every stage of the plan is local to this rank (one rank, or boxes that never move): the batched launches need no arena
+bool transform3d::all_local() const {
+    for(int i=0; i<4; i++) if (fwd[i] or bwd[i]) return false;
+    return true;
+}
+
+// Transforms without any data movement: three batched launches (grid.y = entries), in place where the types allow.  The fused
+// spectral operator runs the last forward and the first backward transform in one kernel; single precision pairs the two
+// transforms of the fast axes through the L2 cache (fft_pair_kernel, tools/kbench_pair.cu).
+int transform3d::run_local(int precision, int mode, int batch, const void *in, void *out, double scale, const void *multiplier){
+    int const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
+    int const cplx_bytes = 2 * real_bytes;
+    bool const complex_data = (tkind == kind_c2c or tkind == kind_r2c);
+    b200_fft1d_plan const *X = exec[precision];
+    // pairing two local transforms through the L2 cache pays for small planes only (tools/kbench_pair.cu: 256^3 fp32 -19 %,
+    // 512^3 fp64 +22 %) and not at all once the L2 is cold between transforms: opt-in
+    static bool const allow_pair = (std::getenv("HEFFTE_B200_PAIR_LOCAL") != nullptr);
+    bool const backward = (mode == mode_backward);
+    long long const spatial_entry = static_cast<long long>(inbox_count) * ((tkind == kind_c2c) ? cplx_bytes : real_bytes);
+    long long const spectral_entry = static_cast<long long>(outbox_count) * (complex_data ? cplx_bytes : real_bytes);
+    long long const in_entry = backward ? spectral_entry : spatial_entry;
+    long long const out_entry = (mode == mode_forward) ? spectral_entry : spatial_entry;
+    int order[6], dirs[6], count = 0;
+    if (mode == mode_forward){ for(int e=0; e<3; e++){ order[count] = e; dirs[count++] = B200_FORWARD; } }
+    else if (mode == mode_backward){ for(int e=2; e>=0; e--){ order[count] = e; dirs[count++] = B200_BACKWARD; } }
+    else{ order[0] = 0; order[1] = 1; order[2] = 2; order[3] = 1; order[4] = 0; dirs[0] = dirs[1] = B200_FORWARD; dirs[2] = 2; dirs[3] = dirs[4] = B200_BACKWARD; count = 5; }
+    const void *cur = in;
+    long long cur_step = in_entry;
+    int rc = B200_SUCCESS;
+    for(int i=0; i<count; i++){
+        int const e = order[i];
+        if (not X[e]) continue;
+        bool const last = (i == count - 1);
+        double const s = (mode == mode_convolve) ? ((dirs[i] == 2) ? scale : 1.0) : (last ? scale : 1.0);
+        // r2c: the first transform changes the element type, so it writes straight into the output array; everything else in place
+        void *dst = out;
+        long long dst_step = out_entry;
+        if (tkind == kind_r2c and backward and e != 0){
+            // complex intermediates of a complex-to-real transform do not fit the real output: they stay in the plan's workspace
+            void *scratch = ensure_workspace(precision, batch);
+            if (scratch == nullptr) return fail(B200_ERR_CUDA, "cannot allocate the workspace");
+            dst = scratch; dst_step = spectral_entry;
+        }
+        if (dirs[i] == 2){
+            rc = b200_fft1d_execute_convolve(X[e], cur, dst, nullptr, multiplier, s, cstream, batch, cur_step, dst_step, 0, 0, 0);
+            if (rc == B200_ERR_UNSUPPORTED){
+                rc = b200_fft1d_execute_batch(X[e], B200_FORWARD, cur, dst, 1.0, cstream, batch, cur_step, dst_step);
+                for(int b=0; b<batch and rc == 0; b++)
+                    rc = b200_pointwise_multiply(precision, lp.out_shape[e][me].count(), static_cast<char*>(dst) + b * dst_step, multiplier, s, cstream);
+                if (rc == 0) rc = b200_fft1d_execute_batch(X[e], B200_BACKWARD, dst, dst, 1.0, cstream, batch, dst_step, dst_step);
+            }
+        }else if (allow_pair and precision == B200_PREC_FLOAT and i + 1 < count and dirs[i + 1] == dirs[i] and X[order[i + 1]] and
+                  b200_fft1d_pairable(X[e], X[order[i + 1]]) and pair_counters(static_cast<size_t>(lp.out_shape[e][me].osize(2)) * batch) != nullptr){
+            bool const next_last = (i + 1 == count - 1);
+            double const s2 = (mode == mode_convolve) ? 1.0 : (next_last ? scale : 1.0);
+            rc = b200_fft1d_execute_pair(X[e], X[order[i + 1]], dirs[i], cur, dst, nullptr, s2, counters, 0, cstream, batch, cur_step, dst_step, 0, 0, 0);
+            if (rc == B200_SUCCESS) i++;
+            else if (rc == B200_ERR_UNSUPPORTED) rc = b200_fft1d_execute_batch(X[e], dirs[i], cur, dst, s, cstream, batch, cur_step, dst_step);
+        }else{
+            rc = b200_fft1d_execute_batch(X[e], dirs[i], cur, dst, s, cstream, batch, cur_step, dst_step);
+        }
+        if (rc) return rc;
+        cur = dst; cur_step = dst_step;
+    }
+    if (cur != out){
+        // nothing ran (empty box) or the data stopped in the scratch array: the output is what the input was
+        idx const n = (mode == mode_forward) ? outbox_count : inbox_count;
+        if (n > 0 and cur == in and in != out){
+            for(int b=0; b<batch; b++)
+                if (cudaMemcpyAsync(static_cast<char*>(out) + b * out_entry, static_cast<const char*>(in) + b * in_entry,
+                                    static_cast<size_t>(std::min(in_entry, out_entry)), cudaMemcpyDeviceToDevice, cstream) != cudaSuccess)
+                    return fail(B200_ERR_CUDA, "cudaMemcpyAsync failed");
+        }
     }
     return B200_SUCCESS;
 }
@@ -612,20 +801,23 @@ void* transform3d::ensure_workspace(int precision, int batch){
 int transform3d::forward(int precision, int batch, const void *in, void *out, void *workspace, int scaling){
     if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
     if (ccomm->size() > 1 and b200_peer_timed_out()) return fail(B200_ERR_PEER, "a peer GPU did not reach a barrier within HEFFTE_B200_BARRIER_TIMEOUT_S");
+    batch = std::max(batch, 1);
     int rc = ensure_executors(precision);
     if (rc) return rc;
-    bool const through_peers = ensure_peer(precision);
-    if ((workspace == nullptr or exec_workspace_count > workspace_count) and not through_peers){
+    if (all_local()) return run_local(precision, mode_forward, batch, in, out, scale_factor(scaling), nullptr);
+    if (ensure_peer(precision, batch)) return run_peer(precision, mode_forward, batch, in, out, scale_factor(scaling), nullptr);
+    // the exchange path: pack -> exchange() -> unpack, entry by entry
+    if (workspace == nullptr or exec_workspace_count > workspace_count){
         workspace = ensure_workspace(precision, 1);
         if (workspace == nullptr) return fail(B200_ERR_CUDA, "cannot allocate the workspace");
     }
     size_t const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
     size_t const in_unit = (tkind == kind_c2c) ? 2 * real_bytes : real_bytes;
     size_t const out_unit = (tkind == kind_c2c or tkind == kind_r2c) ? 2 * real_bytes : real_bytes;
-    for(int b=0; b<std::max(batch, 1); b++){
+    for(int b=0; b<batch; b++){
         const char *src = static_cast<const char*>(in) + b * inbox_count * in_unit;
         char *dst = static_cast<char*>(out) + b * outbox_count * out_unit;
-        rc = through_peers ? run_peer(precision, false, src, dst, scale_factor(scaling)) : run(precision, false, src, dst, workspace, scale_factor(scaling));
+        rc = run(precision, false, src, dst, workspace, scale_factor(scaling));
         if (rc) return rc;
     }
     return B200_SUCCESS;
@@ -634,23 +826,53 @@ int transform3d::forward(int precision, int batch, const void *in, void *out, vo
 int transform3d::backward(int precision, int batch, const void *in, void *out, void *workspace, int scaling){
     if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
     if (ccomm->size() > 1 and b200_peer_timed_out()) return fail(B200_ERR_PEER, "a peer GPU did not reach a barrier within HEFFTE_B200_BARRIER_TIMEOUT_S");
+    batch = std::max(batch, 1);
     int rc = ensure_executors(precision);
     if (rc) return rc;
-    bool const through_peers = ensure_peer(precision);
-    if ((workspace == nullptr or exec_workspace_count > workspace_count) and not through_peers){
+    if (all_local()) return run_local(precision, mode_backward, batch, in, out, scale_factor(scaling), nullptr);
+    if (ensure_peer(precision, batch)) return run_peer(precision, mode_backward, batch, in, out, scale_factor(scaling), nullptr);
+    if (workspace == nullptr or exec_workspace_count > workspace_count){
         workspace = ensure_workspace(precision, 1);
         if (workspace == nullptr) return fail(B200_ERR_CUDA, "cannot allocate the workspace");
     }
     size_t const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
     size_t const in_unit = (tkind == kind_c2c or tkind == kind_r2c) ? 2 * real_bytes : real_bytes;
     size_t const out_unit = (tkind == kind_c2c) ? 2 * real_bytes : real_bytes;
-    for(int b=0; b<std::max(batch, 1); b++){
+    for(int b=0; b<batch; b++){
         const char *src = static_cast<const char*>(in) + b * outbox_count * in_unit;
         char *dst = static_cast<char*>(out) + b * inbox_count * out_unit;
-        rc = through_peers ? run_peer(precision, true, src, dst, scale_factor(scaling)) : run(precision, true, src, dst, workspace, scale_factor(scaling));
+        rc = run(precision, true, src, dst, workspace, scale_factor(scaling));
         if (rc) return rc;
     }
     return B200_SUCCESS;
+}
+
+// forward(in) with `scaling`, times itself or times `multiplier` (an array over convolve_box()), backward -- complex plans whose
+// inbox and outbox hold the same number of entries (the result comes back in the layout of the input)
+int transform3d::convolve(int precision, const void *in, void *out, void *workspace, const void *multiplier, int scaling){
+    if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
+    if (tkind != kind_c2c) return fail(B200_ERR_UNSUPPORTED, "the spectral operator is defined for complex-to-complex plans");
+    if (ccomm->size() > 1 and b200_peer_timed_out()) return fail(B200_ERR_PEER, "a peer GPU did not reach a barrier within HEFFTE_B200_BARRIER_TIMEOUT_S");
+    int rc = ensure_executors(precision);
+    if (rc) return rc;
+    if (all_local()) return run_local(precision, mode_convolve, 1, in, out, scale_factor(scaling), multiplier);
+    if (ensure_peer(precision, 1)) return run_peer(precision, mode_convolve, 1, in, out, scale_factor(scaling), multiplier);
+    // the exchange path has no fused form: forward into the plan's scratch, product, backward.  The multiplier is laid out over
+    // convolve_box(), which the unfused forward transform does not produce, so only the self-product is available here.
+    if (multiplier != nullptr) return fail(B200_ERR_UNSUPPORTED, "a caller multiplier needs the peer-memory or the single-rank path");
+    size_t const cplx_bytes = (precision == B200_PREC_FLOAT) ? 8 : 16;
+    if (workspace == nullptr or exec_workspace_count > workspace_count){
+        workspace = ensure_workspace(precision, 1);
+        if (workspace == nullptr) return fail(B200_ERR_CUDA, "cannot allocate the workspace");
+    }
+    void *spectrum = nullptr;
+    if (cudaMalloc(&spectrum, std::max<size_t>(static_cast<size_t>(outbox_count), 1) * cplx_bytes) != cudaSuccess) return fail(B200_ERR_CUDA, "cannot allocate the spectrum");
+    rc = run(precision, false, in, spectrum, workspace, 1.0);
+    if (rc == 0) rc = b200_pointwise_multiply(precision, outbox_count, spectrum, nullptr, scale_factor(scaling), cstream);
+    if (rc == 0) rc = run(precision, true, spectrum, out, workspace, 1.0);
+    cudaStreamSynchronize(cstream);
+    cudaFree(spectrum);
+    return rc;
 }
 
 int transform3d::run(int precision, bool is_backward, const void *in, void *out, void *workspace, double scale){

@@ -76,6 +76,15 @@ public:
     // precision B200_PREC_*; workspace may be null (a plan-owned buffer is used); scaling 0 none / 1 full / 2 symmetric
     int forward(int precision, int batch, const void *in, void *out, void *workspace, int scaling);
     int backward(int precision, int batch, const void *in, void *out, void *workspace, int scaling);
+    // Fused spectral operator (reference benchmarks/convolution.cpp:86-97: forward(scale), pointwise product, backward), complex
+    // plans only: out = backward( forward(in) * factor * M ) with M = the spectrum itself (multiplier == null: x *= x, the
+    // benchmark's operator) or a caller array laid out in convolve_box().  The two brick reshapes around the product are elided
+    // and the last forward transform, the product and the first backward transform run in ONE kernel where the plan allows.
+    int convolve(int precision, const void *in, void *out, void *workspace, const void *multiplier, int scaling);
+    // the box (of the plan's last forward stage) in which this rank provides / sees the spectrum during convolve()
+    box3 convolve_box() const { return lp.out_shape[2][me]; }
+    // collective: set up the peer-memory data plane for `batch` entries ahead of the first transform (else done lazily there)
+    int prepare(int precision, int batch);
 
     // per-stage device timing of the most recent transform (peer-memory mode): enable, run, synchronise, collect
     struct stage_record { char name[40]; double ms; long long local_bytes; long long sent_bytes; };
@@ -86,30 +95,34 @@ public:
     bool uses_peer_memory(int precision) const { return peer[precision].active; }
 
 private:
+    enum run_mode { mode_forward = 0, mode_backward = 1, mode_convolve = 2 };
     int run(int precision, bool is_backward, const void *in, void *out, void *workspace, double scale);
-    int run_peer(int precision, bool is_backward, const void *in, void *out, double scale);
+    int run_local(int precision, int mode, int batch, const void *in, void *out, double scale, const void *multiplier);
+    int run_peer(int precision, int mode, int batch, const void *in, void *out, double scale, const void *multiplier);
     int ensure_executors(int precision);
     void* ensure_workspace(int precision, int batch);
-    bool ensure_peer(int precision);
+    bool ensure_peer(int precision, int batch);
+    void release_peer(int precision);
     int peer_fence(int precision);
+    void* pair_counters(size_t count);
+    bool all_local() const;
 
     // ---- peer-memory mode: every reshape is fused into the store of the transform in front of it --------------------------
     // (stage 0 = the first reshape, a scatter copy; stage s = 1..3: transform s-1 followed by reshape s)
     struct peer_state {
         bool tried = false, active = false;
-        void *arena = nullptr;                 // [flags | buffer 0 | buffer 1], peer-mapped on every rank of the plan
-        size_t buffer_bytes = 0;
+        void *arena = nullptr;                 // [flags | buffer 0 | buffer 1 | buffer 2], peer-mapped on every rank of the plan
+        size_t entry_bytes = 0;                // room of one batch entry inside a buffer: the largest box of the plan
+        int capacity = 0;                      // batch entries a buffer holds
+        size_t buffer_bytes = 0;               // entry_bytes * capacity
         std::vector<void*> arenas;             // address of every rank's arena as seen from this device
         std::vector<void*> remote_slots;       // my slot in every rank's flag array
         unsigned long long epoch = 0;
-        void *maps = nullptr;                  // device array of scatter maps, index ((direction * 4 + stage) * 2 + buffer); two more
-                                               // entries (16 + direction) hold the last stage's map patched for the caller's array
-        std::vector<scatter_map> host_maps;    // host copy of the 16 plan-time maps
-        std::vector<int> owners;               // rank every cell of those maps lands on (16 x scatter_max_cells)
-        void *patched_out[2] = {nullptr, nullptr};   // caller array the patched map of that direction points to
-        int patched_buffer[2] = {-1, -1};
+        void *maps = nullptr;                  // device array of scatter maps, index ((direction * 4 + stage) * 3 + buffer)
+        int next_buffer = 0;                   // the three buffers rotate: every remote write targets the buffer after the last one used
         bool fused[2][4] = {{false, false, false, false}, {false, false, false, false}};   // reshape of that stage moves data (global fact)
         char* buffer(int index) const { return static_cast<char*>(arena) + 4096 + static_cast<size_t>(index) * buffer_bytes; }
+        int take(){ int const w = next_buffer; next_buffer = (next_buffer + 1) % 3; return w; }
     };
     peer_state peer[2];
     long long sent_elems[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};     // elements that leave this GPU in stage (direction, st)
@@ -118,6 +131,8 @@ private:
     std::vector<cudaEvent_t> marks;
     std::vector<stage_record> pending;
     void mark(const char *name, long long local_bytes, long long sent_bytes);
+    void *counters = nullptr;           // per-plane counters of the paired kernel
+    size_t counters_count = 0;
 
     transform_kind tkind;
     int r2c_dir;

@@ -386,6 +386,47 @@ class heffte_fft_plan:
         if rc != 0:
             raise heffte_input_error("heFFTe(b200) transform failed with code %d: %s" % (rc, _lib.last_error()))
 
+    def convolve(self, inarray, outarray, multiplier=None, scaling=scale.full):
+        """
+        Fused spectral operator of a complex-to-complex plan: outarray = backward(forward(inarray) * factor(scaling) * M), M = the
+        spectrum itself (multiplier None: the x[i] *= x[i] of the reference's benchmarks/convolution.cpp:86-97) or a device array
+        laid out over convolve_box().  One plan-level call: the reshapes around the product are not executed.
+        """
+        self.convolve_buffered(inarray, outarray, None, multiplier, scaling)
+
+    def convolve_buffered(self, inarray, outarray, workspace, multiplier=None, scaling=scale.full):
+        if self.backend_tag != backend.b200 or self.use_r2c:
+            raise heffte_input_error("convolve() is defined for complex-to-complex plans")
+        if not (_is_torch(inarray) and _is_torch(outarray)) and not (not _is_torch(inarray) and not _is_torch(outarray)):
+            raise heffte_input_error("input and output must both be torch CUDA tensors or both be numpy arrays")
+        if _dtype_name(inarray) not in _DTYPE_INFO or _dtype_name(inarray) != _dtype_name(outarray) or not _DTYPE_INFO[_dtype_name(inarray)][1]:
+            raise heffte_input_error("convolve() works on complex64 or complex128 arrays of one type")
+        if _numel(inarray) != self.size_inbox() or _numel(outarray) != self.size_inbox():
+            raise heffte_input_error("convolve() called with invalid array size")
+        if _is_torch(inarray) and not (inarray.is_contiguous() and outarray.is_contiguous()):
+            raise heffte_input_error("torch tensors must be contiguous")
+        if multiplier is not None:
+            lo, hi, _ = self.convolve_box()
+            count = max(0, hi[0] - lo[0] + 1) * max(0, hi[1] - lo[1] + 1) * max(0, hi[2] - lo[2] + 1)
+            if _numel(multiplier) != count or _dtype_name(multiplier) != _dtype_name(inarray):
+                raise heffte_input_error("the multiplier covers convolve_box() with the type of the data")
+        precision = _DTYPE_INFO[_dtype_name(inarray)][0]
+        rc = _lib.load().heffte_convolve(self.plan, precision, self._ptr(inarray), self._ptr(outarray), self._ptr(workspace), self._ptr(multiplier), scaling)
+        if rc != 0:
+            raise heffte_input_error("heFFTe(b200) convolve failed with code %d: %s" % (rc, _lib.last_error()))
+
+    def convolve_box(self):
+        """(low, high, order) of this rank's part of the spectrum while convolve() applies the multiplier"""
+        low, high, order = (ctypes.c_longlong * 3)(), (ctypes.c_longlong * 3)(), (ctypes.c_int * 3)()
+        _lib.load().heffte_convolve_box(self.plan, low, high, order)
+        return [int(v) for v in low], [int(v) for v in high], [int(v) for v in order]
+
+    def prepare(self, precision=1, batch=1):
+        """collective: set up the peer-memory data plane for transforms of up to `batch` entries ahead of the first transform"""
+        rc = _lib.load().heffte_b200_prepare(self.plan, precision, batch)
+        if rc != 0:
+            raise heffte_input_error("heFFTe(b200) prepare failed with code %d: %s" % (rc, _lib.last_error()))
+
     def forward(self, inarray, outarray, scaling=scale.none, batch=1):
         self._run(True, inarray, outarray, None, scaling, batch)
 

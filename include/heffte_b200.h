@@ -148,6 +148,20 @@ void heffte_backward_d2d_buffered(heffte_plan const plan, double const *input, d
 /* generic entry used by the C++ header and the Python binding: precision B200_PREC_*, direction B200_FORWARD/BACKWARD,
  * batch >= 1 (C++ API forward(batch, ...), include/heffte_fft3d.h:391-414); returns an error code instead of void */
 int heffte_execute(heffte_plan const plan, int precision, int direction, int batch, void const *input, void *output, void *workspace, int scale);
+/*
+ * Fused spectral operator (the caller pattern of the reference's benchmarks/convolution.cpp:86-97 -- forward(scale), pointwise
+ * product, backward -- as ONE plan-level call, complex-to-complex plans):  output = backward( forward(input) * factor(scale) * M ),
+ * M = the spectrum itself when multiplier == NULL (the benchmark's x[i] *= x[i]) or a device array laid out over the box
+ * returned by heffte_convolve_box() (this rank's part of the spectrum in the plan's last forward stage, pencils along one axis).
+ * The two brick reshapes around the product are not executed and the last forward transform, the product and the first
+ * backward transform run in one kernel where the axis allows; the result comes back in the layout of the input box.
+ */
+int heffte_convolve(heffte_plan const plan, int precision, void const *input, void *output, void *workspace, void const *multiplier, int scale);
+int heffte_convolve_box(heffte_plan const plan, long long low[3], long long high[3], int order[3]);
+/* COLLECTIVE over the ranks of the plan: sets up the peer-memory data plane (arena of 3 x batch boxes, peer mapping, scatter maps)
+ * for transforms of up to `batch` entries ahead of time.  Without it the first transform of each precision -- and the first one
+ * with a larger batch -- does it: that call then blocks the host and must be entered by every rank with the same precision. */
+int heffte_b200_prepare(heffte_plan const plan, int precision, int batch);
 /* same through pinned host staging: copies input host->device, transforms, copies the result device->host, synchronises */
 int heffte_execute_host(heffte_plan const plan, int precision, int direction, int batch, void const *host_input, void *host_output, int scale);
 /* 1 when the plan moves data between ranks through peer memory (NVLink stores fused into the FFT kernels), 0 when it uses

@@ -109,6 +109,40 @@ int b200_fft1d_execute_range(b200_fft1d_plan plan, int direction, const void *in
  * (reference src/heffte_reshape3d.cpp:365-443, include/heffte_backend_cuda.h:494-524, 800-829).
  */
 int b200_fft1d_execute_scatter(b200_fft1d_plan plan, int direction, const void *in, const void *device_scatter_map, double scale, void *stream);
+/* Batched variants (reference include/heffte_fft3d.h:391-414: forward(batch, ...)): `batch` entries in ONE launch.  Entry e reads
+ * in + e * in_step bytes and writes out + e * out_step bytes; with a fused reshape it adds e * scatter_step bytes to every
+ * destination and local_shift + e * local_step bytes more to the destinations that lie in this rank's own memory (that is how
+ * the last stage of a plan lands its own part straight in the caller's array). */
+int b200_fft1d_execute_batch(b200_fft1d_plan plan, int direction, const void *in, void *out, double scale, void *stream,
+                             int batch, long long in_step, long long out_step);
+int b200_fft1d_execute_scatter_batch(b200_fft1d_plan plan, int direction, const void *in, const void *device_scatter_map, double scale, void *stream,
+                                     int batch, long long in_step, long long scatter_step, long long local_shift, long long local_step);
+/*
+ * TWO consecutive transforms of the same box -- one along the contiguous axis, one along the middle axis -- in ONE persistent
+ * launch, plane by plane: the second finds the output of the first in the L2 cache, and when it carries a fused reshape
+ * (device_scatter_map != NULL) the first, purely local pass hides behind the NVLink-bound stores of the second.
+ * first: in -> mid (may alias); second: mid -> the scatter map, or in place when the map is NULL; `scale` rides on the second.
+ * counters: device memory of batch * (extent of the slowest axis) unsigned ints (zeroed by the call); lag: planes between the
+ * two fronts (<= 0: default).  Returns B200_ERR_UNSUPPORTED -- without an error text -- when the two plans have no paired
+ * kernel (b200_fft1d_pairable() == 0): run them one after the other instead.
+ */
+int b200_fft1d_pairable(b200_fft1d_plan first, b200_fft1d_plan second);
+int b200_fft1d_execute_pair(b200_fft1d_plan first, b200_fft1d_plan second, int direction, const void *in, void *mid,
+                            const void *device_scatter_map, double scale, void *counters, int lag, void *stream,
+                            int batch, long long in_step, long long mid_step, long long scatter_step, long long local_shift, long long local_step);
+/*
+ * Fused spectral operator along the axis of the plan: forward transform, spectrum * scale * M, backward transform of every line
+ * in ONE pass over memory, M = the spectrum itself (multiplier == NULL, the x[i] *= x[i] of the reference's
+ * benchmarks/convolution.cpp:89-94) or a device array with the layout of the input box.  The result goes to `out` (may alias
+ * `in`) or, with a scatter map, through the fused reshape of a backward stage.  Complex plans along a strided axis with a
+ * power-of-two length (b200_fft1d_convolvable() == 1), else B200_ERR_UNSUPPORTED without an error text.
+ */
+int b200_fft1d_convolvable(b200_fft1d_plan plan);
+int b200_fft1d_execute_convolve(b200_fft1d_plan plan, const void *in, void *out, const void *device_scatter_map, const void *multiplier,
+                                double scale, void *stream, int batch, long long in_step, long long out_step,
+                                long long scatter_step, long long local_shift, long long local_step);
+/* pointwise complex product data[i] = data[i] * factor * M[i] (M == NULL: data[i] itself), the unfused form of the operator above */
+int b200_pointwise_multiply(int precision, long long count, void *data, const void *multiplier, double factor, void *stream);
 /* name of the kernel family the plan resolved to ("strided", "contig", "generic"), for tests and profiling */
 const char* b200_fft1d_kernel_name(b200_fft1d_plan plan);
 
@@ -143,6 +177,17 @@ int b200_transpose_unpack(int elem_bytes, long long nfast, long long nmid, long 
  */
 int b200_scatter_copy(int elem_bytes, long long nfast, long long nmid, long long nslow, long long line_stride, long long plane_stride,
                       const void *src, const void *device_scatter_map, void *stream);
+/* batched variant: `batch` entries in one launch, entry e reads src + e * in_step bytes and adds e * scatter_step bytes to every
+ * destination (local_shift + e * local_step more to the destinations inside this rank's own memory) */
+int b200_scatter_copy_batch(int elem_bytes, long long nfast, long long nmid, long long nslow, long long line_stride, long long plane_stride,
+                            const void *src, const void *device_scatter_map, void *stream,
+                            int batch, long long in_step, long long scatter_step, long long local_shift, long long local_step);
+/* Several sub-boxes of one box copied to the same positions of another array of the same layout, all pieces and all batch
+ * entries in ONE launch (16-byte accesses where the geometry allows): the pieces a rank received from the other GPUs move
+ * from the plan's arena into the caller's array.  offsets / nfast / nmid / nslow: npieces entries, in elements. */
+int b200_copy_subboxes(int elem_bytes, int npieces, const long long *offsets, const long long *nfast, const long long *nmid, const long long *nslow,
+                       long long line_stride, long long plane_stride, const void *src, void *dst, void *stream,
+                       int batch, long long src_step, long long dst_step);
 /*
  * Stream-ordered barrier between the GPUs of a plan over peer memory (stands where the reference blocks the host in
  * MPI_Alltoallv / MPI_Waitany, src/heffte_reshape3d.cpp:388-402, 662): remote_slots[p] is the address, in rank p's flag

@@ -147,6 +147,7 @@ inline cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, int){ st
 inline cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, int, cudaStream_t){ std::memmove(dst, src, bytes); return cudaSuccess; }
 inline cudaError_t cudaMemcpyPeerAsync(void *dst, int, const void *src, int, size_t bytes, cudaStream_t){ std::memmove(dst, src, bytes); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *dst, int value, size_t bytes){ std::memset(dst, value, bytes); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *dst, int value, size_t bytes, cudaStream_t){ std::memset(dst, value, bytes); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t){ return cudaSuccess; }
 enum { cudaStreamNonBlocking = 1 };
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned){ static char token[64]; static int next = 0; *s = token + (next++ % 64); return cudaSuccess; }

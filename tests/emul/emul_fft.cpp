@@ -7,9 +7,10 @@
 
 namespace {
 struct emul_launcher {
+    int batch = 1;
     template<typename kernel_t, typename args_t>
     int launch(kernel_t kernel, long long blocks, int threads, size_t smem, args_t const &args){
-        emul::launch(kernel, dim3((unsigned) blocks), dim3((unsigned) threads), smem, args);
+        emul::launch(kernel, dim3((unsigned) blocks, (unsigned) batch), dim3((unsigned) threads), smem, args);
         return 0;
     }
     int run_pow2(bool strided, bool is_float, bool scatter, int n, b200::fft_args const &a){

@@ -39,6 +39,11 @@ def main():
         todo.append((dict(kind="c2c", n=(96, 80, 6), prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 1))
         todo.append((dict(kind="r2c", n=(160, 96, 4), prec=0, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2), r2c_dir=0), 1))
         todo.append((dict(kind="cos", n=(160, 192, 4), prec=1, reorder=True, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 1))
+    # 128-point lines along the two fast axes: the paired kernel (a local transform inside the persistent kernel of the fused
+    # stage behind it; on one rank the single-precision pair through the L2 cache), batched
+    if nranks in (1, 2) and stride != 6:
+        todo.append((dict(kind="c2c", n=(128, 128, 4), prec=0, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 1))
+        todo.append((dict(kind="c2c", n=(128, 128, 4), prec=1, reorder=False, pencils=False, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 2))
     comms = hf.comm_threads(nranks)
     gate = threading.Barrier(nranks)
     failures = [None] * nranks

@@ -162,6 +162,33 @@ def run_config(hf, torch, comm, rank, c, batch=1, stream=None, expect_peer=None,
         err = O.rel_l2(arrays.to_host(d), local) if local.size else 0.0
         if not err <= 2 * tol:
             problems.append("in-place round trip: %.3e" % err)
+    # fused spectral operator (reference benchmarks/convolution.cpp:86-97): forward(scale full), pointwise product, backward, as
+    # ONE plan call -- the spectrum times itself, then times a caller array laid out over convolve_box()
+    if kind == "c2c" and batch == 1 and all(a.count() == b.count() for a, b in zip(inboxes, outboxes)):
+        spectrum = O.fft3d_forward(x, n, "c2c", scaling="full")
+        for use_multiplier in (False, True):
+            lo, hi, order = fft.convolve_box()
+            cbox = O.Box(lo, hi, order)
+            mult_world = None
+            dm = None
+            if use_multiplier:
+                mrng = np.random.default_rng(77)
+                mult_world = (mrng.random(world.count()) + 1j * mrng.random(world.count())).astype(cdt)
+                dm = arrays.to_device(O.get_subbox(world, cbox, mult_world))
+            product = spectrum * (mult_world if use_multiplier else spectrum)
+            expect_c = O.get_subbox(world, inbox, O.fft3d_backward(product, n, "c2c", scaling="none"))
+            d = arrays.to_device(local)
+            dout = arrays.empty(inbox.count(), x.dtype)
+            try:
+                fft.convolve(d, dout, dm, 1)
+            except Exception as e:  # noqa: BLE001  (the exchange path offers the self-product only)
+                if use_multiplier and "multiplier" in str(e):
+                    continue
+                raise
+            err = O.rel_l2(arrays.to_host(dout), expect_c) if expect_c.size else 0.0
+            worst = max(worst, err)
+            if not err <= 4 * tol:
+                problems.append("convolve(%s): rel l2 %.3e" % ("multiplier" if use_multiplier else "self", err))
     assert not problems, "rank %d %s: %s" % (rank, c, "; ".join(problems))
     return worst
 
@@ -189,6 +216,10 @@ def main():
     todo = [(c, 1) for c in configs(size, args.quick, subcomm=args.subcomm)]
     # batched transforms across ranks (test/test_fft3d.h:505-572)
     todo.append((dict(kind="c2c", n=(16, 18, 20), prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 3))
+    # lines of 128 / 256 points along the two fast axes: the local transform in front of a fused stage runs inside its persistent
+    # kernel (fft_pair_kernel), single and batched
+    todo.append((dict(kind="c2c", n=(128, 128, 32), prec=0, reorder=False, pencils=False, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 2))
+    todo.append((dict(kind="c2c", n=(256, 256, 16), prec=1, reorder=False, pencils=True, alg=0, gin=gin, gout=gout, order_out=(0, 1, 2)), 1))
     flag = torch.zeros(1, device="cuda", dtype=torch.int32)
     for c, batch in todo:
         try:
