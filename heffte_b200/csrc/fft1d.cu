@@ -252,6 +252,59 @@ int b200_fft1d_execute_pair(b200_fft1d_plan first, b200_fft1d_plan second, int d
     return (rc == -1) ? B200_ERR_UNSUPPORTED : rc;
 }
 
+// Two transforms of the same box, neither along its slowest axis, both on the complex fast-path kernels: the first can feed
+// the second plane by plane.
+static bool overlappable(host_plan const &x, host_plan const &y){
+    auto fast = [](host_plan const &h){ return (h.family == family_strided or h.family == family_contig) and h.desc.kind == B200_C2C; };
+    if (not fast(x) or not fast(y) or x.desc.precision != y.desc.precision) return false;
+    b200_fft1d_desc const &p = x.desc, &q = y.desc;
+    if (p.count_b < 2 or p.count_b != q.count_b) return false;                       // planes of the slowest axis
+    if (p.out.stride_b != q.in.stride_b or p.in.stride_b != p.out.stride_b or q.in.stride_b != q.out.stride_b) return false;
+    if (p.n * p.count_a != q.n * q.count_a) return false;                            // the same plane
+    return p.count_a < 2147483647LL and q.count_a < 2147483647LL;
+}
+int b200_fft1d_overlappable(b200_fft1d_plan first, b200_fft1d_plan second){
+    return (first != nullptr and second != nullptr and overlappable(first->host, second->host)) ? 1 : 0;
+}
+
+// first: in -> mid on `side_stream`, reporting plane by plane; second: mid -> scatter map on `stream` with a thin grid, waiting
+// plane by plane.  stream: zero the counters, fork; side_stream: first transform, join; stream: second transform, wait for the join.
+int b200_fft1d_execute_overlapped(b200_fft1d_plan first, b200_fft1d_plan second, int direction, const void *in, void *mid,
+                                  const void *device_scatter_map, int map_nb, double scale, void *counters, void *stream, void *side_stream,
+                                  void *fork_event, void *join_event,
+                                  int batch, long long in_step, long long mid_step, long long scatter_step, long long local_shift, long long local_step,
+                                  int thin_blocks){
+    if (first == nullptr or second == nullptr or mid == nullptr or counters == nullptr or device_scatter_map == nullptr) return fail(B200_ERR_INVALID, "null argument");
+    if (batch < 1) return fail(B200_ERR_INVALID, "batch must be positive");
+    if (not overlappable(first->host, second->host)) return B200_ERR_UNSUPPORTED;
+    long long const planes = first->host.desc.count_b;
+    cudaStream_t const main_stream = static_cast<cudaStream_t>(stream), side = static_cast<cudaStream_t>(side_stream);
+    int rc = check_cuda(cudaMemsetAsync(counters, 0, sizeof(unsigned) * static_cast<size_t>(planes) * batch, main_stream), "cudaMemsetAsync(plane counters)");
+    if (rc == 0) rc = check_cuda(cudaEventRecord(static_cast<cudaEvent_t>(fork_event), main_stream), "cudaEventRecord(fork)");
+    if (rc == 0) rc = check_cuda(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(fork_event), 0), "cudaStreamWaitEvent(fork)");
+    if (rc) return rc;
+    {
+        cuda_launcher L{side};
+        batch_steps steps; steps.batch = batch; steps.in_step = in_step; steps.out_step = mid_step;
+        steps.done = static_cast<unsigned*>(counters); steps.done_mode = 1; steps.order_nb = map_nb;
+        rc = run_host_plan(first->host, first->twiddle, direction, in, mid, 1.0, L, nullptr, 0, -1, steps);
+        if (rc == -1) return fail(B200_ERR_UNSUPPORTED, "no kernel for this length");
+        if (rc == 0) rc = check_cuda(cudaEventRecord(static_cast<cudaEvent_t>(join_event), side), "cudaEventRecord(join)");
+        if (rc) return rc;
+    }
+    {
+        cuda_launcher L{main_stream};
+        batch_steps steps; steps.batch = batch; steps.in_step = mid_step;
+        steps.scatter_step = scatter_step; steps.local_shift = local_shift; steps.local_step = local_step;
+        steps.done = static_cast<unsigned*>(counters); steps.done_mode = 2; steps.done_need = static_cast<unsigned>(first->host.desc.count_a);
+        steps.max_blocks = (thin_blocks > 0) ? thin_blocks : 0;
+        rc = run_host_plan(second->host, second->twiddle, direction, mid, nullptr, scale, L, device_scatter_map, 0, -1, steps);
+        if (rc == -1) return fail(B200_ERR_UNSUPPORTED, "no kernel for this length");
+        if (rc == 0) rc = check_cuda(cudaStreamWaitEvent(main_stream, static_cast<cudaEvent_t>(join_event), 0), "cudaStreamWaitEvent(join)");
+    }
+    return rc;
+}
+
 int b200_fft1d_convolvable(b200_fft1d_plan plan){
     if (plan == nullptr) return 0;
     b200_fft1d_desc const &d = plan->host.desc;

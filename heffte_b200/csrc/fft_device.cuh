@@ -154,6 +154,29 @@ template<typename T> struct butterfly<T, 5>{
     }
 };
 
+template<typename T> struct butterfly<T, 7>{
+    __device__ __forceinline__ static void run(cplx<T> (&v)[7]){
+        // cos / sin of 2 pi m / 7, m = 1, 2, 3
+        const T c1 = static_cast<T>( 0.62348980185873353052500488400424), c2 = static_cast<T>(-0.22252093395631440428890256449679),
+                c3 = static_cast<T>(-0.90096886790241912623610231950745);
+        const T s1 = static_cast<T>( 0.78183148246802980870844452667406), s2 = static_cast<T>( 0.97492791218182360701813168299393),
+                s3 = static_cast<T>( 0.43388373911755812047576833284836);
+        const cplx<T> a1 = cadd(v[1], v[6]), a2 = cadd(v[2], v[5]), a3 = cadd(v[3], v[4]);
+        const cplx<T> b1 = csub(v[1], v[6]), b2 = csub(v[2], v[5]), b3 = csub(v[3], v[4]);
+        // even parts r_m = v0 + sum_k cos(2 pi m k / 7) a_k,  odd parts i_m = sum_k sin(2 pi m k / 7) b_k
+        const cplx<T> r1 = mk<T>(v[0].x + c1 * a1.x + c2 * a2.x + c3 * a3.x, v[0].y + c1 * a1.y + c2 * a2.y + c3 * a3.y);
+        const cplx<T> r2 = mk<T>(v[0].x + c2 * a1.x + c3 * a2.x + c1 * a3.x, v[0].y + c2 * a1.y + c3 * a2.y + c1 * a3.y);
+        const cplx<T> r3 = mk<T>(v[0].x + c3 * a1.x + c1 * a2.x + c2 * a3.x, v[0].y + c3 * a1.y + c1 * a2.y + c2 * a3.y);
+        const cplx<T> i1 = mk<T>(s1 * b1.x + s2 * b2.x + s3 * b3.x, s1 * b1.y + s2 * b2.y + s3 * b3.y);
+        const cplx<T> i2 = mk<T>(s2 * b1.x - s3 * b2.x - s1 * b3.x, s2 * b1.y - s3 * b2.y - s1 * b3.y);
+        const cplx<T> i3 = mk<T>(s3 * b1.x - s1 * b2.x + s2 * b3.x, s3 * b1.y - s1 * b2.y + s2 * b3.y);
+        v[0] = mk<T>(v[0].x + a1.x + a2.x + a3.x, v[0].y + a1.y + a2.y + a3.y);
+        v[1] = mk<T>(r1.x + i1.y, r1.y - i1.x);   v[6] = mk<T>(r1.x - i1.y, r1.y + i1.x);      // r - i i  /  r + i i
+        v[2] = mk<T>(r2.x + i2.y, r2.y - i2.x);   v[5] = mk<T>(r2.x - i2.y, r2.y + i2.x);
+        v[3] = mk<T>(r3.x + i3.y, r3.y - i3.x);   v[4] = mk<T>(r3.x - i3.y, r3.y + i3.x);
+    }
+};
+
 // R = P * Q in registers: P-point transforms over n1 (input n = n1 Q + n2), twiddles W_R^(n2 k1), Q-point transforms over n2,
 // output k = k1 + P k2.  COS / SIN hold cos / sin of 2 pi m / R for m = 0 .. R-1.
 template<typename T, int P, int Q, typename TABLE>
@@ -237,6 +260,14 @@ struct fft_args {
     // its own part in the caller's array without a per-call copy of the map.
     long long in_step, out_step, scatter_step, local_shift, local_step;
     const void *multiplier;    // fused spectral operator (fft_strided_conv_kernel): null = the spectrum times itself
+    // two kernels that overlap on two streams (a local transform feeding the fused transform behind it, plane by plane):
+    // done[b] counts the tiles of the producer stored for plane b (b = line / count_a).  done_mode 1: this launch signals,
+    // 2: this launch waits until done[b] >= done_need before it touches plane b.  order_nb > 1: the planes are visited
+    // round-robin over that many ranges (the order of the fused kernels, scatter_tile_order) so that producer and consumer agree.
+    unsigned *done;
+    int done_mode;
+    unsigned done_need;
+    int order_nb;
 };
 struct batch_shift { long long all, local; };
 // the arguments of batch entry blockIdx.y
@@ -246,6 +277,7 @@ __device__ __forceinline__ fft_args batch_entry(fft_args a, batch_shift &shift){
     if (a.out != nullptr) a.out = static_cast<char*>(a.out) + e * a.out_step;
     shift.all = e * a.scatter_step;
     shift.local = a.local_shift + e * a.local_step;
+    if (a.done_mode != 0) a.done += e * (a.nlines / a.count_a);      // one set of plane counters per entry
     return a;
 }
 
@@ -324,6 +356,22 @@ template<int BYTES> inline void async_copy(void *smem_dst, const void *gsrc){ st
 inline void async_wait_all(){}
 #endif
 
+#ifndef B200_HOST_EMULATION
+__device__ __forceinline__ unsigned load_acquire(const unsigned *p){
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ticket_take(unsigned *p){ return atomicAdd(p, 1u); }
+__device__ __forceinline__ void count_release(unsigned *p){ __threadfence(); atomicAdd(p, 1u); }
+__device__ __forceinline__ void count_release_n(unsigned *p, unsigned n){ __threadfence(); atomicAdd(p, n); }
+#else
+inline unsigned load_acquire(const unsigned *p){ return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline unsigned ticket_take(unsigned *p){ return __atomic_fetch_add(p, 1u, __ATOMIC_ACQ_REL); }
+inline void count_release(unsigned *p){ __atomic_fetch_add(p, 1u, __ATOMIC_ACQ_REL); }
+inline void count_release_n(unsigned *p, unsigned n){ __atomic_fetch_add(p, n, __ATOMIC_ACQ_REL); }
+#endif
+
 __host__ __device__ constexpr int cmax(int a, int b){ return a > b ? a : b; }
 __host__ __device__ constexpr int ilog2(int n){ return n <= 1 ? 0 : 1 + ilog2(n / 2); }
 
@@ -385,8 +433,13 @@ __device__ __forceinline__ long long tile_line_offset(line_geom const &g, int co
 // those GPUs becomes the limit (measured on 4 GPUs: 417 GB/s per sender instead of 680).  A bijection on the tile
 // indices; the identity when the tiles straddle rows of the box or the ranges do not divide it.
 template<int LPB>
+__device__ __forceinline__ unsigned round_robin_tile_order(fft_args const &a, unsigned nb, unsigned blk);
+template<int LPB>
 __device__ __forceinline__ unsigned scatter_tile_order(fft_args const &a, unsigned blk){
-    const unsigned nb = static_cast<unsigned>(a.smap->nb);
+    return round_robin_tile_order<LPB>(a, static_cast<unsigned>(a.smap->nb), blk);
+}
+template<int LPB>
+__device__ __forceinline__ unsigned round_robin_tile_order(fft_args const &a, unsigned nb, unsigned blk){
     const unsigned ca = static_cast<unsigned>(a.count_a);
     if (nb <= 1 || ca % LPB != 0) return blk;
     const unsigned tiles_per_b = ca / LPB;
@@ -511,6 +564,39 @@ __device__ __forceinline__ void strided_tile(cplx<T> *sm, const scatter_map *sma
 // number of tiles of a launch
 template<int LPB> __host__ __device__ inline unsigned tile_count(fft_args const &a){ return static_cast<unsigned>((a.nlines + LPB - 1) / LPB); }
 
+// Overlap of two launches plane by plane (fft_args::done).  A consumer waits for the planes its tile touches; a producer visits
+// the planes in the consumer's order and reports every tile it has stored.  Whole CTA; ends with a barrier when it waited.
+template<int LPB>
+__device__ __forceinline__ void wait_for_planes(fft_args const &a, unsigned ordered_tile){
+    if (a.done_mode != 2) return;
+    if (threadIdx.x == 0){
+        const unsigned first = (ordered_tile * LPB) / static_cast<unsigned>(a.count_a);
+        long long last_line = static_cast<long long>(ordered_tile) * LPB + LPB - 1;
+        if (last_line >= a.nlines) last_line = a.nlines - 1;
+        const unsigned last = static_cast<unsigned>(last_line / a.count_a);
+        for(unsigned b = first; b <= last; b++){ while(load_acquire(a.done + b) < a.done_need){} }
+    }
+    __syncthreads();
+}
+template<int LPB>
+__device__ __forceinline__ void report_plane(fft_args const &a, unsigned ordered_tile){
+    if (a.done_mode != 1) return;
+    __syncthreads();                   // every thread has issued its stores
+    if (threadIdx.x == 0){
+        // the LINES of this tile, plane by plane (a tile may straddle two planes): the consumer waits for count_a lines
+        const long long l0 = static_cast<long long>(ordered_tile) * LPB;
+        long long l1 = l0 + LPB;
+        if (l1 > a.nlines) l1 = a.nlines;
+        for(long long l = l0; l < l1; ){
+            const long long b = l / a.count_a;
+            long long end = (b + 1) * a.count_a;
+            if (end > l1) end = l1;
+            count_release_n(a.done + b, static_cast<unsigned>(end - l));
+            l = end;
+        }
+    }
+}
+
 // The kernel walks the tiles grid-stride: one tile per CTA when the grid covers the box (the usual launch), several when the
 // grid is kept thin on purpose so that another kernel can share the SMs (NVLink-bound stages of a multi-GPU plan).
 template<typename T, typename RL, int TPL, int LPB, int MINB, bool BWD, bool SCATTER>
@@ -526,7 +612,15 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a
     }
     const unsigned ntiles = tile_count<LPB>(a);
     for(unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
-        strided_tile<T, RL, TPL, LPB, BWD, SCATTER>(sm, smap, a, tile);
+        if constexpr (SCATTER){
+            if (a.done_mode == 2) wait_for_planes<LPB>(a, scatter_tile_order<LPB>(a, tile));
+            strided_tile<T, RL, TPL, LPB, BWD, SCATTER>(sm, smap, a, tile);
+        }else{
+            const unsigned at = (a.order_nb > 1) ? round_robin_tile_order<LPB>(a, static_cast<unsigned>(a.order_nb), tile) : tile;
+            wait_for_planes<LPB>(a, at);
+            strided_tile<T, RL, TPL, LPB, BWD, SCATTER>(sm, smap, a, at);
+            report_plane<LPB>(a, at);
+        }
         if (tile + gridDim.x < ntiles) __syncthreads();
     }
 }
@@ -835,7 +929,15 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_contig_kernel(fft_args a0
     }
     const unsigned ntiles = tile_count<LPB>(a);
     for(unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
-        contig_tile<T, RL, LPB, BWD, SCATTER, TPL>(smem_raw, smap, a, tile);
+        if constexpr (SCATTER){
+            if (a.done_mode == 2) wait_for_planes<LPB>(a, scatter_tile_order<LPB>(a, tile));
+            contig_tile<T, RL, LPB, BWD, SCATTER, TPL>(smem_raw, smap, a, tile);
+        }else{
+            const unsigned at = (a.order_nb > 1) ? round_robin_tile_order<LPB>(a, static_cast<unsigned>(a.order_nb), tile) : tile;
+            wait_for_planes<LPB>(a, at);
+            contig_tile<T, RL, LPB, BWD, SCATTER, TPL>(smem_raw, smap, a, at);
+            report_plane<LPB>(a, at);
+        }
         if (tile + gridDim.x < ntiles) __syncthreads();
     }
 }
@@ -860,19 +962,6 @@ struct pair_args {
     unsigned *done;                // [planes], zeroed before the launch: tiles of the first transform stored, per plane
 };
 
-#ifndef B200_HOST_EMULATION
-__device__ __forceinline__ unsigned load_acquire(const unsigned *p){
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned ticket_take(unsigned *p){ return atomicAdd(p, 1u); }
-__device__ __forceinline__ void count_release(unsigned *p){ __threadfence(); atomicAdd(p, 1u); }
-#else
-inline unsigned load_acquire(const unsigned *p){ return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
-inline unsigned ticket_take(unsigned *p){ return __atomic_fetch_add(p, 1u, __ATOMIC_ACQ_REL); }
-inline void count_release(unsigned *p){ __atomic_fetch_add(p, 1u, __ATOMIC_ACQ_REL); }
-#endif
 
 // shared memory of the paired kernel: the larger of the two tiles, then (scatter variants) the staged map, then the ticket
 template<typename T, typename RLA, int LPBA, typename RLB, int LPBB>

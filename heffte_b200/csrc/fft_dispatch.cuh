@@ -16,14 +16,16 @@ constexpr bool is_pow2(long long n){ return n > 0 && (n & (n - 1)) == 0; }
 constexpr int pow2_max = 4096;
 constexpr int pow2_min = 16;
 
-// lengths with odd factors served by the register/shared-memory kernels (radices 3, 5, 6, 10, 12 next to 2, 4, 8, 16)
-// (48 and 100 have kernels in the tables below but stay on the generic kernel until the new kernels have had a GPU run: they
-// are the two mixed lengths the GPU parity suite and smoke() of this round already use)
+// lengths with odd factors served by the register/shared-memory kernels (radices 3, 5, 6, 7, 10, 12 next to 2, 4, 8, 16)
 constexpr bool is_mixed_fast_length(long long n){
-    return n == 96 || n == 192 || n == 384 || n == 768 || n == 1536 ||
+    return n == 48 || n == 96 || n == 192 || n == 384 || n == 768 || n == 1536 ||
            n == 80 || n == 160 || n == 320 || n == 640 || n == 1280 ||
-           n == 200 || n == 400 || n == 500 || n == 1000 || n == 2000;
+           n == 100 || n == 200 || n == 400 || n == 500 || n == 1000 || n == 2000 ||
+           n == 112 || n == 224 || n == 448 || n == 896 || n == 1792 || n == 3584;
 }
+// real lengths 2 m whose half m has a schedule in the real-data tables (48 and 100 have none there)
+// (nor for 3584: a real line of 7168 points is beyond the generic kernel that backs up unaligned lines)
+constexpr bool is_mixed_fast_half(long long m){ return is_mixed_fast_length(m) && m != 48 && m != 100 && m != 3584; }
 constexpr bool is_fast_length(long long n){ return (is_pow2(n) && n >= pow2_min && n <= pow2_max) || is_mixed_fast_length(n); }
 
 template<typename T, typename RL, int TPL, int LPB, int MINB, bool SCATTER, typename Launcher>
@@ -84,6 +86,13 @@ int dispatch_strided(int n, fft_args const &a, Launcher &L){
         case 500:  return launch_strided<T, radix_list<10, 10, 5, 1>,  25,  8 * M, 2, SCATTER>(a, L);
         case 1000: return launch_strided<T, radix_list<10, 10, 10, 1>, 50,  4 * M, 1, SCATTER>(a, L);
         case 2000: return launch_strided<T, radix_list<10, 10, 10, 2>, 100, 2 * M, 1, SCATTER>(a, L);
+        // 7 * 2^k
+        case 112:  return launch_strided<T, radix_list<7, 4, 4, 1>,     4, 16 * M, 2, SCATTER>(a, L);
+        case 224:  return launch_strided<T, radix_list<7, 8, 4, 1>,     4,  8 * M, 2, SCATTER>(a, L);
+        case 448:  return launch_strided<T, radix_list<7, 8, 8, 1>,     8,  8 * M, 2, SCATTER>(a, L);
+        case 896:  return launch_strided<T, radix_list<7, 8, 16, 1>,    8,  8 * M, 1, SCATTER>(a, L);
+        case 1792: return launch_strided<T, radix_list<7, 16, 16, 1>,  16,  4 * M, 1, SCATTER>(a, L);
+        case 3584: return launch_strided<T, radix_list<7, 8, 8, 8>,    64,  2 * M, 1, SCATTER>(a, L);
         default: return -1;
     }
 }
@@ -146,6 +155,12 @@ int dispatch_contig(int n, fft_args const &a, Launcher &L){
         case 500:  return launch_contig_tpl<T, radix_list<10, 10, 5, 1>,  25,  4, 4, SCATTER>(a, L);
         case 1000: return launch_contig_tpl<T, radix_list<10, 10, 10, 1>, 50,  2, 2, SCATTER>(a, L);
         case 2000: return launch_contig_tpl<T, radix_list<10, 10, 10, 2>, 100, 1, 2, SCATTER>(a, L);
+        case 112:  return launch_contig_tpl<T, radix_list<7, 4, 4, 1>,     4, 16, 4, SCATTER>(a, L);
+        case 224:  return launch_contig_tpl<T, radix_list<7, 8, 4, 1>,     4,  8, 4, SCATTER>(a, L);
+        case 448:  return launch_contig_tpl<T, radix_list<7, 8, 8, 1>,     8,  8, 4, SCATTER>(a, L);
+        case 896:  return launch_contig_tpl<T, radix_list<7, 8, 16, 1>,    8,  4, 4, SCATTER>(a, L);
+        case 1792: return launch_contig_tpl<T, radix_list<7, 16, 16, 1>,  16,  2, 2, SCATTER>(a, L);
+        case 3584: return launch_contig_tpl<T, radix_list<7, 8, 8, 8>,    64,  1, 2, SCATTER>(a, L);
         default: return -1;
     }
 }
@@ -210,7 +225,7 @@ constexpr int real_pow2_min = 2 * pow2_min;   // real lengths served by the fast
 constexpr int real_pow2_max = 4096;
 // real lengths n = 2m served by the real-data kernels: powers of two 32 ... 4096 and twice the mixed c2c lengths
 constexpr bool is_fast_real_length(long long n){
-    return (is_pow2(n) && n >= real_pow2_min && n <= real_pow2_max) || (n % 2 == 0 && is_mixed_fast_length(n / 2));
+    return (is_pow2(n) && n >= real_pow2_min && n <= real_pow2_max) || (n % 2 == 0 && is_mixed_fast_half(n / 2));
 }
 
 template<typename T, typename RL, int TPL, int LPB, int MINB, int KIND, bool SCATTER, typename Launcher>
@@ -251,6 +266,12 @@ int dispatch_contig_real_kind(int m, fft_args const &a, Launcher &L){
         case 500:  return launch_contig_real_tpl<T, radix_list<10, 10, 5, 1>,  25,  4, 4, KIND, SCATTER>(a, L);
         case 1000: return launch_contig_real_tpl<T, radix_list<10, 10, 10, 1>, 50,  2, 2, KIND, SCATTER>(a, L);
         case 2000: return launch_contig_real_tpl<T, radix_list<10, 10, 10, 2>, 100, 1, 2, KIND, SCATTER>(a, L);
+        // m = 7 * 2^k (real lengths 224 ... 7168); the radix 7 comes last: the first radix stays even for the sine kinds
+        case 112:  return launch_contig_real_tpl<T, radix_list<4, 4, 7, 1>,     4, 16, 4, KIND, SCATTER>(a, L);
+        case 224:  return launch_contig_real_tpl<T, radix_list<8, 4, 7, 1>,     4,  8, 4, KIND, SCATTER>(a, L);
+        case 448:  return launch_contig_real_tpl<T, radix_list<8, 8, 7, 1>,     8,  8, 4, KIND, SCATTER>(a, L);
+        case 896:  return launch_contig_real_tpl<T, radix_list<16, 8, 7, 1>,    8,  4, 4, KIND, SCATTER>(a, L);
+        case 1792: return launch_contig_real_tpl<T, radix_list<16, 16, 7, 1>,  16,  2, 2, KIND, SCATTER>(a, L);
         default: return -1;
     }
 }
@@ -292,6 +313,11 @@ int dispatch_strided_real_kind(int m, fft_args const &a, Launcher &L){
         case 500:  return launch_strided_real<T, radix_list<10, 10, 5, 1>,  25,  8 * F, 1, KIND, SCATTER>(a, L);
         case 1000: return launch_strided_real<T, radix_list<10, 10, 10, 1>, 50,  4 * F, 1, KIND, SCATTER>(a, L);
         case 2000: return launch_strided_real<T, radix_list<10, 10, 10, 2>, 100, 2 * F, 1, KIND, SCATTER>(a, L);
+        case 112:  return launch_strided_real<T, radix_list<4, 4, 7, 1>,     4, 32 * F, 2, KIND, SCATTER>(a, L);
+        case 224:  return launch_strided_real<T, radix_list<8, 4, 7, 1>,     4, 16 * F, 2, KIND, SCATTER>(a, L);
+        case 448:  return launch_strided_real<T, radix_list<8, 8, 7, 1>,     8, 16 * F, 2, KIND, SCATTER>(a, L);
+        case 896:  return launch_strided_real<T, radix_list<16, 8, 7, 1>,    8,  8 * F, 1, KIND, SCATTER>(a, L);
+        case 1792: return launch_strided_real<T, radix_list<16, 16, 7, 1>,  16,  4 * F, 1, KIND, SCATTER>(a, L);
         default: return -1;
     }
 }

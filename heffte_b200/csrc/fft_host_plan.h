@@ -120,10 +120,17 @@ inline line_geom to_geom(b200_line_geom const &g){ return line_geom{g.stride, g.
 struct batch_steps {
     int batch = 1;
     long long in_step = 0, out_step = 0, scatter_step = 0, local_shift = 0, local_step = 0;
+    // plane-wise overlap of two launches (fft_args::done ...): complex fast-path kernels only
+    unsigned *done = nullptr;
+    int done_mode = 0;
+    unsigned done_need = 0;
+    int order_nb = 0;
+    long long max_blocks = 0;       // > 0: a thin grid (the kernels walk their tiles grid-stride)
 };
 template<typename args_t> inline void set_steps(args_t &a, batch_steps const &s){
     a.in_step = s.in_step; a.out_step = s.out_step; a.scatter_step = s.scatter_step; a.local_shift = s.local_shift; a.local_step = s.local_step;
 }
+inline void set_hooks(fft_args &a, batch_steps const &s){ a.done = s.done; a.done_mode = s.done_mode; a.done_need = s.done_need; a.order_nb = s.order_nb; }
 
 // runs the plan through a Launcher (CUDA stream launcher in the product, thread emulation in tests/emul)
 // `scatter` (device pointer to a scatter_map, or null) fuses the following reshape into the store of the transform
@@ -132,6 +139,7 @@ template<typename Launcher>
 int run_host_plan(host_plan const &plan, const void *twiddle, int direction, const void *in, void *out, double scale, Launcher &L,
                   const void *scatter = nullptr, long long b_begin = 0, long long b_count = -1, batch_steps const &steps = batch_steps()){
     L.batch = steps.batch;
+    L.max_blocks = 0;
     b200_fft1d_desc const &d = plan.desc;
     bool const backward = (direction == B200_BACKWARD);
     bool const is_float = (d.precision == B200_PREC_FLOAT);
@@ -172,10 +180,11 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
             a.scale = scale;
             a.smap = static_cast<const scatter_map*>(scatter);
             set_steps(a, steps);
+            a.done = nullptr; a.done_mode = 0; a.done_need = 0; a.order_nb = 0; a.multiplier = nullptr;
             return L.run_real(plan.family == family_strided_real, is_float, scatter != nullptr, plan.real_kind, static_cast<int>(d.n / 2), a);
         }
     }else if (plan.family != family_generic){
-        fft_args a;
+        fft_args a{};
         a.in = in; a.out = out; a.twiddle = twiddle; a.twiddle2 = nullptr;
         a.ig = to_geom(backward ? d.out : d.in);   // backward swaps the roles of the two geometries
         a.og = to_geom(backward ? d.in : d.out);
@@ -185,6 +194,8 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
         a.scale = scale;
         a.smap = static_cast<const scatter_map*>(scatter);
         set_steps(a, steps);
+        set_hooks(a, steps);
+        L.max_blocks = steps.max_blocks;
         return L.run_pow2(plan.family == family_strided, is_float, scatter != nullptr, static_cast<int>(d.n), a);
     }
 

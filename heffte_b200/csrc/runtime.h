@@ -26,9 +26,11 @@ void allow_smem(const void *kernel, size_t bytes);
 struct cuda_launcher {
     cudaStream_t stream;
     int batch = 1;          // grid.y: entries of a batched transform (the kernels read blockIdx.y)
+    long long max_blocks = 0;   // > 0: cap of grid.x (set only for kernels that walk their tiles grid-stride)
     template<typename kernel_t, typename args_t>
     int launch(kernel_t kernel, long long blocks, int threads, size_t smem, args_t const &args){
         if (blocks <= 0 or batch <= 0) return B200_SUCCESS;
+        if (max_blocks > 0 and blocks > max_blocks) blocks = max_blocks;
         if (blocks > 2147483647LL or batch > 65535) return fail(B200_ERR_UNSUPPORTED, "grid too large");
 #ifdef B200_HOST_EMULATION
         emul::launch(kernel, dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(batch)), dim3(static_cast<unsigned>(threads)), smem, args);   // tests/emul only

@@ -191,6 +191,15 @@ transform3d::transform3d(transform_kind kind, box3 const &inbox, box3 const &out
     // (2) the plan that is executed (plan_logic.h: no reorder of the intermediate boxes, traffic balancing)
     lp = make_execution_plan(ins, outs, r2c_dir, effective, me, &balanced_swaps);
 
+    // backward transforms of complex and real-to-real plans: planned like a forward transform from the output boxes to the
+    // input boxes (see transform.h, view_backward); r2c plans keep the mirror image (the real transform must come last)
+    for(int p=0; p<2; p++) for(int i=0; i<3; i++) bexec[p][i] = nullptr;
+    if (kind != kind_r2c and n > 1 and std::getenv("HEFFTE_B200_MIRRORED_BACKWARD") == nullptr){
+        try{
+            lb = make_execution_plan(outs, ins, -1, effective, me);
+            lb_active = true;
+        }catch(std::exception &){ lb_active = false; }
+    }
     {   // the executed plan depends on per-process switches (HEFFTE_B200_REFERENCE_PLAN, HEFFTE_B200_DECOMPOSITION): every rank
         // must have arrived at the same boxes, or the fused stores would land at wrong addresses
         unsigned long long h = 1469598103934665603ULL;
@@ -199,6 +208,13 @@ transform3d::transform3d(transform_kind kind, box3 const &inbox, box3 const &out
             for(shape const *sh : {&lp.in_shape[s], &lp.out_shape[s]})
                 for(box3 const &b : *sh) for(int d=0; d<3; d++){ mix(b.low[d]); mix(b.high[d]); mix(b.order[d]); }
         for(int d=0; d<3; d++) mix(lp.fft_direction[d]);
+        mix(lb_active ? 1 : 0);
+        if (lb_active){
+            for(int s=0; s<4; s++)
+                for(shape const *sh : {&lb.in_shape[s], &lb.out_shape[s]})
+                    for(box3 const &b : *sh) for(int d=0; d<3; d++){ mix(b.low[d]); mix(b.high[d]); mix(b.order[d]); }
+            for(int d=0; d<3; d++) mix(lb.fft_direction[d]);
+        }
         std::vector<unsigned long long> all_hashes(static_cast<size_t>(n));
         if (comm->allgather(&h, all_hashes.data(), sizeof(h)) != 0) throw std::runtime_error("allgather of the plan signature failed");
         for(unsigned long long v : all_hashes)
@@ -263,8 +279,12 @@ void transform3d::release_peer(int precision){
 transform3d::~transform3d(){
     for(int p=0; p<2; p++) release_peer(p);
     for(int p=0; p<2; p++) for(int i=0; i<3; i++) if (exec[p][i]) b200_fft1d_destroy(exec[p][i]);
+    for(int p=0; p<2; p++) for(int i=0; i<3; i++) if (bexec[p][i]) b200_fft1d_destroy(bexec[p][i]);
     if (own_workspace) cudaFree(own_workspace);
     if (counters) cudaFree(counters);
+    if (side_stream){ cudaStreamSynchronize(side_stream); cudaStreamDestroy(side_stream); }
+    if (fork_event) cudaEventDestroy(fork_event);
+    if (join_event) cudaEventDestroy(join_event);
     for(cudaEvent_t e : marks) cudaEventDestroy(e);
 }
 
@@ -284,9 +304,9 @@ bool transform3d::ensure_peer(int precision, int batch){
     int const cplx_bytes = 2 * real_bytes;
     bool const complex_data = (tkind == kind_c2c or tkind == kind_r2c);
     bool any = false;
+    int const nviews = lb_active ? 3 : 2;
     for(int s=0; s<4; s++){
-        P.fused[0][s] = shapes_differ(lp.in_shape[s], lp.out_shape[s]);
-        P.fused[1][s] = shapes_differ(lp.out_shape[3-s], lp.in_shape[3-s]);
+        for(int v=0; v<nviews; v++) P.fused[v][s] = shapes_differ(vin(v, s), vout(v, s));
         any = any or P.fused[0][s];
     }
     if (not any){ P.tried = true; return false; }
@@ -299,7 +319,10 @@ bool transform3d::ensure_peer(int precision, int batch){
     // rank: the buffers of a peer sit at known offsets inside its arena)
     idx largest = 1;
     for(int s=0; s<4; s++)
-        for(int r=0; r<n; r++) largest = std::max(largest, std::max(lp.in_shape[s][r].count(), lp.out_shape[s][r].count()));
+        for(int r=0; r<n; r++){
+            largest = std::max(largest, std::max(lp.in_shape[s][r].count(), lp.out_shape[s][r].count()));
+            if (lb_active) largest = std::max(largest, std::max(lb.in_shape[s][r].count(), lb.out_shape[s][r].count()));
+        }
     P.entry_bytes = ((static_cast<size_t>(largest) * (complex_data ? cplx_bytes : real_bytes) + 255) / 256) * 256;
     P.capacity = batch;
     P.buffer_bytes = P.entry_bytes * static_cast<size_t>(batch);
@@ -324,33 +347,31 @@ bool transform3d::ensure_peer(int precision, int batch){
     P.remote_slots.resize(n);
     for(int r=0; r<n; r++) P.remote_slots[r] = static_cast<char*>(arenas[r]) + sizeof(unsigned long long) * me;
 
-    // scatter maps: ((direction * 4 + stage) * 3 + buffer)
-    std::vector<scatter_map> maps(24);
+    // scatter maps: ((view * 4 + stage) * 3 + buffer)
+    std::vector<scatter_map> maps(36);
     std::string why;
     int built = 1;
-    for(int dir=0; dir<2 and built; dir++){
+    for(int view=0; view<nviews and built; view++){
         for(int st=0; st<4 and built; st++){
-            if (not P.fused[dir][st]) continue;
-            shape const &dest = (dir == 0) ? lp.out_shape[st] : lp.in_shape[3-st];
+            if (not P.fused[view][st]) continue;
+            shape const &dest = vout(view, st);
             // the box this rank writes in that stage, the axis of the transform in front of the reshape, the element size
-            box3 written;
+            box3 const written = vin(view, st)[me];
             int k_pos = 0, bytes = complex_data ? cplx_bytes : real_bytes;
             if (st == 0){
-                written = (dir == 0) ? lp.in_shape[0][me] : lp.out_shape[3][me];
-                if (tkind == kind_r2c and dir == 0) bytes = real_bytes;
+                if (tkind == kind_r2c and view == view_forward) bytes = real_bytes;
             }else{
-                int const e = (dir == 0) ? st - 1 : 3 - st;                 // executor in front of this reshape
-                written = (dir == 0) ? lp.in_shape[st][me] : lp.out_shape[3-st][me];
-                if (not written.empty()) k_pos = written.position_of(lp.fft_direction[e]);
-                if (tkind == kind_r2c and dir == 1 and e == 0) bytes = real_bytes;   // c2r output
+                int const e = st - 1;                                       // transform in front of this reshape
+                if (not written.empty()) k_pos = written.position_of(vdim(view, e));
+                if (tkind == kind_r2c and view == view_mirror and real_id(view, e) == 0) bytes = real_bytes;   // c2r output
             }
-            stage_elems[dir][st] = written.count();
-            sent_elems[dir][st] = 0;
-            for(int r=0; r<n; r++) if (r != me) sent_elems[dir][st] += written.overlap(dest[r]).count();
+            stage_elems[view][st] = written.count();
+            sent_elems[view][st] = 0;
+            for(int r=0; r<n; r++) if (r != me) sent_elems[view][st] += written.overlap(dest[r]).count();
             for(int w=0; w<3; w++){
                 std::vector<void*> bases(n);
                 for(int r=0; r<n; r++) bases[r] = static_cast<char*>(arenas[r]) + 4096 + static_cast<size_t>(w) * P.buffer_bytes;
-                if (not build_scatter_map(written, k_pos, dest, bases, bytes, maps[(dir * 4 + st) * 3 + w], why, nullptr, me)){ built = 0; break; }
+                if (not build_scatter_map(written, k_pos, dest, bases, bytes, maps[(view * 4 + st) * 3 + w], why, nullptr, me)){ built = 0; break; }
             }
         }
     }
@@ -365,7 +386,18 @@ bool transform3d::ensure_peer(int precision, int batch){
         release_peer(precision);
         return false;
     }
+    P.host_maps = maps;
     P.active = true;
+    return true;
+}
+
+bool transform3d::ensure_side_stream(){
+    if (side_stream != nullptr) return true;
+    if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess){ side_stream = nullptr; cudaGetLastError(); return false; }
+    if (cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming) != cudaSuccess or cudaEventCreateWithFlags(&join_event, cudaEventDisableTiming) != cudaSuccess){
+        cudaGetLastError();
+        return false;
+    }
     return true;
 }
 
@@ -437,31 +469,34 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
     int const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
     int const cplx_bytes = 2 * real_bytes;
     bool const complex_data = (tkind == kind_c2c or tkind == kind_r2c);
-    b200_fft1d_plan const *X = exec[precision];
-    static bool const allow_pair = (std::getenv("HEFFTE_B200_NO_PAIR") == nullptr);
+    static bool const allow_pair = (std::getenv("HEFFTE_B200_NO_OVERLAP") == nullptr);
     static bool const allow_direct = (std::getenv("HEFFTE_B200_NO_DIRECT_OUTPUT") == nullptr);
+    static int const thin_blocks = []{ const char *e = std::getenv("HEFFTE_B200_THIN_CTAS_PER_SM"); int const k = e ? std::atoi(e) : 2; return 148 * ((k > 0) ? k : 2); }();
+    bool const shared_device = (std::strcmp(ccomm->kind(), "threads") == 0) and std::getenv("HEFFTE_B200_OVERLAP_ON_SHARED_DEVICE") == nullptr;
     static bool const trace = (std::getenv("HEFFTE_B200_TRACE") != nullptr);
 
-    // the sequence of stages: (direction, stage); a convolution replaces the last forward stage and the first backward stage
-    // by the operator kernel, whose store is the reshape of backward stage 1
-    struct op { int dir, st; bool conv; };
+    // the sequence of stages: (view, stage), see transform.h; a convolution replaces the last forward stage and the first stage of
+    // the mirrored backward transform by the operator kernel, whose store is the reshape of that backward stage
+    struct op { int dir, st; bool conv; };      // dir: the view the stage belongs to
     std::vector<op> ops;
     if (mode == mode_convolve){
-        ops = {{0, 0, false}, {0, 1, false}, {0, 2, false}, {1, 1, true}, {1, 2, false}, {1, 3, false}};
+        ops = {{view_forward, 0, false}, {view_forward, 1, false}, {view_forward, 2, false}, {view_mirror, 1, true}, {view_mirror, 2, false}, {view_mirror, 3, false}};
     }else{
-        int const d = (mode == mode_backward) ? 1 : 0;
+        int const d = (mode == mode_backward) ? (lb_active ? view_backward : view_mirror) : view_forward;
         ops = {{d, 0, false}, {d, 1, false}, {d, 2, false}, {d, 3, false}};
     }
-    auto executor_of = [](op const &o){ return (o.dir == 0) ? o.st - 1 : 3 - o.st; };
+    auto executor_of = [](op const &o){ return o.st - 1; };           // index inside the view
+    auto X = [&](op const &o){ return vexec(precision, o.dir, o.st - 1); };
     auto map_of = [&](op const &o, int w){ return static_cast<const char*>(P.maps) + sizeof(scatter_map) * static_cast<size_t>((o.dir * 4 + o.st) * 3 + w); };
-    // element size on the input / output side of executor e run in direction dir
+    // element size on the input / output side of transform e of view `dir`
     auto bytes_of = [&](int e, int dir, bool output){
         if (tkind == kind_c2c) return cplx_bytes;
         if (tkind != kind_r2c) return real_bytes;
-        if (e != 0) return cplx_bytes;
-        return (output != (dir == 1)) ? cplx_bytes : real_bytes;   // r2c forward writes complex, c2r backward writes real
+        if (real_id(dir, e) != 0) return cplx_bytes;
+        return (output != (dir != view_forward)) ? cplx_bytes : real_bytes;   // r2c forward writes complex, c2r backward writes real
     };
-    bool const last_is_backward = (ops.back().dir == 1);
+    bool const last_is_backward = (ops.back().dir != view_forward);
+    int const last_view = ops.back().dir;
     int const in_unit = (mode == mode_backward) ? (complex_data ? cplx_bytes : real_bytes)
                                                 : ((tkind == kind_c2c) ? cplx_bytes : real_bytes);
     bool const real_out = (tkind == kind_r2c and last_is_backward) or not complex_data;
@@ -485,9 +520,9 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
         if (o.st == 0){
             // ---- the first reshape of a transform: a scatter copy ------------------------------------------------------------
             if (not fused) continue;
-            box3 const &box = (o.dir == 1) ? lp.out_shape[3][me] : lp.in_shape[0][me];
+            box3 const &box = vin(o.dir, 0)[me];
             int bytes = complex_data ? cplx_bytes : real_bytes;
-            if (tkind == kind_r2c and o.dir == 0) bytes = real_bytes;
+            if (tkind == kind_r2c and o.dir == view_forward) bytes = real_bytes;
             int const w = P.take();
             if (not box.empty()){
                 rc = b200_scatter_copy_batch(bytes, box.osize(0), box.osize(1), box.osize(2), box.osize(0), box.osize(0) * box.osize(1), cur, map_of(o, w),
@@ -502,11 +537,12 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
             continue;
         }
         int const e = executor_of(o);
-        int const direction = (o.dir == 1) ? B200_BACKWARD : B200_FORWARD;
+        int const direction = (o.dir != view_forward) ? B200_BACKWARD : B200_FORWARD;
+        b200_fft1d_plan const Xe = X(o);
         // the scaling rides on ONE stage of the plan -- a global choice: a rank whose box is empty in that stage must not scale
         // earlier, its data would be scaled again by the ranks that receive it.  Transforms: the last stage; operator: the product.
         double const stage_scale = (mode == mode_convolve) ? (o.conv ? scale : 1.0) : ((static_cast<int>(i) == last_fft_op) ? scale : 1.0);
-        bool const type_changes = (tkind == kind_r2c and e == 0);          // r2c / c2r cannot run in place
+        bool const type_changes = (tkind == kind_r2c and real_id(o.dir, e) == 0);          // r2c / c2r cannot run in place
         bool const is_last = (i + 1 == ops.size());
         bool later_fused = false;
         for(size_t t=i+1; t<ops.size(); t++) later_fused = later_fused or P.fused[ops[t].dir][ops[t].st];
@@ -522,27 +558,28 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
                 landed_direct = true;
             }
             if (trace) std::fprintf(stderr, "[b200 rank %d] stage (%d,%d) fused -> buffer %d\n", me, o.dir, o.st, w);
-            if (X[e]){
+            if (Xe){
                 if (o.conv){
-                    rc = b200_fft1d_execute_convolve(X[e], cur, nullptr, map_of(o, w), multiplier, stage_scale, cstream, batch, cur_step, 0, arena_entry, local_shift, local_step);
+                    rc = b200_fft1d_execute_convolve(Xe, cur, nullptr, map_of(o, w), multiplier, stage_scale, cstream, batch, cur_step, 0, arena_entry, local_shift, local_step);
                     if (rc == B200_ERR_UNSUPPORTED){
                         // no operator kernel for this axis: transform in place, multiply, and let the backward kernel carry the reshape
                         void *here = const_cast<void*>(cur);
                         if (cur_buffer < 0) return fail(B200_ERR_UNSUPPORTED, "the fused spectral operator needs the plan's buffers");
-                        rc = b200_fft1d_execute_batch(X[e], B200_FORWARD, cur, here, 1.0, cstream, batch, cur_step, cur_step);
+                        rc = b200_fft1d_execute_batch(Xe, B200_FORWARD, cur, here, 1.0, cstream, batch, cur_step, cur_step);
                         for(int b=0; b<batch and rc == 0; b++)
-                            rc = b200_pointwise_multiply(precision, lp.out_shape[e][me].count(), static_cast<char*>(here) + b * cur_step, multiplier, stage_scale, cstream);
-                        if (rc == 0) rc = b200_fft1d_execute_scatter_batch(X[e], B200_BACKWARD, cur, map_of(o, w), 1.0, cstream, batch, cur_step, arena_entry, local_shift, local_step);
+                            rc = b200_pointwise_multiply(precision, vout(o.dir, e)[me].count(), static_cast<char*>(here) + b * cur_step, multiplier, stage_scale, cstream);
+                        if (rc == 0) rc = b200_fft1d_execute_scatter_batch(Xe, B200_BACKWARD, cur, map_of(o, w), 1.0, cstream, batch, cur_step, arena_entry, local_shift, local_step);
                     }
                 }else{
-                    rc = b200_fft1d_execute_scatter_batch(X[e], direction, cur, map_of(o, w), stage_scale, cstream, batch, cur_step, arena_entry, local_shift, local_step);
+                    rc = b200_fft1d_execute_scatter_batch(Xe, direction, cur, map_of(o, w), stage_scale, cstream, batch, cur_step, arena_entry, local_shift, local_step);
                 }
                 if (rc) return rc;
             }
             {
                 char label[40];
-                std::snprintf(label, sizeof(label), o.conv ? "fft%d * ifft%d + reshape%d (fused)" : "fft%d + reshape%d (fused)", e, o.conv ? e : o.st, o.st);
-                long long const read_bytes = X[e] ? static_cast<long long>(lp.out_shape[e][me].count()) * bytes_of(e, o.dir, false) : 0;
+                int const axis = vdim(o.dir, e);      // the labels name the transformed dimension
+                std::snprintf(label, sizeof(label), o.conv ? "fft%d * ifft%d + reshape%d (fused)" : "fft%d + reshape%d (fused)", axis, o.conv ? axis : o.st, o.st);
+                long long const read_bytes = Xe ? static_cast<long long>(vout(o.dir, e)[me].count()) * bytes_of(e, o.dir, false) : 0;
                 long long const wrote = stage_elems[o.dir][o.st] * bytes_of(e, o.dir, true), sent = sent_elems[o.dir][o.st] * bytes_of(e, o.dir, true);
                 mark(label, batch * (read_bytes + wrote - sent), batch * sent);
             }
@@ -564,13 +601,15 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
         else if (cur_buffer >= 0 and not type_changes){ dst = const_cast<void*>(cur); dst_buffer = cur_buffer; dst_step = cur_step; }
         else{ dst_buffer = P.take(); dst = P.buffer(dst_buffer); dst_step = arena_entry; }
 
-        // followed by a fused stage of the same box: both in one persistent launch, this one hidden behind the transfers of the next
+        // followed by a fused stage of the same box: the two launches overlap on two streams, plane by plane -- this one, bound by
+        // HBM, hides behind the remote stores of the next, which runs with a thin grid (tools/kbench_peer.cu).  Ranks that are host
+        // threads sharing one GPU keep the launches apart: their thin kernels together could occupy every SM while they wait.
         bool paired = false;
-        if (allow_pair and not o.conv and i + 1 < ops.size() and tkind == kind_c2c and X[e]){
+        if (allow_pair and not shared_device and not o.conv and i + 1 < ops.size() and tkind == kind_c2c and Xe){
             op const &next = ops[i + 1];
             int const e2 = executor_of(next);
-            if (P.fused[next.dir][next.st] and not next.conv and next.dir == o.dir and X[e2] and b200_fft1d_pairable(X[e], X[e2])){
-                box3 const &box = lp.out_shape[e][me];
+            if (P.fused[next.dir][next.st] and not next.conv and next.dir == o.dir and X(next) and b200_fft1d_overlappable(Xe, X(next)) and ensure_side_stream()){
+                box3 const &box = vout(o.dir, e)[me];
                 void *planes = pair_counters(static_cast<size_t>(box.osize(2)) * batch);
                 if (planes != nullptr){
                     bool const next_last = (i + 2 == ops.size());
@@ -581,13 +620,15 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
                         local_step = out_entry - arena_entry;
                     }
                     double const next_scale = (mode != mode_convolve and static_cast<int>(i + 1) == last_fft_op) ? scale : 1.0;
-                    rc = b200_fft1d_execute_pair(X[e], X[e2], direction, cur, dst, map_of(next, w), next_scale, planes, 0, cstream,
-                                                 batch, cur_step, dst_step, arena_entry, local_shift, local_step);
+                    int const nb = P.host_maps[static_cast<size_t>((next.dir * 4 + next.st) * 3 + w)].nb;
+                    rc = b200_fft1d_execute_overlapped(Xe, X(next), direction, cur, dst, map_of(next, w), nb, next_scale, planes, cstream, side_stream,
+                                                       fork_event, join_event, batch, cur_step, dst_step, arena_entry, local_shift, local_step, thin_blocks);
                     if (rc == B200_SUCCESS){
                         paired = true;
                         if (next_last and allow_direct) landed_direct = true;
+                        if (trace) std::fprintf(stderr, "[b200 rank %d] stages (%d,%d) and (%d,%d) overlapped -> buffer %d\n", me, o.dir, o.st, next.dir, next.st, w);
                         char label[40];
-                        std::snprintf(label, sizeof(label), "fft%d + fft%d + reshape%d (paired)", e, e2, next.st);
+                        std::snprintf(label, sizeof(label), "fft%d | fft%d + reshape%d (overlapped)", vdim(o.dir, e), vdim(next.dir, e2), next.st);
                         long long const count = box.count();
                         long long const wrote = stage_elems[next.dir][next.st] * cplx_bytes, sent = sent_elems[next.dir][next.st] * cplx_bytes;
                         mark(label, batch * (3 * count * cplx_bytes + wrote - sent), batch * sent);
@@ -603,27 +644,29 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
         }
         if (paired) continue;
 
-        if (X[e]){
+        if (Xe){
             if (o.conv){
-                rc = b200_fft1d_execute_convolve(X[e], cur, dst, nullptr, multiplier, stage_scale, cstream, batch, cur_step, dst_step, 0, 0, 0);
+                rc = b200_fft1d_execute_convolve(Xe, cur, dst, nullptr, multiplier, stage_scale, cstream, batch, cur_step, dst_step, 0, 0, 0);
                 if (rc == B200_ERR_UNSUPPORTED){
-                    rc = b200_fft1d_execute_batch(X[e], B200_FORWARD, cur, dst, 1.0, cstream, batch, cur_step, dst_step);
+                    rc = b200_fft1d_execute_batch(Xe, B200_FORWARD, cur, dst, 1.0, cstream, batch, cur_step, dst_step);
                     for(int b=0; b<batch and rc == 0; b++)
-                        rc = b200_pointwise_multiply(precision, lp.out_shape[e][me].count(), static_cast<char*>(dst) + b * dst_step, multiplier, stage_scale, cstream);
-                    if (rc == 0) rc = b200_fft1d_execute_batch(X[e], B200_BACKWARD, dst, dst, 1.0, cstream, batch, dst_step, dst_step);
+                        rc = b200_pointwise_multiply(precision, vout(o.dir, e)[me].count(), static_cast<char*>(dst) + b * dst_step, multiplier, stage_scale, cstream);
+                    if (rc == 0) rc = b200_fft1d_execute_batch(Xe, B200_BACKWARD, dst, dst, 1.0, cstream, batch, dst_step, dst_step);
                 }
             }else{
-                rc = b200_fft1d_execute_batch(X[e], direction, cur, dst, stage_scale, cstream, batch, cur_step, dst_step);
+                rc = b200_fft1d_execute_batch(Xe, direction, cur, dst, stage_scale, cstream, batch, cur_step, dst_step);
             }
             if (rc) return rc;
         }
         {   // the mark is emitted on every rank, also with an empty box: all ranks report the same list of stages
             char label[40];
-            std::snprintf(label, sizeof(label), o.conv ? "fft%d * ifft%d (local)" : "fft%d (local)", e, e);
-            long long const count = X[e] ? lp.out_shape[e][me].count() : 0;
-            long long const half = X[e] ? lp.in_shape[1][me].count() : 0;
-            long long const out_count = (tkind == kind_r2c and e == 0) ? ((o.dir == 1) ? count : half) : count;
-            long long const in_count = (tkind == kind_r2c and e == 0 and o.dir == 1) ? half : count;
+            std::snprintf(label, sizeof(label), o.conv ? "fft%d * ifft%d (local)" : "fft%d (local)", vdim(o.dir, e), vdim(o.dir, e));
+            bool const real_stage = (tkind == kind_r2c and real_id(o.dir, e) == 0);
+            // the real transform of an r2c plan: real box lp.out_shape[0], shortened complex box lp.in_shape[1]
+            long long const count = Xe ? (real_stage ? lp.out_shape[0][me].count() : vout(o.dir, e)[me].count()) : 0;
+            long long const half = Xe ? lp.in_shape[1][me].count() : 0;
+            long long const out_count = real_stage ? ((o.dir != view_forward) ? count : half) : count;
+            long long const in_count = (real_stage and o.dir != view_forward) ? half : count;
             mark(label, batch * (in_count * bytes_of(e, o.dir, false) + out_count * bytes_of(e, o.dir, true)), 0);
         }
         cur = dst; cur_buffer = dst_buffer; cur_step = dst_step;     // also without a transform (empty box): every rank follows the same buffers
@@ -632,8 +675,8 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
     if (cur != out and landed_direct){
         // what the other GPUs sent sits in the arena at its final position inside my box: move those sub-boxes only, all of
         // them and all batch entries in one launch
-        shape const &from = last_is_backward ? lp.out_shape[0] : lp.in_shape[3];
-        box3 const &mine = last_is_backward ? lp.in_shape[0][me] : lp.out_shape[3][me];
+        shape const &from = vin(last_view, 3);
+        box3 const &mine = vout(last_view, 3)[me];
         std::vector<long long> offsets, nf, nm, ns;
         long long moved = 0;
         for(int r=0; r<ccomm->size() and not mine.empty(); r++){
@@ -781,6 +824,19 @@ int transform3d::ensure_executors(int precision){
             }else d.kind = B200_C2C;
         }else d.kind = static_cast<int>(tkind);
         int rc = b200_fft1d_create(&d, &exec[precision][i]);
+        if (rc) return rc;
+    }
+    for(int i=0; i<3 and lb_active; i++){
+        box3 const &box = lb.out_shape[i][me];
+        if (box.empty()) continue;
+        int const dim = lb.fft_direction[i];
+        b200_fft1d_desc d{};
+        d.precision = precision;
+        d.n = box.size(dim);
+        line_layout(box, dim, d.in, d.count_a, d.count_b);
+        d.out = d.in;
+        d.kind = static_cast<int>(tkind);
+        int rc = b200_fft1d_create(&d, &bexec[precision][i]);
         if (rc) return rc;
     }
     exec_ready[precision] = true;

@@ -118,21 +118,40 @@ private:
         std::vector<void*> arenas;             // address of every rank's arena as seen from this device
         std::vector<void*> remote_slots;       // my slot in every rank's flag array
         unsigned long long epoch = 0;
-        void *maps = nullptr;                  // device array of scatter maps, index ((direction * 4 + stage) * 3 + buffer)
+        void *maps = nullptr;                  // device array of scatter maps, index ((view * 4 + stage) * 3 + buffer)
+        std::vector<scatter_map> host_maps;    // host copy (the plan reads the cell counts)
         int next_buffer = 0;                   // the three buffers rotate: every remote write targets the buffer after the last one used
-        bool fused[2][4] = {{false, false, false, false}, {false, false, false, false}};   // reshape of that stage moves data (global fact)
+        bool fused[3][4] = {{false, false, false, false}, {false, false, false, false}, {false, false, false, false}};   // [view][stage]: the reshape moves data (global fact)
         char* buffer(int index) const { return static_cast<char*>(arena) + 4096 + static_cast<size_t>(index) * buffer_bytes; }
         int take(){ int const w = next_buffer; next_buffer = (next_buffer + 1) % 3; return w; }
     };
     peer_state peer[2];
-    long long sent_elems[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};     // elements that leave this GPU in stage (direction, st)
-    long long stage_elems[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};    // elements this rank writes in that stage
+    long long sent_elems[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};     // elements that leave this GPU in stage (view, st)
+    long long stage_elems[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};    // elements this rank writes in that stage
+    // The stages of a run as a forward-shaped sequence (reshape s, then the transform of stage s).  view 0: the forward transform;
+    // view 1: the backward transform as the mirror image of the forward plan (what r2c plans and the spectral operator need);
+    // view 2: the backward transform planned like a forward transform from the output boxes to the input boxes (`lb`): the
+    // purely local transforms then come FIRST, where they overlap with the transfers of the stage behind them, instead of last.
+    enum { view_forward = 0, view_mirror = 1, view_backward = 2 };
+    logic_plan lb;
+    bool lb_active = false;
+    b200_fft1d_plan bexec[2][3];
+    shape const& vin(int view, int s) const { return (view == view_forward) ? lp.in_shape[s] : ((view == view_mirror) ? lp.out_shape[3-s] : lb.in_shape[s]); }
+    shape const& vout(int view, int s) const { return (view == view_forward) ? lp.out_shape[s] : ((view == view_mirror) ? lp.in_shape[3-s] : lb.out_shape[s]); }
+    int vdim(int view, int e) const { return (view == view_forward) ? lp.fft_direction[e] : ((view == view_mirror) ? lp.fft_direction[2-e] : lb.fft_direction[e]); }
+    int real_id(int view, int e) const { return (view == view_mirror) ? 2 - e : e; }      // which executor of the r2c chain this is
+    b200_fft1d_plan vexec(int precision, int view, int e) const {
+        return (view == view_forward) ? exec[precision][e] : ((view == view_mirror) ? exec[precision][2-e] : bexec[precision][e]);
+    }
     bool timing = false;
     std::vector<cudaEvent_t> marks;
     std::vector<stage_record> pending;
     void mark(const char *name, long long local_bytes, long long sent_bytes);
-    void *counters = nullptr;           // per-plane counters of the paired kernel
+    void *counters = nullptr;           // per-plane counters of two overlapped launches
     size_t counters_count = 0;
+    cudaStream_t side_stream = nullptr; // the local transform of an overlapped pair runs here
+    cudaEvent_t fork_event = nullptr, join_event = nullptr;
+    bool ensure_side_stream();
 
     transform_kind tkind;
     int r2c_dir;

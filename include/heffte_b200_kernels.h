@@ -131,6 +131,21 @@ int b200_fft1d_execute_pair(b200_fft1d_plan first, b200_fft1d_plan second, int d
                             const void *device_scatter_map, double scale, void *counters, int lag, void *stream,
                             int batch, long long in_step, long long mid_step, long long scatter_step, long long local_shift, long long local_step);
 /*
+ * The same idea with TWO launches on TWO streams (what the plan uses): the first, local transform runs on `side_stream` and
+ * reports the planes it has stored; the second transform -- with a fused reshape, bound by NVLink -- runs on `stream` with a thin
+ * grid (`thin_blocks` CTAs walking the tiles) and waits plane by plane, so the HBM traffic of the first hides behind the remote
+ * stores of the second (tools/kbench_peer.cu: a thin remote-store kernel and an HBM-bound kernel overlap almost perfectly).
+ * fork_event / join_event: two cudaEvent_t of the caller, used to order side_stream after the work in front and to join it.  map_nb: the number of destination ranges of
+ * the scatter map along the slowest axis (the producer visits the planes in the consumer's order).  Any two complex fast-path
+ * transforms of the same box that are not along its slowest axis (b200_fft1d_overlappable() == 1).
+ */
+int b200_fft1d_overlappable(b200_fft1d_plan first, b200_fft1d_plan second);
+int b200_fft1d_execute_overlapped(b200_fft1d_plan first, b200_fft1d_plan second, int direction, const void *in, void *mid,
+                                  const void *device_scatter_map, int map_nb, double scale, void *counters, void *stream, void *side_stream,
+                                  void *fork_event, void *join_event,
+                                  int batch, long long in_step, long long mid_step, long long scatter_step, long long local_shift, long long local_step,
+                                  int thin_blocks);
+/*
  * Fused spectral operator along the axis of the plan: forward transform, spectrum * scale * M, backward transform of every line
  * in ONE pass over memory, M = the spectrum itself (multiplier == NULL, the x[i] *= x[i] of the reference's
  * benchmarks/convolution.cpp:89-94) or a device array with the layout of the input box.  The result goes to `out` (may alias

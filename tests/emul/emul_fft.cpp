@@ -8,6 +8,7 @@
 namespace {
 struct emul_launcher {
     int batch = 1;
+    long long max_blocks = 0;
     template<typename kernel_t, typename args_t>
     int launch(kernel_t kernel, long long blocks, int threads, size_t smem, args_t const &args){
         emul::launch(kernel, dim3((unsigned) blocks, (unsigned) batch), dim3((unsigned) threads), smem, args);

@@ -20,6 +20,9 @@ def main():
         os.environ["HEFFTE_B200_DISABLE_P2P"] = "1"
     else:
         os.environ.pop("HEFFTE_B200_DISABLE_P2P", None)
+    # emulated launches are synchronous, so the two-stream overlap of a local and a fused transform (kept off for ranks that
+    # share a real GPU) is safe to exercise here
+    os.environ["HEFFTE_B200_OVERLAP_ON_SHARED_DEVICE"] = "1"
     from tests.emul.build_emul_library import build
     from heffte_b200 import _lib
     _lib.LIB_PATH = build()          # the emulated library stands in for libheffte_b200.so in THIS process only

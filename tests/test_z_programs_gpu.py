@@ -40,7 +40,7 @@ def test_subcomm_plans_on_thread_ranks(lib, nranks):
 
 
 @pytest.mark.parametrize("prec", [0, 1])
-@pytest.mark.parametrize("length", [96, 192, 384, 768, 1536, 80, 160, 320, 640, 1280, 200, 400, 500, 1000, 2000])
+@pytest.mark.parametrize("length", [96, 192, 384, 768, 1536, 80, 160, 320, 640, 1280, 200, 400, 500, 1000, 2000, 48, 100, 112, 224, 448, 896, 1792, 3584])
 def test_c2c_mixed_radix_lengths(lib, prec, length):
     """lengths with factors 3 and 5 on the register / shared-memory kernels (radices 3, 5, 6, 10, 12): contiguous and strided"""
     import numpy as np
@@ -59,7 +59,7 @@ def test_c2c_mixed_radix_lengths(lib, prec, length):
 
 
 @pytest.mark.parametrize("prec", [0, 1])
-@pytest.mark.parametrize("half", [96, 192, 384, 768, 1536, 80, 160, 320, 640, 1280, 200, 400, 500, 1000, 2000])
+@pytest.mark.parametrize("half", [96, 192, 384, 768, 1536, 80, 160, 320, 640, 1280, 200, 400, 500, 1000, 2000, 112, 224, 448, 896, 1792])
 def test_real_mixed_radix_lengths(lib, prec, half):
     """real transforms of length 2 * (a mixed c2c length): r2c / c2r / DCT / DST on the half-length mixed-radix engine"""
     import numpy as np
