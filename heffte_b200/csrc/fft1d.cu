@@ -2,7 +2,11 @@
 // Replaces heffte::plan_cufft / plan_cufft_r2c and the cufftExec* calls
 // (reference: include/heffte_backend_cuda.h:346-422, 494-524, 580-621, 694-727).
 #include "fft_host_plan.h"
+#include "composite.cuh"
 #include "runtime.h"
+
+#include <complex>
+#include <memory>
 
 #include <cstring>
 
@@ -75,10 +79,238 @@ int cuda_launcher::run_generic(bool is_float, long long blocks, int threads, siz
 
 using namespace b200;
 
+// the composite engine (composite.cuh): any length through sub-plans over a workspace
+struct composite_plan {
+    long long engine = 0;        // length of the complex sequence built from a line: n, or 2 (n - 1) for the type-I cosine transform
+    long long m_fft = 0, n1 = 0, n2 = 1;
+    long long L = 0;             // lines per chunk
+    bool bluestein = false;
+    b200_fft1d_plan sub_a = nullptr, sub_c = nullptr;
+    void *work = nullptr, *twiddle = nullptr, *chirp = nullptr, *bhat = nullptr, *w4n = nullptr;
+    ~composite_plan(){
+        if (sub_a) b200_fft1d_destroy(sub_a);
+        if (sub_c) b200_fft1d_destroy(sub_c);
+        for(void *p : {work, twiddle, chirp, bhat, w4n}) if (p) cudaFree(p);
+    }
+};
+
 struct b200_fft1d_plan_s {
     host_plan host;
     void *twiddle = nullptr;   // device table
+    std::unique_ptr<composite_plan> composite;
 };
+
+namespace {
+
+int largest_prime_factor(long long m){
+    long long best = 1;
+    for(long long p = 2; p * p <= m; p++) while(m % p == 0){ best = p; m /= p; }
+    return static_cast<int>(std::max(best, m));
+}
+// lengths a sub-plan serves well: the register / shared-memory kernels, or the generic kernel with small prime factors
+bool good_sub_length(long long n){ return n >= 2 and n <= 4096 and (is_fast_length(n) or largest_prime_factor(n) <= 61); }
+
+// m = n1 * n2 with both factors good sub-plan lengths, as balanced as possible; false when there is no such split
+bool split_length(long long m, long long &n1, long long &n2){
+    long long root = 1;
+    while((root + 1) * (root + 1) <= m) root++;
+    for(long long d = root; d >= 2; d--){
+        if (m % d != 0) continue;
+        if (good_sub_length(d) and good_sub_length(m / d)){ n1 = m / d; n2 = d; return true; }
+    }
+    return false;
+}
+
+template<typename T>
+int upload(std::vector<std::complex<long double>> const &host, void **device){
+    std::vector<T> flat(2 * host.size());
+    for(size_t i=0; i<host.size(); i++){ flat[2*i] = static_cast<T>(host[i].real()); flat[2*i+1] = static_cast<T>(host[i].imag()); }
+    int rc = check_cuda(cudaMalloc(device, flat.size() * sizeof(T)), "cudaMalloc(composite table)");
+    if (rc == 0) rc = check_cuda(cudaMemcpy(*device, flat.data(), flat.size() * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy(composite table)");
+    return rc;
+}
+
+// in-place radix-2 transform of a power-of-two sequence on the host (plan time only: the chirp of Bluestein's algorithm)
+void host_fft(std::vector<std::complex<long double>> &x){
+    size_t const n = x.size();
+    for(size_t i=1, j=0; i<n; i++){
+        size_t bit = n >> 1;
+        for(; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(x[i], x[j]);
+    }
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for(size_t len = 2; len <= n; len <<= 1){
+        std::vector<std::complex<long double>> w(len / 2);
+        for(size_t k=0; k<len/2; k++) w[k] = std::complex<long double>(cosl(2 * pi * k / len), -sinl(2 * pi * k / len));
+        for(size_t i=0; i<n; i+=len)
+            for(size_t k=0; k<len/2; k++){
+                std::complex<long double> const u = x[i+k], v = x[i+k+len/2] * w[k];
+                x[i+k] = u + v; x[i+k+len/2] = u - v;
+            }
+    }
+}
+
+template<typename T>
+int build_composite(b200_fft1d_plan_s &plan, long long engine){
+    std::unique_ptr<composite_plan> c(new composite_plan());
+    b200_fft1d_desc const &d = plan.host.desc;
+    c->engine = engine;
+    const long double pi = 3.141592653589793238462643383279502884L;
+    if (good_sub_length(engine)){ c->m_fft = engine; c->n1 = engine; c->n2 = 1; }
+    else if (split_length(engine, c->n1, c->n2)) c->m_fft = engine;
+    else{
+        c->bluestein = true;
+        c->m_fft = 16;
+        while(c->m_fft < 2 * engine - 1) c->m_fft *= 2;
+        if (c->m_fft <= 4096){ c->n1 = c->m_fft; c->n2 = 1; }
+        else{
+            c->n1 = 1;
+            while(c->n1 * c->n1 < c->m_fft) c->n1 *= 2;
+            c->n2 = c->m_fft / c->n1;
+            if (c->n1 > 4096 or c->n2 > 4096) return fail(B200_ERR_UNSUPPORTED, "transform length beyond the composite engine (about 8 million points)");
+        }
+    }
+    size_t const csize = sizeof(T) * 2;
+    long long const nlines = std::max<long long>(1, d.count_a * d.count_b);
+    // a chunk of lines whose workspace stays below 256 MB
+    long long L = std::max<long long>(1, (256LL << 20) / static_cast<long long>(csize * c->m_fft));
+    L = std::min<long long>(L, nlines);
+    if (L > 8) L -= L % 8;
+    c->L = L;
+    int rc = check_cuda(cudaMalloc(&c->work, csize * static_cast<size_t>(c->m_fft) * static_cast<size_t>(L)), "cudaMalloc(composite workspace)");
+    if (rc) return rc;
+    // sub-plans over the workspace [position][line]
+    {
+        b200_fft1d_desc a{};
+        a.precision = d.precision; a.kind = B200_C2C;
+        a.n = c->n1;
+        a.in = b200_line_geom{c->n2 * L, 1, 0}; a.out = a.in;
+        a.count_a = c->n2 * L; a.count_b = 1;
+        rc = b200_fft1d_create(&a, &c->sub_a);
+        if (rc) return rc;
+        if (c->n2 > 1){
+            b200_fft1d_desc s{};
+            s.precision = d.precision; s.kind = B200_C2C;
+            s.n = c->n2;
+            s.in = b200_line_geom{L, 1, c->n2 * L}; s.out = s.in;
+            s.count_a = L; s.count_b = c->n1;
+            rc = b200_fft1d_create(&s, &c->sub_c);
+            if (rc) return rc;
+        }
+    }
+    if (c->n2 > 1){
+        std::vector<std::complex<long double>> tw(static_cast<size_t>(c->m_fft));
+        for(long long t=0; t<c->m_fft; t++){
+            long double const angle = 2 * pi * static_cast<long double>(t) / static_cast<long double>(c->m_fft);
+            tw[t] = std::complex<long double>(cosl(angle), -sinl(angle));
+        }
+        rc = upload<T>(tw, &c->twiddle);
+        if (rc) return rc;
+    }
+    if (c->bluestein){
+        // w_j = exp(-i pi j^2 / E), the angle reduced through j^2 mod 2E
+        std::vector<std::complex<long double>> w(static_cast<size_t>(engine));
+        for(long long j=0; j<engine; j++){
+            long long const r = static_cast<long long>((static_cast<unsigned __int128>(j) * static_cast<unsigned __int128>(j)) % static_cast<unsigned __int128>(2 * engine));
+            long double const angle = pi * static_cast<long double>(r) / static_cast<long double>(engine);
+            w[j] = std::complex<long double>(cosl(angle), -sinl(angle));
+        }
+        rc = upload<T>(w, &c->chirp);
+        if (rc) return rc;
+        std::vector<std::complex<long double>> b(static_cast<size_t>(c->m_fft), std::complex<long double>(0, 0));
+        b[0] = std::conj(w[0]);
+        for(long long j=1; j<engine; j++){ b[j] = std::conj(w[j]); b[c->m_fft - j] = std::conj(w[j]); }
+        host_fft(b);
+        std::vector<std::complex<long double>> placed(b.size());
+        for(long long k=0; k<c->m_fft; k++){
+            long long const pos = (c->n2 == 1) ? k : (k % c->n1) * c->n2 + k / c->n1;
+            placed[pos] = b[k] / static_cast<long double>(c->m_fft);
+        }
+        rc = upload<T>(placed, &c->bhat);
+        if (rc) return rc;
+    }
+    if (d.kind == B200_COS or d.kind == B200_SIN){
+        std::vector<std::complex<long double>> q(static_cast<size_t>(d.n + 1));
+        for(long long k=0; k<=d.n; k++){
+            long double const angle = 2 * pi * static_cast<long double>(k) / static_cast<long double>(4 * d.n);
+            q[k] = std::complex<long double>(cosl(angle), -sinl(angle));
+        }
+        rc = upload<T>(q, &c->w4n);
+        if (rc) return rc;
+    }
+    plan.composite = std::move(c);
+    return B200_SUCCESS;
+}
+
+// one chunk after the other: gather, transform the workspace, scatter back
+int run_composite(b200_fft1d_plan_s const &plan, int direction, const void *in, void *out, double scale, cudaStream_t stream,
+                  const void *scatter, batch_shift shift){
+    composite_plan const &c = *plan.composite;
+    b200_fft1d_desc const &d = plan.host.desc;
+    bool const backward = (direction == B200_BACKWARD);
+    bool const is_float = (d.precision == B200_PREC_FLOAT);
+    composite_args a{};
+    generic_args &g = a.g;
+    g.in = in; g.out = out; g.twiddle = nullptr;
+    g.ig = to_geom(backward ? d.out : d.in);
+    g.og = to_geom(backward ? d.in : d.out);
+    g.nlines = d.count_a * d.count_b;
+    g.count_a = static_cast<int>(d.count_a);
+    g.backward = backward ? 1 : 0;
+    g.scale = scale;
+    g.n = static_cast<int>(d.n);
+    g.m = static_cast<int>(c.engine);
+    g.smap = static_cast<const scatter_map*>(scatter);
+    switch(d.kind){
+        case B200_C2C:  g.mode = mode_c2c; break;
+        case B200_R2C:  g.mode = backward ? mode_c2r : mode_r2c; break;
+        case B200_COS:  g.mode = backward ? mode_dct3 : mode_dct2; break;
+        case B200_SIN:  g.mode = backward ? mode_dst3 : mode_dst2; break;
+        default:        g.mode = mode_dct1; break;
+    }
+    a.work = c.work; a.L = c.L; a.m_fft = c.m_fft; a.n1 = c.n1; a.n2 = c.n2;
+    a.twiddle = c.twiddle; a.chirp = c.chirp; a.bhat = c.bhat; a.w4n = c.w4n;
+    a.shift = shift;
+    cuda_launcher L{stream};
+    long long const cells = c.m_fft * c.L;
+    long long const blocks = std::max<long long>(1, std::min<long long>((cells + 255) / 256, 148LL * 16));
+    auto launch = [&](int which){
+        switch(which){
+            case 0: return is_float ? L.launch(composite_load_kernel<float>, blocks, 256, 0, a) : L.launch(composite_load_kernel<double>, blocks, 256, 0, a);
+            case 1: return is_float ? L.launch(composite_twiddle_kernel<float>, blocks, 256, 0, a) : L.launch(composite_twiddle_kernel<double>, blocks, 256, 0, a);
+            case 2: return is_float ? L.launch(composite_pointwise_kernel<float>, blocks, 256, 0, a) : L.launch(composite_pointwise_kernel<double>, blocks, 256, 0, a);
+            default: return is_float ? L.launch(composite_store_kernel<float>, blocks, 256, 0, a) : L.launch(composite_store_kernel<double>, blocks, 256, 0, a);
+        }
+    };
+    for(long long line0 = 0; line0 < g.nlines; line0 += c.L){
+        a.line0 = line0;
+        a.lines = std::min<long long>(c.L, g.nlines - line0);
+        int rc = launch(0);
+        // forward four-step: sub-transforms of length n1, twiddles, sub-transforms of length n2
+        if (rc == 0) rc = b200_fft1d_execute(c.sub_a, B200_FORWARD, c.work, c.work, 1.0, stream);
+        if (rc == 0 and c.n2 > 1){
+            a.conjugate = 0;
+            rc = launch(1);
+            if (rc == 0) rc = b200_fft1d_execute(c.sub_c, B200_FORWARD, c.work, c.work, 1.0, stream);
+        }
+        if (rc == 0 and c.bluestein){
+            rc = launch(2);
+            // back: the steps undone in reverse order (permuted order in, natural order out)
+            if (rc == 0 and c.n2 > 1){
+                rc = b200_fft1d_execute(c.sub_c, B200_BACKWARD, c.work, c.work, 1.0, stream);
+                a.conjugate = 1;
+                if (rc == 0) rc = launch(1);
+            }
+            if (rc == 0) rc = b200_fft1d_execute(c.sub_a, B200_BACKWARD, c.work, c.work, 1.0, stream);
+        }
+        if (rc == 0) rc = launch(3);
+        if (rc) return rc;
+    }
+    return B200_SUCCESS;
+}
+
+} // namespace
 
 extern "C" {
 
@@ -125,6 +357,20 @@ int b200_fft1d_create(const b200_fft1d_desc *desc, b200_fft1d_plan *out){
     auto *plan = new b200_fft1d_plan_s();
     const char *why = "";
     int rc = make_host_plan(*desc, plan->host, &why);
+    // lines beyond the shared-memory engine, and lines with a large prime factor (O(N p) in the generic kernel), take the
+    // composite engine: four-step over sub-plans, Bluestein for lengths that do not split (composite.cuh)
+    bool const too_long = (rc == B200_ERR_UNSUPPORTED and std::strstr(why, "shared-memory engine") != nullptr);
+    bool const awkward = (rc == B200_SUCCESS and plan->host.family == family_generic and largest_prime_factor(plan->host.m) >= 128 and
+                          std::getenv("HEFFTE_B200_NO_COMPOSITE") == nullptr);
+    if (too_long or awkward){
+        if (b200_device_count() < 1){ delete plan; return fail(B200_ERR_NO_DEVICE, "no CUDA device: the b200 backend has no CPU fallback"); }
+        plan->host.desc = *desc;
+        long long const engine = (desc->kind == B200_COS1) ? 2 * (desc->n - 1) : desc->n;
+        rc = (desc->precision == B200_PREC_FLOAT) ? build_composite<float>(*plan, engine) : build_composite<double>(*plan, engine);
+        if (rc){ delete plan; return rc; }
+        *out = plan;
+        return B200_SUCCESS;
+    }
     if (rc){ delete plan; return fail(rc, why); }
     if (b200_device_count() < 1){ delete plan; return fail(B200_ERR_NO_DEVICE, "no CUDA device: the b200 backend has no CPU fallback"); }
     size_t bytes = 0;
@@ -153,6 +399,7 @@ int b200_fft1d_destroy(b200_fft1d_plan plan){
 
 const char* b200_fft1d_kernel_name(b200_fft1d_plan plan){
     if (plan == nullptr) return "null";
+    if (plan->composite) return plan->composite->bluestein ? "composite (Bluestein)" : "composite (four-step)";
     switch(plan->host.family){
         case family_strided: return "strided";
         case family_contig: return "contig";
@@ -164,6 +411,7 @@ const char* b200_fft1d_kernel_name(b200_fft1d_plan plan){
 
 int b200_fft1d_execute(b200_fft1d_plan plan, int direction, const void *in, void *out, double scale, void *stream){
     if (plan == nullptr) return fail(B200_ERR_INVALID, "null plan");
+    if (plan->composite) return run_composite(*plan, direction, in, out, scale, static_cast<cudaStream_t>(stream), nullptr, batch_shift{0, 0});
     cuda_launcher L{static_cast<cudaStream_t>(stream)};
     int rc = run_host_plan(plan->host, plan->twiddle, direction, in, out, scale, L);
     if (rc == -1) return fail(B200_ERR_UNSUPPORTED, "no kernel for this length");
@@ -172,6 +420,7 @@ int b200_fft1d_execute(b200_fft1d_plan plan, int direction, const void *in, void
 
 int b200_fft1d_execute_range(b200_fft1d_plan plan, int direction, const void *in, void *out, double scale, void *stream, long long b_begin, long long b_count){
     if (plan == nullptr) return fail(B200_ERR_INVALID, "null plan");
+    if (plan->composite) return fail(B200_ERR_UNSUPPORTED, "line ranges are not available for composite plans");
     if (b_count < 0) return fail(B200_ERR_INVALID, "negative line count");
     cuda_launcher L{static_cast<cudaStream_t>(stream)};
     int rc = run_host_plan(plan->host, plan->twiddle, direction, in, out, scale, L, nullptr, b_begin, b_count);
@@ -348,6 +597,14 @@ int b200_fft1d_execute_batch(b200_fft1d_plan plan, int direction, const void *in
                              int batch, long long in_step, long long out_step){
     if (plan == nullptr) return fail(B200_ERR_INVALID, "null plan");
     if (batch < 1) return fail(B200_ERR_INVALID, "batch must be positive");
+    if (plan->composite){
+        for(int e=0; e<batch; e++){
+            int rc = run_composite(*plan, direction, static_cast<const char*>(in) + e * in_step, static_cast<char*>(out) + e * out_step, scale,
+                                   static_cast<cudaStream_t>(stream), nullptr, batch_shift{0, 0});
+            if (rc) return rc;
+        }
+        return B200_SUCCESS;
+    }
     cuda_launcher L{static_cast<cudaStream_t>(stream)};
     batch_steps steps; steps.batch = batch; steps.in_step = in_step; steps.out_step = out_step;
     int rc = run_host_plan(plan->host, plan->twiddle, direction, in, out, scale, L, nullptr, 0, -1, steps);
@@ -359,6 +616,14 @@ int b200_fft1d_execute_scatter_batch(b200_fft1d_plan plan, int direction, const 
                                      int batch, long long in_step, long long scatter_step, long long local_shift, long long local_step){
     if (plan == nullptr or device_scatter_map == nullptr) return fail(B200_ERR_INVALID, "null plan or scatter map");
     if (batch < 1) return fail(B200_ERR_INVALID, "batch must be positive");
+    if (plan->composite){
+        for(int e=0; e<batch; e++){
+            int rc = run_composite(*plan, direction, static_cast<const char*>(in) + e * in_step, nullptr, scale, static_cast<cudaStream_t>(stream),
+                                   device_scatter_map, batch_shift{e * scatter_step, local_shift + e * local_step});
+            if (rc) return rc;
+        }
+        return B200_SUCCESS;
+    }
     cuda_launcher L{static_cast<cudaStream_t>(stream)};
     batch_steps steps; steps.batch = batch; steps.in_step = in_step; steps.scatter_step = scatter_step; steps.local_shift = local_shift; steps.local_step = local_step;
     int rc = run_host_plan(plan->host, plan->twiddle, direction, in, nullptr, scale, L, device_scatter_map, 0, -1, steps);

@@ -1693,6 +1693,78 @@ __device__ __forceinline__ cplx<T> generic_load(generic_args const &a, const voi
     }
 }
 
+// element i (0 <= i < m) of the complex engine input of the line at element offset `off`, every mode; w4n: W_{4n}^k, k < n
+template<typename T>
+__device__ __forceinline__ cplx<T> generic_input(generic_args const &a, long long off, int i, const cplx<T> *w4n){
+    const int n = a.n, m = a.m;
+    if (a.mode == mode_dct3 || a.mode == mode_dst3){
+        // inverse of the Makhoul post-twiddle: V_k = e^{+i pi k / 2n} (y_k - i y_{n-k}), y_n := 0;
+        // for the sine variant y is replaced by the reversed input (y_k -> x_{n-1-k}).
+        const T *src = reinterpret_cast<const T*>(a.in);
+        T yk, ynk;
+        if (a.mode == mode_dct3){
+            yk  = src[off + (long long)i * a.ig.stride];
+            ynk = (i == 0) ? T(0) : src[off + (long long)(n - i) * a.ig.stride];
+        }else{
+            yk  = src[off + (long long)(n - 1 - i) * a.ig.stride];
+            ynk = (i == 0) ? T(0) : src[off + (long long)(i - 1) * a.ig.stride];
+        }
+        cplx<T> w = ldg_c<T>(w4n + i);            // e^{+i pi k/2n} = conj(W_{4n}^k)
+        cplx<T> z = mk<T>(yk, -ynk);
+        return cswap(cmul(z, mk<T>(w.x, -w.y)));  // swapped: the engine runs forward
+    }
+    if (a.mode == mode_dct1){
+        // even extension of length m = 2(n-1): s_i = x_i (i < n), s_{m-i} = x_i
+        int src = (i < n) ? i : m - i;
+        return mk<T>(reinterpret_cast<const T*>(a.in)[off + (long long)src * a.ig.stride], 0);
+    }
+    return generic_load<T>(a, a.in, off, i);
+}
+
+// output element i of a line from the engine result res(k) (natural order), written to `where`
+template<typename T, typename R>
+__device__ __forceinline__ void generic_output(generic_args const &a, R const &res, int i, const cplx<T> *w4n, void *where, T scale){
+    const int n = a.n;
+    switch(a.mode){
+        case mode_c2c: {
+            cplx<T> x = res(i);
+            if (a.backward) x = cswap(x);
+            x.x *= scale; x.y *= scale;
+            *static_cast<cplx<T>*>(where) = x;
+        } break;
+        case mode_r2c: {
+            cplx<T> x = res(i);
+            x.x *= scale; x.y *= scale;
+            *static_cast<cplx<T>*>(where) = x;
+        } break;
+        case mode_c2r: {
+            // engine ran forward on swapped input: result = swap(ifft); real part sits in .y
+            *static_cast<T*>(where) = res(i).y * scale;
+        } break;
+        case mode_dct2: {
+            // y_k = 2 Re( e^{-i pi k / 2n} V_k ),  e^{-i pi k/2n} = W_{4n}^k
+            cplx<T> z = cmul(res(i), ldg_c<T>(w4n + i));
+            *static_cast<T*>(where) = T(2) * z.x * scale;
+        } break;
+        case mode_dst2: {
+            cplx<T> z = cmul(res(n - 1 - i), ldg_c<T>(w4n + (n - 1 - i)));
+            *static_cast<T*>(where) = T(2) * z.x * scale;
+        } break;
+        case mode_dct3: case mode_dst3: {
+            // v = ifft(V) * n is in res (swapped: real part in .y); x_{2i} = v_i, x_{2i+1} = v_{n-1-i}
+            int srcpos = (i & 1) ? (n - 1 - (i >> 1)) : (i >> 1);
+            T v = res(srcpos).y * T(2);
+            if (a.mode == mode_dst3 && (i & 1)) v = -v;
+            *static_cast<T*>(where) = v * scale;
+        } break;
+        case mode_dct1: {
+            T v = res(i).x;
+            if (a.backward) v *= T(2);
+            *static_cast<T*>(where) = v * scale;
+        } break;
+    }
+}
+
 template<typename T>
 __global__ void fft_generic_kernel(generic_args a){
     B200_DYN_SMEM(smem_raw);
@@ -1718,34 +1790,7 @@ __global__ void fft_generic_kernel(generic_args a){
         if (a.lines_fast){ t = idx % lpb; i = idx / lpb; } else { i = idx % m; t = idx / m; }
         long long line = line0 + t;
         cplx<T> x = mk<T>(0, 0);
-        if (line < a.nlines){
-            long long off = line_offset(a.ig, a.count_a, line);
-            if (a.mode == mode_dct3 || a.mode == mode_dst3){
-                // inverse of the Makhoul post-twiddle: V_k = e^{+i pi k / 2n} (y_k - i y_{n-k}), y_n := 0;
-                // for the sine variant y is replaced by the reversed input (y_k -> x_{n-1-k}).
-                const T *src = reinterpret_cast<const T*>(a.in);
-                T yk, ynk;
-                if (a.mode == mode_dct3){
-                    yk  = src[off + (long long)i * a.ig.stride];
-                    ynk = (i == 0) ? T(0) : src[off + (long long)(n - i) * a.ig.stride];
-                }else{
-                    yk  = src[off + (long long)(n - 1 - i) * a.ig.stride];
-                    ynk = (i == 0) ? T(0) : src[off + (long long)(i - 1) * a.ig.stride];
-                }
-                // e^{+i pi k/2n} = conj(W_{4n}^k); the table for these modes holds W_{4n}^k, k < 4n ... stored after the first m entries
-                cplx<T> w = ldg_c<T>(tw + m + i);
-                cplx<T> z = mk<T>(yk, -ynk);
-                x = cmul(z, mk<T>(w.x, -w.y));
-                x = cswap(x); // backward engine
-            }else if (a.mode == mode_dct1){
-                // even extension of length m = 2(n-1): s_i = x_i (i < n), s_{m-i} = x_i
-                int src = (i < n) ? i : m - i;
-                T v = reinterpret_cast<const T*>(a.in)[off + (long long)src * a.ig.stride];
-                x = mk<T>(v, 0);
-            }else{
-                x = generic_load<T>(a, a.in, off, i);
-            }
-        }
+        if (line < a.nlines) x = generic_input<T>(a, line_offset(a.ig, a.count_a, line), i, tw + m);
         buf0[t * m + i] = x;
     }
     __syncthreads();
@@ -1806,46 +1851,7 @@ __global__ void fft_generic_kernel(generic_args a){
                 where = complex_out ? static_cast<void*>(reinterpret_cast<cplx<T>*>(a.out) + pos) : static_cast<void*>(reinterpret_cast<T*>(a.out) + pos);
             }
         }
-        switch(a.mode){
-            case mode_c2c: {
-                cplx<T> x = res[i];
-                if (a.backward) x = cswap(x);
-                x.x *= scale; x.y *= scale;
-                *static_cast<cplx<T>*>(where) = x;
-            } break;
-            case mode_r2c: {
-                cplx<T> x = res[i];
-                x.x *= scale; x.y *= scale;
-                *static_cast<cplx<T>*>(where) = x;
-            } break;
-            case mode_c2r: {
-                // engine ran forward on swapped input: result = swap(ifft); real part sits in .y
-                *static_cast<T*>(where) = res[i].y * scale;
-            } break;
-            case mode_dct2: {
-                // y_k = 2 Re( e^{-i pi k / 2n} V_k ),  e^{-i pi k/2n} = W_{4n}^k
-                cplx<T> w = ldg_c<T>(tw + m + i);
-                cplx<T> z = cmul(res[i], w);
-                *static_cast<T*>(where) = T(2) * z.x * scale;
-            } break;
-            case mode_dst2: {
-                cplx<T> w = ldg_c<T>(tw + m + (n - 1 - i));
-                cplx<T> z = cmul(res[n - 1 - i], w);
-                *static_cast<T*>(where) = T(2) * z.x * scale;
-            } break;
-            case mode_dct3: case mode_dst3: {
-                // v = ifft(V) * n is in res (swapped: real part in .y); x_{2i} = v_i, x_{2i+1} = v_{n-1-i}
-                int srcpos = (i & 1) ? (n - 1 - (i >> 1)) : (i >> 1);
-                T v = res[srcpos].y * T(2);
-                if (a.mode == mode_dst3 && (i & 1)) v = -v;
-                *static_cast<T*>(where) = v * scale;
-            } break;
-            case mode_dct1: {
-                T v = res[i].x;
-                if (a.backward) v *= T(2);
-                *static_cast<T*>(where) = v * scale;
-            } break;
-        }
+        generic_output<T>(a, [res](int k){ return res[k]; }, i, tw + m, where, scale);
     }
 }
 

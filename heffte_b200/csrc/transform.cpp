@@ -469,7 +469,10 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
     int const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
     int const cplx_bytes = 2 * real_bytes;
     bool const complex_data = (tkind == kind_c2c or tkind == kind_r2c);
-    static bool const allow_pair = (std::getenv("HEFFTE_B200_NO_OVERLAP") == nullptr);
+    // Two-stream overlap of a local transform with the fused stage behind it: measured on 2 x B200 (profiles/r02_multi_2gpu) it
+    // LOSES -- the fused kernels need every resident CTA to keep the link busy (thin grids: 400 instead of 690 GB/s), so the
+    // local transform has no SM time to hide in.  Opt-in for experiments.
+    static bool const allow_pair = (std::getenv("HEFFTE_B200_OVERLAP") != nullptr);
     static bool const allow_direct = (std::getenv("HEFFTE_B200_NO_DIRECT_OUTPUT") == nullptr);
     static int const thin_blocks = []{ const char *e = std::getenv("HEFFTE_B200_THIN_CTAS_PER_SM"); int const k = e ? std::atoi(e) : 2; return 148 * ((k > 0) ? k : 2); }();
     bool const shared_device = (std::strcmp(ccomm->kind(), "threads") == 0) and std::getenv("HEFFTE_B200_OVERLAP_ON_SHARED_DEVICE") == nullptr;

@@ -96,6 +96,69 @@ def main():
     assert lib.b200_fft1d_convolvable(pc) == 0       # contiguous axis: the plan falls back to three launches
     lib.b200_fft1d_destroy(pc)
 
+    # ---- any length: the composite engine (four-step over sub-plans, Bluestein for lengths that do not split) --------------------
+    def run1d(kind, prec, n, lines, direction, x, contiguous):
+        rdt, cdt = (np.float32, np.complex64) if prec == 0 else (np.float64, np.complex128)
+        nc = n // 2 + 1
+        if contiguous:
+            gin, gout = (1, n, 0), (1, nc if kind == 1 else n, 0)
+        else:
+            gin, gout = (lines, 1, 0), (lines, 1, 0)
+        d = b200_fft1d_desc(prec, kind, n, lines, 1, b200_line_geom(*gin), b200_line_geom(*gout))
+        p = vp()
+        rc = lib.b200_fft1d_create(ctypes.byref(d), ctypes.byref(p))
+        assert rc == 0, (n, _lib.last_error())
+        name = lib.b200_fft1d_kernel_name(p).decode()
+        real_in = (kind == 1 and direction == 0) or kind >= 2
+        real_out = (kind == 1 and direction == 1) or kind >= 2
+        src = np.ascontiguousarray(x.astype(rdt if real_in else cdt))
+        count_out = lines * (nc if (kind == 1 and direction == 0) else n)
+        dst = np.zeros(count_out, dtype=rdt if real_out else cdt)
+        rc = lib.b200_fft1d_execute(p, direction, vp(src.ctypes.data), vp(dst.ctypes.data), ctypes.c_double(1.0), None)
+        assert rc == 0, (n, _lib.last_error())
+        lib.b200_fft1d_destroy(p)
+        return dst, name
+
+    for prec, n, lines, expect in ((1, 8192, 3, "four-step"), (1, 7168, 2, "four-step"), (0, 7168, 2, "generic"), (1, 1021, 4, "Bluestein"), (1, 10007, 2, "Bluestein"),
+                                   (0, 12289, 1, "Bluestein"), (1, 16384, 1, "four-step"), (1, 4099, 2, "Bluestein")):
+        tol = 3e-5 if prec == 0 else 2e-11
+        for contiguous in (True, False):
+            x = rng.random(n * lines) + 1j * rng.random(n * lines)
+            view = x.reshape(lines, n) if contiguous else x.reshape(n, lines).T
+            for direction in (0, 1):
+                ref = np.fft.fft(view, axis=1) if direction == 0 else np.fft.ifft(view, axis=1) * n
+                ref = ref.reshape(-1) if contiguous else ref.T.reshape(-1)
+                y, name = run1d(0, prec, n, lines, direction, x, contiguous)
+                if expect not in name:
+                    failures.append("length %d: kernel %s, expected %s" % (n, name, expect))
+                err = np.linalg.norm(y - ref) / np.linalg.norm(ref)
+                if not err <= tol:
+                    failures.append("composite c2c n=%d prec=%d contiguous=%s direction=%d: rel l2 %.3e" % (n, prec, contiguous, direction, err))
+    # real transforms of awkward lengths: r2c / c2r of a prime length, DCT-II / DCT-III and DST-II / III of a prime length, long DCT-I
+    from oracle import heffte_oracle as O
+    for n, lines in ((1021, 3), (8200, 2)):
+        box = O.Box((0, 0, 0), (n - 1, lines - 1, 0))
+        xr = rng.random(n * lines)
+        y, name = run1d(1, 1, n, lines, 0, xr, True)
+        ref = O.exec1d_r2c(xr, box, 0)
+        if not O.rel_l2(y, ref) <= 2e-11:
+            failures.append("composite r2c n=%d (%s): %.3e" % (n, name, O.rel_l2(y, ref)))
+        z, _ = run1d(1, 1, n, lines, 1, ref, True)
+        if not O.rel_l2(z, O.exec1d_c2r(ref, box, 0)) <= 2e-11:
+            failures.append("composite c2r n=%d: %.3e" % (n, O.rel_l2(z, O.exec1d_c2r(ref, box, 0))))
+    for kind, kname, n in ((2, "cos", 509), (3, "sin", 509), (2, "cos", 9000), (4, "cos1", 4200)):
+        lines = 2
+        box = O.Box((0, 0, 0), (n - 1, lines - 1, 0))
+        xr = rng.random(n * lines)
+        f, name = run1d(kind, 1, n, lines, 0, xr, True)
+        if "composite" not in name:
+            failures.append("%s n=%d ran on %s" % (kname, n, name))
+        if not O.rel_l2(f, O.r2r_forward(xr, box, 0, kname)) <= 1e-10:
+            failures.append("composite %s forward n=%d: %.3e" % (kname, n, O.rel_l2(f, O.r2r_forward(xr, box, 0, kname))))
+        b, _ = run1d(kind, 1, n, lines, 1, xr, True)
+        if not O.rel_l2(b, O.r2r_backward(xr, box, 0, kname)) <= 1e-10:
+            failures.append("composite %s backward n=%d: %.3e" % (kname, n, O.rel_l2(b, O.r2r_backward(xr, box, 0, kname))))
+
     if failures:
         print("emul_kernels_worker: FAILED", failures, flush=True)
         sys.exit(1)
