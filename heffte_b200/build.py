@@ -16,7 +16,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function"]
 CUDA_SOURCES = ["fft1d.cu", "pack.cu"] + ["fft_inst_%s_%s_%s.cu" % (f, t, m) for f in ("strided", "contig", "real", "sreal", "pair", "conv") for t in ("f32", "f64")
-                                           for m in ("direct", "scatter")]
+                                           for m in ("direct", "scatter")] + ["fft_inst_sreal2_f32_direct.cu", "fft_inst_sreal2_f64_direct.cu"]
 HOST_SOURCES = ["plan_logic.cpp", "comm.cpp", "transform.cpp", "capi.cpp"]
 
 

@@ -268,6 +268,7 @@ struct fft_args {
     int done_mode;
     unsigned done_need;
     int order_nb;
+    const void *twiddle0;      // real-data kernels, second generation: W_n^k for the full real length n
 };
 struct batch_shift { long long all, local; };
 // the arguments of batch entry blockIdx.y
@@ -1613,6 +1614,173 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_real_kernel(fft_a
                 if (k > 0) put_y(M + k, T(-2) * a2.y);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// real-data transforms along the middle / slow axis, second generation (plain stores): TWO adjacent real lines make ONE
+// complex line.  Neighbouring lines are adjacent in memory, so a row of 2 LPB reals IS a row of LPB complex numbers
+// c = x1 + i x2: the tile is loaded exactly like a tile of the complex kernel (16-byte asynchronous copies, no
+// de-interleaving, no 8-byte copies), transformed with the complex passes at the full length n, and the two lines are
+// separated afterwards from the pair (k, n-k):   V1_k = (C_k + conj C_{n-k}) / 2,   V2_k = -i (C_k - conj C_{n-k}) / 2.
+//   r2c:  row k of the output holds (V1_k, V2_k), k <= n/2 -- two adjacent complex numbers, one 32-byte store
+//   DCT-II: rows enter in Makhoul's order (a row permutation of the load); y_k = 2 Re(w_k V_k), y_{n-k} = -2 Im(w_k V_k)
+//   backward: C_k = V1_k + i V2_k and C_{n-k} = conj V1_k + i conj V2_k are built from the rows k and n-k, the complex passes
+//   run on swapped data, and the rows of the result are stored as pairs of reals (DCT-III: permuted, times two)
+// Same algebra as fft_strided_real_kernel, on n x LPB complex numbers instead of n/2 x 2 LPB: the same shared memory and
+// the same instruction mix per byte as the complex kernel, which runs at the HBM roofline.  Needs an even number of
+// adjacent lines and rows aligned to a complex number; other shapes keep the first-generation kernel.
+// ---------------------------------------------------------------------------------------------------------
+template<typename T, typename RL, int TPL, int LPB, int MINB, int KIND, bool BWD>
+__global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_real2_kernel(fft_args a0){
+    B200_DYN_SMEM(smem_raw);
+    batch_shift shift;
+    const fft_args a = batch_entry(a0, shift);
+    constexpr unsigned N = RL::N;                  // the real length
+    constexpr bool R2C = (KIND == real_r2c);
+    constexpr int P = RL::passes;
+    cplx<T> *sm = reinterpret_cast<cplx<T>*>(smem_raw);
+    const unsigned t = threadIdx.x % LPB, j = threadIdx.x / LPB;
+    const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle0);
+    const cplx<T> *tx = reinterpret_cast<const cplx<T>*>(a.twiddle2);     // W_{4n}^k
+    const T scale = static_cast<T>(a.scale);
+    const bool do_scale = a.scale != 1.0;
+    const scatter_ctx sc{nullptr, 0, 0, 0};
+    const unsigned npairs = static_cast<unsigned>((a.nlines + 1) / 2);    // complex lines
+    const unsigned half_a = static_cast<unsigned>(a.count_a / 2);         // complex lines per row of the box
+    const unsigned ntiles = (npairs + LPB - 1) / LPB;
+    for(unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
+        const unsigned pair = tile * LPB + t;
+        const bool valid = pair < npairs;
+        // offsets of the first line of the pair, in reals
+        const unsigned pb = pair / half_a, pa = pair - pb * half_a;
+        const long long ioff = valid ? (2LL * pa * a.ig.stride_a + static_cast<long long>(pb) * a.ig.stride_b) : 0;
+        const long long ooff = valid ? (2LL * pa * a.og.stride_a + static_cast<long long>(pb) * a.og.stride_b) : 0;
+
+        if constexpr (!BWD){
+            // ---- load: rows of two adjacent reals, in Makhoul's order for the cosine / sine transforms -----------------------------
+            if (valid){
+                const T *src = reinterpret_cast<const T*>(a.in) + ioff;
+                #pragma unroll 4
+                for(unsigned i = j; i < N; i += TPL){
+                    const unsigned p = R2C ? i : ((i & 1) ? N - 1 - (i >> 1) : (i >> 1));
+                    async_copy<sizeof(cplx<T>)>(sm + p * LPB + t, src + static_cast<long long>(i) * a.ig.stride);
+                }
+            }
+            async_wait_all();
+            __syncthreads();
+            // ---- complex passes, the spectrum stays in the tile (digit-reversed positions) -----------------------------------------
+            if constexpr (KIND == real_sin){
+                // DST-II: the odd samples fill the upper half of the permuted sequence and carry a minus sign
+                for(unsigned i = N / 2 + j; i < N; i += TPL){ cplx<T> x = sm[i * LPB + t]; sm[i * LPB + t] = mk<T>(-x.x, -x.y); }
+                __syncthreads();
+            }
+            if constexpr (P > 1){ conv_forward_pass<T, RL, 0, TPL, LPB>(sm, t, j, tw); __syncthreads(); }
+            if constexpr (P > 2){ conv_forward_pass<T, RL, 1, TPL, LPB>(sm, t, j, tw); __syncthreads(); }
+            if constexpr (P > 3){ conv_forward_pass<T, RL, 2, TPL, LPB>(sm, t, j, tw); __syncthreads(); }
+            {
+                constexpr unsigned S = P - 1, R = RL::radix(S), NB = N / R;
+                #pragma unroll 1
+                for(unsigned u=0; u<NB/TPL; u++){
+                    cplx<T> *cell = sm + (j + u * TPL) * R * LPB + t;
+                    cplx<T> v[R];
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++) v[r] = cell[r * LPB];
+                    butterfly<T, R>::run(v);
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++) cell[r * LPB] = v[r];
+                }
+            }
+            __syncthreads();
+            // ---- the two lines apart: pair (k, n-k) ----------------------------------------------------------------------------------
+            if (valid){
+                const T half = static_cast<T>(0.5);
+                T *rout = reinterpret_cast<T*>(a.out) + (R2C ? 2 * ooff : ooff);
+                for(unsigned k = j; k <= N / 2; k += TPL){
+                    const cplx<T> ck = sm[dif_position_of<RL>(k) * LPB + t], cm = sm[dif_position_of<RL>((N - k) % N) * LPB + t];
+                    cplx<T> v1 = mk<T>((ck.x + cm.x) * half, (ck.y - cm.y) * half);
+                    cplx<T> v2 = mk<T>((ck.y + cm.y) * half, (cm.x - ck.x) * half);
+                    if constexpr (R2C){
+                        if (do_scale){ v1.x *= scale; v1.y *= scale; v2.x *= scale; v2.y *= scale; }
+                        cplx<T> *dst = reinterpret_cast<cplx<T>*>(rout) + static_cast<long long>(k) * a.og.stride;     // complex row k: (line 1, line 2)
+                        dst[0] = v1; dst[1] = v2;
+                    }else{
+                        const cplx<T> w = ldg_c<T>(tx + k);
+                        const cplx<T> z1 = cmul(w, v1), z2 = cmul(w, v2);
+                        const T two = do_scale ? T(2) * scale : T(2);
+                        auto put = [&](unsigned p, T y1, T y2){
+                            const unsigned row = (KIND == real_sin) ? N - 1 - p : p;
+                            *reinterpret_cast<cplx<T>*>(rout + static_cast<long long>(row) * a.og.stride) = mk<T>(y1, y2);
+                        };
+                        put(k, two * z1.x, two * z2.x);
+                        if (k > 0 && 2 * k != N) put(N - k, -two * z1.y, -two * z2.y);
+                    }
+                }
+            }
+        }else{
+            // ---- backward: C_k and C_{n-k} from the rows k and n-k, written swapped for the forward engine -----------------------------------
+            if (valid){
+                const T *rin = reinterpret_cast<const T*>(a.in) + (R2C ? 2 * ioff : ioff);
+                for(unsigned k = j; k <= N / 2; k += TPL){
+                    cplx<T> v1, v2;
+                    if constexpr (R2C){
+                        const cplx<T> *src = reinterpret_cast<const cplx<T>*>(rin) + static_cast<long long>(k) * a.ig.stride;
+                        v1 = src[0]; v2 = src[1];
+                        if (k == 0 || 2 * k == N){ v1.y = 0; v2.y = 0; }       // c2r ignores the imaginary part of the self-conjugate entries
+                    }else{
+                        // V_k = conj(w_k) (y_k - i y_{n-k}), y_n := 0; the sine transform reads the reversed input
+                        auto get = [&](unsigned p){
+                            const unsigned row = (KIND == real_sin) ? N - 1 - p : p;
+                            return *reinterpret_cast<const cplx<T>*>(rin + static_cast<long long>(row) * a.ig.stride);
+                        };
+                        const cplx<T> yk = get(k);
+                        const cplx<T> ym = (k == 0) ? mk<T>(0, 0) : get(N - k);
+                        const cplx<T> w = ldg_c<T>(tx + k);
+                        v1 = cmul(mk<T>(yk.x, -ym.x), mk<T>(w.x, -w.y));
+                        v2 = cmul(mk<T>(yk.y, -ym.y), mk<T>(w.x, -w.y));
+                    }
+                    // C_k = V1_k + i V2_k,  C_{n-k} = conj(V1_k) + i conj(V2_k); stored swapped
+                    const cplx<T> ck = mk<T>(v1.x - v2.y, v1.y + v2.x);
+                    const cplx<T> cm = mk<T>(v1.x + v2.y, v2.x - v1.y);
+                    sm[k * LPB + t] = cswap(ck);
+                    if (k > 0 && 2 * k != N) sm[(N - k) * LPB + t] = cswap(cm);
+                }
+            }
+            __syncthreads();
+            if constexpr (P > 1){ conv_forward_pass<T, RL, 0, TPL, LPB>(sm, t, j, tw); __syncthreads(); }
+            if constexpr (P > 2){ conv_forward_pass<T, RL, 1, TPL, LPB>(sm, t, j, tw); __syncthreads(); }
+            if constexpr (P > 3){ conv_forward_pass<T, RL, 2, TPL, LPB>(sm, t, j, tw); __syncthreads(); }
+            {
+                // last pass: natural index of leg r is k0 + r N/R; the two reals of a row are stored together
+                constexpr unsigned S = P - 1, R = RL::radix(S), NB = N / R;
+                T *rout = reinterpret_cast<T*>(a.out) + ooff;
+                const T factor = (R2C ? T(1) : T(2)) * (do_scale ? scale : T(1));
+                #pragma unroll 1
+                for(unsigned u=0; u<NB/TPL; u++){
+                    const unsigned p0 = (j + u * TPL) * R;
+                    cplx<T> *cell = sm + p0 * LPB + t;
+                    cplx<T> v[R];
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++) v[r] = cell[r * LPB];
+                    butterfly<T, R>::run(v);
+                    if (valid){
+                        const unsigned k0 = dif_output_index<RL>(p0);
+                        #pragma unroll
+                        for(unsigned r=0; r<R; r++){
+                            const unsigned e = k0 + r * (N / R);          // position in the sequence v (swapped: .y is line 1, .x is line 2)
+                            unsigned row; T f = factor;
+                            if constexpr (R2C) row = e;
+                            else{
+                                row = (e < (N + 1) / 2) ? 2 * e : 2 * (N - 1 - e) + 1;
+                                if (KIND == real_sin && (row & 1)) f = -f;
+                            }
+                            *reinterpret_cast<cplx<T>*>(rout + static_cast<long long>(row) * a.og.stride) = mk<T>(v[r].y * f, v[r].x * f);
+                        }
+                    }
+                }
+            }
+        }
+        if (tile + gridDim.x < ntiles) __syncthreads();
     }
 }
 

@@ -321,6 +321,42 @@ int dispatch_strided_real_kind(int m, fft_args const &a, Launcher &L){
         default: return -1;
     }
 }
+// second generation of the strided real kernels (fft_strided_real2_kernel): two adjacent real lines per complex line, the tile
+// shapes of the complex strided kernel for the full real length n
+template<typename T, typename RL, int TPL, int LPB, int MINB, int KIND, typename Launcher>
+int launch_strided_real2(fft_args const &a, Launcher &L){
+    long long const pairs = (a.nlines + 1) / 2;
+    long long blocks = (pairs + LPB - 1) / LPB;
+    size_t smem = sizeof(cplx<T>) * (size_t)RL::N * LPB;
+    if (a.backward) return L.launch(fft_strided_real2_kernel<T, RL, TPL, LPB, MINB, KIND, true>, blocks, TPL * LPB, smem, a);
+    return L.launch(fft_strided_real2_kernel<T, RL, TPL, LPB, MINB, KIND, false>, blocks, TPL * LPB, smem, a);
+}
+constexpr bool is_real2_length(long long n){ return is_pow2(n) && n >= 32 && n <= 4096; }
+template<typename T, int KIND, typename Launcher>
+int dispatch_strided_real2_kind(int n, fft_args const &a, Launcher &L){
+    constexpr int M = row_lines<T>::value / 8;
+    switch(n){
+        case 32:   return launch_strided_real2<T, radix_list<8, 4, 1, 1>,   4 / M, 32 * M, 2, KIND>(a, L);
+        case 64:   return launch_strided_real2<T, radix_list<8, 8, 1, 1>,   8 / M, 16 * M, 2, KIND>(a, L);
+        case 128:  return launch_strided_real2<T, radix_list<8, 4, 4, 1>,  16 / M,  8 * M, 2, KIND>(a, L);
+        case 256:  return launch_strided_real2<T, radix_list<8, 8, 4, 1>,  32 / M,  8 * M, 2, KIND>(a, L);
+        case 512:  return launch_strided_real2<T, radix_list<8, 8, 8, 1>,  32 / M,  8 * M, 3, KIND>(a, L);
+        case 1024: return launch_strided_real2<T, radix_list<16, 8, 8, 1>, 32 / M,  8 * M, 1, KIND>(a, L);
+        case 2048: return launch_strided_real2<T, radix_list<8, 8, 8, 4>, 128 / M,  4 * M, 1, KIND>(a, L);
+        case 4096: return launch_strided_real2<T, radix_list<8, 8, 8, 8>, 256 / M,  2 * M, 1, KIND>(a, L);
+        default: return -1;
+    }
+}
+template<typename T, typename Launcher>
+int dispatch_strided_real2(int kind, int n, fft_args const &a, Launcher &L){
+    switch(kind){
+        case real_r2c: return dispatch_strided_real2_kind<T, real_r2c>(n, a, L);
+        case real_cos: return dispatch_strided_real2_kind<T, real_cos>(n, a, L);
+        case real_sin: return dispatch_strided_real2_kind<T, real_sin>(n, a, L);
+        default: return -1;
+    }
+}
+
 template<typename T, bool SCATTER, typename Launcher>
 int dispatch_strided_real(int kind, int m, fft_args const &a, Launcher &L){
     switch(kind){

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/heffte_b200_kernels.h"
@@ -116,6 +117,21 @@ inline int make_host_plan(b200_fft1d_desc const &desc, host_plan &plan, const ch
 
 inline line_geom to_geom(b200_line_geom const &g){ return line_geom{g.stride, g.stride_a, g.stride_b}; }
 
+// the second-generation strided real kernel pairs adjacent lines: an even number of them per row, rows aligned to a complex number
+inline bool real2_applies(bool is_float, int kind, int m, fft_args const &a){
+    static bool const off = (std::getenv("HEFFTE_B200_REAL_KERNELS_V1") != nullptr);
+    if (off or not is_real2_length(2LL * m) or a.count_a % 2 != 0 or a.nlines % 2 != 0) return false;
+    size_t const csize = is_float ? 8 : 16;
+    bool const real_in = not (kind == real_r2c and a.backward), real_out = not (kind == real_r2c and not a.backward);
+    auto even = [](line_geom const &g){ return g.stride % 2 == 0 and g.stride_b % 2 == 0 and g.stride_a == 1; };
+    if (reinterpret_cast<uintptr_t>(a.in) % csize or reinterpret_cast<uintptr_t>(a.out) % csize or (a.in_step % static_cast<long long>(csize)) or (a.out_step % static_cast<long long>(csize))) return false;
+    if (real_in and not even(a.ig)) return false;
+    if (real_out and not even(a.og)) return false;
+    if (not real_in and a.ig.stride_a != 1) return false;
+    if (not real_out and a.og.stride_a != 1) return false;
+    return true;
+}
+
 // batched execution: `batch` entries, entry e works on in + e * in_step / out + e * out_step (bytes); fused stores: see fft_args
 struct batch_steps {
     int batch = 1;
@@ -181,6 +197,7 @@ int run_host_plan(host_plan const &plan, const void *twiddle, int direction, con
             a.smap = static_cast<const scatter_map*>(scatter);
             set_steps(a, steps);
             a.done = nullptr; a.done_mode = 0; a.done_need = 0; a.order_nb = 0; a.multiplier = nullptr;
+            a.twiddle0 = twiddle;         // W_n^k, k < n: the full-length engine of the second-generation kernels
             return L.run_real(plan.family == family_strided_real, is_float, scatter != nullptr, plan.real_kind, static_cast<int>(d.n / 2), a);
         }
     }else if (plan.family != family_generic){

@@ -1,0 +1,7 @@
+// One slice of the second-generation strided real kernel instantiations (double); see fft_dispatch.cuh.
+#include "fft_dispatch.cuh"
+#include "runtime.h"
+
+namespace b200 {
+int run_sreal2_f64(int kind, int n, fft_args const &a, cuda_launcher &L){ return dispatch_strided_real2<double>(kind, n, a, L); }
+}

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "heffte_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libheffte_b200_emul.so")
 UNITS = ["fft1d.cu", "pack.cu", "plan_logic.cpp", "comm.cpp", "transform.cpp", "capi.cpp"] + \
-        ["fft_inst_%s_%s_%s.cu" % (f, t, m) for f in ("strided", "contig", "real", "sreal", "pair", "conv") for t in ("f32", "f64") for m in ("direct", "scatter")]
+        ["fft_inst_%s_%s_%s.cu" % (f, t, m) for f in ("strided", "contig", "real", "sreal", "pair", "conv") for t in ("f32", "f64") for m in ("direct", "scatter")] + ["fft_inst_sreal2_f32_direct.cu", "fft_inst_sreal2_f64_direct.cu"]
 
 
 def build(force=False):

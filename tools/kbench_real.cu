@@ -35,7 +35,7 @@ int main(){
     const double gb_r2r = 2.0 * elems * 8 * 1e-9, gb_r2c = (elems * 8.0 + (double)(n/2+1)*n*n*16) * 1e-9;
     auto report = [&](const char *name, double gb, float ms){ printf("%-60s %8.3f ms  %7.1f GB/s\n", name, ms, gb / ms * 1e3); fflush(stdout); };
 
-    fft_args a; a.twiddle = tw + 16 * (hp.table_main + hp.table_extra); a.twiddle2 = tw + 16 * hp.table_main;
+    fft_args a{}; a.twiddle = tw + 16 * (hp.table_main + hp.table_extra); a.twiddle2 = tw + 16 * hp.table_main;
     a.nlines = elems / n; a.scale = 1.0; a.smap = nullptr;
     using R884 = radix_list<8,8,4,1>; using R1616 = radix_list<16,16,1,1>; using R488 = radix_list<4,8,8,1>;
 
@@ -134,6 +134,28 @@ int main(){
         SV(R1616, 16, 16, 2, "strided_real <16,16> TPL16 LPB16 minb2")
         SV(R1616, 16, 8, 4, "strided_real <16,16> TPL16 LPB8 minb4 (128thr 32KB)")
         SV(R488, 16, 16, 3, "strided_real <4,8,8> TPL16 LPB16 minb3")
+    }
+    // ---- second-generation strided real kernel: two adjacent real lines per complex line, full-length complex passes ---------
+    {
+        a.in = x; a.out = x; a.ig = a.og = line_geom{n, 1, (long long)n*n}; a.count_a = n; a.twiddle0 = tw; a.in_step = a.out_step = 0;
+        using R888 = radix_list<8,8,8,1>; using R8164 = radix_list<8,16,4,1>; using R4816 = radix_list<4,8,16,1>;
+        for(int backward=0; backward<2; backward++){
+            a.backward = backward;
+            printf("-- strided real2 kind cos %s\n", backward ? "backward" : "forward");
+#define S2(RL, TPL, LPB, MINB, label) report(label, gb_r2r, timeit([&]{ launch_strided_real2<double, RL, TPL, LPB, MINB, real_cos>(a, l); }));
+            S2(R888, 32, 8, 3, "strided_real2 <8,8,8> TPL32 LPB8 minb3")
+            S2(R888, 32, 8, 2, "strided_real2 <8,8,8> TPL32 LPB8 minb2")
+            S2(R888, 64, 8, 1, "strided_real2 <8,8,8> TPL64 LPB8 minb1 (512thr)")
+            S2(R8164, 32, 8, 3, "strided_real2 <8,16,4> TPL32 LPB8 minb3")
+            S2(R4816, 32, 8, 3, "strided_real2 <4,8,16> TPL32 LPB8 minb3")
+        }
+        line_geom rg{n, 1, (long long)n*n}, cg{n, 1, (long long)n*(n/2+1)};
+        a.backward = 0; a.in = x; a.out = y; a.ig = rg; a.og = cg;
+        printf("-- strided real2 kind r2c forward / backward\n");
+        report("strided_real2 r2c fwd <8,8,8> TPL32 LPB8 minb3", gb_r2c, timeit([&]{ launch_strided_real2<double, R888, 32, 8, 3, real_r2c>(a, l); }));
+        a.backward = 1; a.in = y; a.out = x; a.ig = cg; a.og = rg;
+        report("strided_real2 c2r bwd <8,8,8> TPL32 LPB8 minb3", gb_r2c, timeit([&]{ launch_strided_real2<double, R888, 32, 8, 3, real_r2c>(a, l); }));
+        a.backward = 0;
     }
     // r2c along the middle axis
     {
