@@ -1719,6 +1719,20 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_real2_kernel(fft_
             }
         }else{
             // ---- backward: C_k and C_{n-k} from the rows k and n-k, written swapped for the forward engine -----------------------------------
+            // cosine / sine: the rows arrive asynchronously (the sine transform reads the reversed input: row i lands at n-1-i) and
+            // every pair is rewritten in place by the thread that read it
+            if constexpr (!R2C){
+                if (valid){
+                    const T *src = reinterpret_cast<const T*>(a.in) + ioff;
+                    #pragma unroll 4
+                    for(unsigned i = j; i < N; i += TPL){
+                        const unsigned p = (KIND == real_sin) ? N - 1 - i : i;
+                        async_copy<sizeof(cplx<T>)>(sm + p * LPB + t, src + static_cast<long long>(i) * a.ig.stride);
+                    }
+                }
+                async_wait_all();
+                __syncthreads();
+            }
             if (valid){
                 const T *rin = reinterpret_cast<const T*>(a.in) + (R2C ? 2 * ioff : ioff);
                 for(unsigned k = j; k <= N / 2; k += TPL){
@@ -1728,13 +1742,9 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_real2_kernel(fft_
                         v1 = src[0]; v2 = src[1];
                         if (k == 0 || 2 * k == N){ v1.y = 0; v2.y = 0; }       // c2r ignores the imaginary part of the self-conjugate entries
                     }else{
-                        // V_k = conj(w_k) (y_k - i y_{n-k}), y_n := 0; the sine transform reads the reversed input
-                        auto get = [&](unsigned p){
-                            const unsigned row = (KIND == real_sin) ? N - 1 - p : p;
-                            return *reinterpret_cast<const cplx<T>*>(rin + static_cast<long long>(row) * a.ig.stride);
-                        };
-                        const cplx<T> yk = get(k);
-                        const cplx<T> ym = (k == 0) ? mk<T>(0, 0) : get(N - k);
+                        // V_k = conj(w_k) (y_k - i y_{n-k}), y_n := 0
+                        const cplx<T> yk = sm[k * LPB + t];
+                        const cplx<T> ym = (k == 0) ? mk<T>(0, 0) : sm[(N - k) * LPB + t];
                         const cplx<T> w = ldg_c<T>(tx + k);
                         v1 = cmul(mk<T>(yk.x, -ym.x), mk<T>(w.x, -w.y));
                         v2 = cmul(mk<T>(yk.y, -ym.y), mk<T>(w.x, -w.y));

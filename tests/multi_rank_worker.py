@@ -96,6 +96,27 @@ class HostArrays:
         return t
 
 
+_memo, _memo_lock = {}, __import__("threading").Lock()
+
+
+def _shared(key, compute):
+    """the oracle answers of a configuration, computed once per process: ranks that are threads of one process (the emulated and
+    the single-GPU thread-rank tests) would otherwise repeat the same numpy transforms under the GIL, one after the other"""
+    with _memo_lock:
+        slot = _memo.get(key)
+        if slot is None:
+            slot = {"lock": __import__("threading").Lock(), "value": None}
+            _memo[key] = slot
+            if len(_memo) > 64:
+                for old in list(_memo)[:32]:
+                    if old != key:
+                        _memo.pop(old, None)
+    with slot["lock"]:
+        if slot["value"] is None:
+            slot["value"] = compute()
+        return slot["value"]
+
+
 def run_config(hf, torch, comm, rank, c, batch=1, stream=None, expect_peer=None, arrays=None):
     arrays = arrays or TorchArrays(torch)
     n, kind, prec = c["n"], c["kind"], c["prec"]
@@ -127,7 +148,7 @@ def run_config(hf, torch, comm, rank, c, batch=1, stream=None, expect_peer=None,
     worst = 0.0
     problems = []   # reported at the end: every rank must issue the same sequence of collective calls whatever the numbers are
     for scaling, sname in ((1, "full"), (0, "none")):
-        ref = O.fft3d_forward(x, n, kind, r2c_dir=r2c_dir, scaling=sname)
+        ref = _shared(("fwd", kind, n, prec, r2c_dir, sname), lambda: O.fft3d_forward(x, n, kind, r2c_dir=r2c_dir, scaling=sname))
         dx = arrays.to_device(np.tile(local, batch))
         dy = arrays.empty(batch * outbox.count(), out_dtype)
         fft.forward(dx, dy, scaling, batch=batch)
@@ -141,7 +162,7 @@ def run_config(hf, torch, comm, rank, c, batch=1, stream=None, expect_peer=None,
                 problems.append("forward(%s): rel l2 %.3e > %.1e" % (sname, err, tol))
         dz = arrays.empty(batch * inbox.count(), x.dtype)
         fft.backward(dy, dz, scaling, batch=batch)
-        refb = O.fft3d_backward(ref, n, kind, r2c_dir=r2c_dir, scaling=sname)
+        refb = _shared(("bwd", kind, n, prec, r2c_dir, sname), lambda: O.fft3d_backward(ref, n, kind, r2c_dir=r2c_dir, scaling=sname))
         expect_b = O.get_subbox(world, inbox, refb)
         got = arrays.to_host(dz)
         for b in range(batch):
@@ -165,7 +186,7 @@ def run_config(hf, torch, comm, rank, c, batch=1, stream=None, expect_peer=None,
     # fused spectral operator (reference benchmarks/convolution.cpp:86-97): forward(scale full), pointwise product, backward, as
     # ONE plan call -- the spectrum times itself, then times a caller array laid out over convolve_box()
     if kind == "c2c" and batch == 1 and all(a.count() == b.count() for a, b in zip(inboxes, outboxes)):
-        spectrum = O.fft3d_forward(x, n, "c2c", scaling="full")
+        spectrum = _shared(("fwd", kind, n, prec, r2c_dir, "full"), lambda: O.fft3d_forward(x, n, "c2c", scaling="full"))
         for use_multiplier in (False, True):
             lo, hi, order = fft.convolve_box()
             cbox = O.Box(lo, hi, order)
@@ -176,7 +197,8 @@ def run_config(hf, torch, comm, rank, c, batch=1, stream=None, expect_peer=None,
                 mult_world = (mrng.random(world.count()) + 1j * mrng.random(world.count())).astype(cdt)
                 dm = arrays.to_device(O.get_subbox(world, cbox, mult_world))
             product = spectrum * (mult_world if use_multiplier else spectrum)
-            expect_c = O.get_subbox(world, inbox, O.fft3d_backward(product, n, "c2c", scaling="none"))
+            conv_world = _shared(("conv", n, prec, use_multiplier), lambda: O.fft3d_backward(product, n, "c2c", scaling="none"))
+            expect_c = O.get_subbox(world, inbox, conv_world)
             d = arrays.to_device(local)
             dout = arrays.empty(inbox.count(), x.dtype)
             try:
