@@ -57,7 +57,13 @@ int run_sreal_f64_direct(int kind, int m, fft_args const &a, cuda_launcher &L);
 int run_sreal_f64_scatter(int kind, int m, fft_args const &a, cuda_launcher &L);
 int run_sreal2_f32(int kind, int n, fft_args const &a, cuda_launcher &L);
 int run_sreal2_f64(int kind, int n, fft_args const &a, cuda_launcher &L);
+int run_creal2_f32(int kind, int n, fft_args const &a, cuda_launcher &L);
+int run_creal2_f64(int kind, int n, fft_args const &a, cuda_launcher &L);
 int cuda_launcher::run_real(bool strided, bool is_float, bool scatter, int kind, int m, fft_args const &a){
+    if (not strided and not scatter and contig_real2_applies(kind, m, a)){
+        int const rc = is_float ? run_creal2_f32(kind, 2 * m, a, *this) : run_creal2_f64(kind, 2 * m, a, *this);
+        if (rc != -1) return rc;
+    }
     if (strided and not scatter and real2_applies(is_float, kind, m, a)){
         int const rc = is_float ? run_sreal2_f32(kind, 2 * m, a, *this) : run_sreal2_f64(kind, 2 * m, a, *this);
         if (rc != -1) return rc;

@@ -1618,6 +1618,127 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_real_kernel(fft_a
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// DCT / DST along contiguous lines, third generation (plain stores): two neighbouring lines x1, x2 form ONE complex line
+// c = x1 + i x2 (see fft_strided_real2_kernel for the algebra) and the complex Stockham passes run at the full length n.  The
+// first pass gathers its legs straight from global memory in Makhoul's order (8-byte loads from both lines, the sign of the sine
+// transform on the way); the lines are separated from the pair (k, n-k) of the spectrum in shared memory and stored with unit
+// stride.  Backward: the pairs are built from unit-stride loads, the last pass leaves the sequence in shared memory and the
+// rows go out in Makhoul's order with unit stride.
+// ---------------------------------------------------------------------------------------------------------
+template<typename T, typename RL, int LPB, int MINB, int KIND, bool BWD, int TPL_ = RL::N / RL::rmax>
+__global__ void __launch_bounds__(TPL_ * LPB, MINB) fft_contig_real2_kernel(fft_args a0){
+    B200_DYN_SMEM(smem_raw);
+    static_assert(KIND == real_cos || KIND == real_sin, "cosine / sine transforms");
+    batch_shift shift;
+    const fft_args a = batch_entry(a0, shift);
+    constexpr unsigned N = RL::N;
+    constexpr int TPL = TPL_;
+    constexpr int P = RL::passes;
+    constexpr unsigned PITCH = pad_index(RL::N) + 1;
+    constexpr int N1 = RL::radix(0), N2 = N1 * RL::radix(1), N3 = N2 * RL::radix(2);
+    const unsigned j = threadIdx.x % TPL, t = threadIdx.x / TPL;
+    cplx<T> *row = reinterpret_cast<cplx<T>*>(smem_raw) + t * PITCH;
+    const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle0);
+    const cplx<T> *tx = reinterpret_cast<const cplx<T>*>(a.twiddle2);
+    const T scale = static_cast<T>(a.scale);
+    const bool do_scale = a.scale != 1.0;
+    const scatter_ctx sc{nullptr, 0, 0, 0};
+    const unsigned npairs = static_cast<unsigned>(a.nlines / 2);
+    const unsigned ntiles = (npairs + LPB - 1) / LPB;
+    for(unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
+        const unsigned pair = tile * LPB + t;
+        const bool valid = pair < npairs;
+        const T *in1 = reinterpret_cast<const T*>(a.in) + (valid ? tile_line_offset(a.ig, a.count_a, 2 * pair) : 0);
+        const T *in2 = reinterpret_cast<const T*>(a.in) + (valid ? tile_line_offset(a.ig, a.count_a, 2 * pair + 1) : 0);
+        T *out1 = reinterpret_cast<T*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, 2 * pair) : 0);
+        T *out2 = reinterpret_cast<T*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, 2 * pair + 1) : 0);
+
+        if constexpr (!BWD){
+            // ---- first pass: legs gathered in Makhoul's order from both lines --------------------------------------------------------
+            {
+                constexpr unsigned R = RL::radix(0), NB = N / R, BPT = NB / TPL;
+                cplx<T> v[BPT][R];
+                #pragma unroll
+                for(unsigned u=0; u<BPT; u++){
+                    const unsigned q = j + u * TPL;
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++){
+                        const unsigned p = q + r * NB;                                          // position in the permuted sequence
+                        const bool upper = 2 * p >= N;
+                        const unsigned i = upper ? 2 * (N - 1 - p) + 1 : 2 * p;                 // the sample that sits there
+                        T x1 = valid ? in1[i] : T(0), x2 = valid ? in2[i] : T(0);
+                        if (KIND == real_sin && upper){ x1 = -x1; x2 = -x2; }
+                        v[u][r] = mk<T>(x1, x2);
+                    }
+                }
+                #pragma unroll
+                for(unsigned u=0; u<BPT; u++){
+                    const unsigned q = j + u * TPL;
+                    butterfly<T, R>::run(v[u]);
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++) row[pad_index(q * R + r)] = v[u][r];
+                }
+            }
+            if constexpr (P > 1){ __syncthreads(); contig_pass<T, RL, 1, N1, TPL, false, false, false, (P == 2)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
+            if constexpr (P > 2){ __syncthreads(); contig_pass<T, RL, 2, N2, TPL, false, false, false, (P == 3)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
+            if constexpr (P > 3){ __syncthreads(); contig_pass<T, RL, 3, N3, TPL, false, false, false, true>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
+            __syncthreads();
+            // ---- the two lines apart, quarter-wave twiddle, unit-stride stores -------------------------------------------------------
+            if (valid){
+                const T half = static_cast<T>(0.5);
+                const T two = do_scale ? T(2) * scale : T(2);
+                for(unsigned k = j; k <= N / 2; k += TPL){
+                    const cplx<T> ck = row[pad_index(k)], cm = row[pad_index((N - k) % N)];
+                    const cplx<T> v1 = mk<T>((ck.x + cm.x) * half, (ck.y - cm.y) * half);
+                    const cplx<T> v2 = mk<T>((ck.y + cm.y) * half, (cm.x - ck.x) * half);
+                    const cplx<T> w = ldg_c<T>(tx + k);
+                    const cplx<T> z1 = cmul(w, v1), z2 = cmul(w, v2);
+                    const unsigned lo = (KIND == real_sin) ? N - 1 - k : k;
+                    out1[lo] = two * z1.x; out2[lo] = two * z2.x;
+                    if (k > 0 && 2 * k != N){
+                        const unsigned hi = (KIND == real_sin) ? k - 1 : N - k;
+                        out1[hi] = -two * z1.y; out2[hi] = -two * z2.y;
+                    }
+                }
+            }
+        }else{
+            // ---- C_k and C_{n-k} from unit-stride loads of both lines, written swapped for the forward engine ----------------------------------
+            if (valid){
+                for(unsigned k = j; k <= N / 2; k += TPL){
+                    const unsigned lo = (KIND == real_sin) ? N - 1 - k : k, hi = (KIND == real_sin) ? k - 1 : N - k;
+                    const T y1k = in1[lo], y2k = in2[lo];
+                    const T y1m = (k == 0) ? T(0) : in1[hi], y2m = (k == 0) ? T(0) : in2[hi];
+                    const cplx<T> w = ldg_c<T>(tx + k);
+                    const cplx<T> v1 = cmul(mk<T>(y1k, -y1m), mk<T>(w.x, -w.y));
+                    const cplx<T> v2 = cmul(mk<T>(y2k, -y2m), mk<T>(w.x, -w.y));
+                    const cplx<T> ck = mk<T>(v1.x - v2.y, v1.y + v2.x);
+                    const cplx<T> cm = mk<T>(v1.x + v2.y, v2.x - v1.y);
+                    row[pad_index(k)] = cswap(ck);
+                    if (k > 0 && 2 * k != N) row[pad_index(N - k)] = cswap(cm);
+                }
+            }
+            __syncthreads();
+            contig_pass<T, RL, 0, 1, TPL, true, false, true, (P == 1)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc);
+            if constexpr (P > 1){ __syncthreads(); contig_pass<T, RL, 1, N1, TPL, true, false, false, (P == 2)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
+            if constexpr (P > 2){ __syncthreads(); contig_pass<T, RL, 2, N2, TPL, true, false, false, (P == 3)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
+            if constexpr (P > 3){ __syncthreads(); contig_pass<T, RL, 3, N3, TPL, true, false, false, true>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
+            __syncthreads();
+            // ---- the sequence v (swapped: .y is line 1, .x is line 2) goes out in Makhoul's order: x_2e = 2 v_e, x_2e+1 = 2 v_{n-1-e} ----------
+            if (valid){
+                const T two = do_scale ? T(2) * scale : T(2);
+                for(unsigned i = j; i < N; i += TPL){
+                    const unsigned p = (i & 1) ? N - 1 - (i >> 1) : (i >> 1);
+                    const cplx<T> c = row[pad_index(p)];
+                    const T f = (KIND == real_sin && (i & 1)) ? -two : two;
+                    out1[i] = f * c.y; out2[i] = f * c.x;
+                }
+            }
+        }
+        if (tile + gridDim.x < ntiles) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // real-data transforms along the middle / slow axis, second generation (plain stores): TWO adjacent real lines make ONE
 // complex line.  Neighbouring lines are adjacent in memory, so a row of 2 LPB reals IS a row of LPB complex numbers
 // c = x1 + i x2: the tile is loaded exactly like a tile of the complex kernel (16-byte asynchronous copies, no

@@ -357,6 +357,39 @@ int dispatch_strided_real2(int kind, int n, fft_args const &a, Launcher &L){
     }
 }
 
+// contiguous-axis DCT / DST, two lines per complex line (fft_contig_real2_kernel): the shapes of the complex contiguous kernel
+template<typename T, typename RL, int LPB, int MINB, int KIND, typename Launcher>
+int launch_contig_real2(fft_args const &a, Launcher &L){
+    long long const pairs = a.nlines / 2;
+    long long blocks = (pairs + LPB - 1) / LPB;
+    constexpr int PITCH = pad_index(RL::N) + 1;
+    size_t smem = ((sizeof(cplx<T>) * (size_t)PITCH * LPB + 15) / 16) * 16;
+    if (a.backward) return L.launch(fft_contig_real2_kernel<T, RL, LPB, MINB, KIND, true>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
+    return L.launch(fft_contig_real2_kernel<T, RL, LPB, MINB, KIND, false>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
+}
+template<typename T, int KIND, typename Launcher>
+int dispatch_contig_real2_kind(int n, fft_args const &a, Launcher &L){
+    switch(n){
+        case 32:   return launch_contig_real2<T, radix_list<8, 4, 1, 1>,   32, 6, KIND>(a, L);
+        case 64:   return launch_contig_real2<T, radix_list<8, 8, 1, 1>,   16, 6, KIND>(a, L);
+        case 128:  return launch_contig_real2<T, radix_list<8, 4, 4, 1>,    8, 6, KIND>(a, L);
+        case 256:  return launch_contig_real2<T, radix_list<16, 16, 1, 1>,  4, 6, KIND>(a, L);
+        case 512:  return launch_contig_real2<T, radix_list<4, 8, 16, 1>,   2, 8, KIND>(a, L);
+        case 1024: return launch_contig_real2<T, radix_list<16, 8, 8, 1>,   1, 4, KIND>(a, L);
+        case 2048: return launch_contig_real2<T, radix_list<8, 8, 8, 4>,    1, 2, KIND>(a, L);
+        case 4096: return launch_contig_real2<T, radix_list<8, 8, 8, 8>,    1, 1, KIND>(a, L);
+        default: return -1;
+    }
+}
+template<typename T, typename Launcher>
+int dispatch_contig_real2(int kind, int n, fft_args const &a, Launcher &L){
+    switch(kind){
+        case real_cos: return dispatch_contig_real2_kind<T, real_cos>(n, a, L);
+        case real_sin: return dispatch_contig_real2_kind<T, real_sin>(n, a, L);
+        default: return -1;
+    }
+}
+
 template<typename T, bool SCATTER, typename Launcher>
 int dispatch_strided_real(int kind, int m, fft_args const &a, Launcher &L){
     switch(kind){

@@ -4,4 +4,5 @@
 
 namespace b200 {
 int run_sreal2_f32(int kind, int n, fft_args const &a, cuda_launcher &L){ return dispatch_strided_real2<float>(kind, n, a, L); }
+int run_creal2_f32(int kind, int n, fft_args const &a, cuda_launcher &L){ return dispatch_contig_real2<float>(kind, n, a, L); }
 }

@@ -4,4 +4,5 @@
 
 namespace b200 {
 int run_sreal2_f64(int kind, int n, fft_args const &a, cuda_launcher &L){ return dispatch_strided_real2<double>(kind, n, a, L); }
+int run_creal2_f64(int kind, int n, fft_args const &a, cuda_launcher &L){ return dispatch_contig_real2<double>(kind, n, a, L); }
 }

@@ -25,6 +25,10 @@ struct emul_launcher {
     }
     int run_real(bool strided, bool is_float, bool scatter, int kind, int m, b200::fft_args const &a){
         using namespace b200;
+        if (not strided and not scatter and contig_real2_applies(kind, m, a)){
+            int const rc = is_float ? dispatch_contig_real2<float>(kind, 2 * m, a, *this) : dispatch_contig_real2<double>(kind, 2 * m, a, *this);
+            if (rc != -1) return rc;
+        }
         if (strided and not scatter and real2_applies(is_float, kind, m, a)){
             int const rc = is_float ? dispatch_strided_real2<float>(kind, 2 * m, a, *this) : dispatch_strided_real2<double>(kind, 2 * m, a, *this);
             if (rc != -1) return rc;

@@ -94,27 +94,22 @@ int main(){
             CK(cudaMemset(x, 0, elems*8));
         }
         a.backward = 0;
-        printf("-- contig dct2 kernel, cos forward\n");
-#define DV(RL, LPB, MINB, TPL, label) report(label, gb_r2r, timeit([&]{ run_dct(fft_contig_dct_kernel<double, RL, LPB, MINB, real_cos, false, TPL>, TPL * LPB, pitch * LPB, LPB); }));
-        DV(R488, 4, 4, 32, "dct2 fwd <4,8,8> TPL32 LPB4 minb4 (128thr)")
-        DV(R488, 4, 6, 32, "dct2 fwd <4,8,8> TPL32 LPB4 minb6 (128thr)")
-        DV(R488, 2, 12, 32, "dct2 fwd <4,8,8> TPL32 LPB2 minb12 (64thr)")
-        DV(R488, 8, 3, 32, "dct2 fwd <4,8,8> TPL32 LPB8 minb3 (256thr)")
-        DV(R884b, 4, 6, 16, "dct2 fwd <8,8,4> TPL16 LPB4 minb6 (64thr)")
-        DV(R884b, 8, 4, 16, "dct2 fwd <8,8,4> TPL16 LPB8 minb4 (128thr)")
-        DV(R448, 4, 6, 16, "dct2 fwd <4,4,16> TPL16 LPB4 minb6 (64thr)")
-        DV(R448, 8, 4, 16, "dct2 fwd <4,4,16> TPL16 LPB8 minb4 (128thr)")
-        a.backward = 1;
-        printf("-- contig dct2 kernel, cos backward\n");
-#define DB(RL, LPB, MINB, TPL, label) report(label, gb_r2r, timeit([&]{ run_dct(fft_contig_dct_kernel<double, RL, LPB, MINB, real_cos, true, TPL>, TPL * LPB, pitch * LPB, LPB); }));
-        DB(R884b, 4, 4, 32, "dct2 bwd <8,8,4> TPL32 LPB4 minb4 (128thr)")
-        DB(R884b, 4, 6, 32, "dct2 bwd <8,8,4> TPL32 LPB4 minb6 (128thr)")
-        DB(R884b, 2, 12, 32, "dct2 bwd <8,8,4> TPL32 LPB2 minb12 (64thr)")
-        DB(R884b, 8, 3, 32, "dct2 bwd <8,8,4> TPL32 LPB8 minb3 (256thr)")
-        DB(R884b, 4, 6, 16, "dct2 bwd <8,8,4> TPL16 LPB4 minb6 (64thr)")
-        DB(R488, 4, 6, 16, "dct2 bwd <4,8,8> TPL16 LPB4 minb6 (64thr)")
-        DB(R1644, 4, 6, 16, "dct2 bwd <16,4,4> TPL16 LPB4 minb6 (64thr)")
-        DB(R1644, 8, 4, 16, "dct2 bwd <16,4,4> TPL16 LPB8 minb4 (128thr)")
+    }
+    // ---- third-generation contiguous DCT kernel: two neighbouring lines per complex line, full-length Stockham passes -----------
+    {
+        a.count_a = n * n; a.in = x; a.out = x; a.ig = a.og = line_geom{1, n, 0}; a.twiddle0 = tw; a.in_step = a.out_step = 0;
+        using C4816 = radix_list<4,8,16,1>; using C888 = radix_list<8,8,8,1>; using C1684 = radix_list<16,8,4,1>;
+        for(int backward=0; backward<2; backward++){
+            a.backward = backward;
+            printf("-- contig real2 kind cos %s\n", backward ? "backward" : "forward");
+#define C2(RL, LPB, MINB, label) report(label, gb_r2r, timeit([&]{ launch_contig_real2<double, RL, LPB, MINB, real_cos>(a, l); }));
+            C2(C4816, 2, 8, "contig_real2 <4,8,16> LPB2 minb8 (64thr)")
+            C2(C4816, 4, 4, "contig_real2 <4,8,16> LPB4 minb4 (128thr)")
+            C2(C4816, 2, 12, "contig_real2 <4,8,16> LPB2 minb12 (64thr)")
+            C2(C888, 2, 6, "contig_real2 <8,8,8> LPB2 minb6 (128thr)")
+            C2(C888, 4, 3, "contig_real2 <8,8,8> LPB4 minb3 (256thr)")
+            C2(C1684, 2, 8, "contig_real2 <16,8,4> LPB2 minb8 (64thr)")
+        }
         a.backward = 0;
     }
     // ---- middle axis (stride n, neighbours adjacent) ----------------------------------------------------------------------
