@@ -58,6 +58,7 @@ def load():
     sig("b200_copy_to_device", c_int, c_vp, c_vp, ctypes.c_size_t, c_vp)
     sig("b200_copy_to_host", c_int, c_vp, c_vp, ctypes.c_size_t, c_vp)
     sig("b200_copy_on_device", c_int, c_vp, c_vp, ctypes.c_size_t, c_vp)
+    sig("b200_copy_any", c_int, c_vp, c_vp, ctypes.c_size_t)
     sig("b200_stream_synchronize", c_int, c_vp)
     sig("b200_device_set", c_int, c_int)
     sig("b200_fft1d_create", c_int, ctypes.POINTER(b200_fft1d_desc), ctypes.POINTER(c_vp))

@@ -251,6 +251,7 @@ public:
     int barrier(cudaStream_t) override { group->sync(); return 0; }
     const char* kind() const override { return "threads"; }
     void after_peer_barrier() override { group->sync(); }
+    void before_peer_barrier() override { group->sync(); }
     bool map_peers(void *local, size_t bytes, std::vector<void*> &peers) override {
         (void) bytes;
         const char *off = std::getenv("HEFFTE_B200_DISABLE_P2P");

@@ -40,6 +40,11 @@ public:
     // kernels of different streams can share a hardware queue, and a spinning barrier kernel followed by dependent work of the
     // same stream would otherwise block the barrier kernel of another rank queued behind it.  One process per GPU: nothing to do.
     virtual void after_peer_barrier(){}
+    // Called right before a peer barrier kernel is enqueued.  Ranks that are host threads sharing one GPU rendezvous here as
+    // well: the first launch of a kernel loads its module lazily, which waits for the kernels running on the device -- a rank
+    // without work in a stage (sub-communicator plans) would already spin in its barrier kernel, waiting for the very rank whose
+    // launch cannot start.  After this rendezvous every rank has ENQUEUED its stage before any barrier kernel of the fence exists.
+    virtual void before_peer_barrier(){}
 protected:
     int my_rank = 0, nranks = 1;
 };

@@ -354,6 +354,11 @@ int b200_copy_on_device(const void *source, void *destination, size_t bytes, voi
     if (bytes == 0) return B200_SUCCESS;
     return check_cuda(cudaMemcpyAsync(destination, source, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)), "copy on device");
 }
+// any mix of host and device pointers (unified addressing), synchronous -- what a GPU-aware message layer does with the buffers it is handed
+int b200_copy_any(void *destination, const void *source, size_t bytes){
+    if (bytes == 0) return B200_SUCCESS;
+    return check_cuda(cudaMemcpy(destination, source, bytes, cudaMemcpyDefault), "copy");
+}
 int b200_stream_synchronize(void *stream){ return check_cuda(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "stream synchronize"); }
 int b200_stream_create(void **stream){
     if (stream == nullptr) return fail(B200_ERR_INVALID, "null argument");

@@ -1618,119 +1618,203 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_real_kernel(fft_a
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// DCT / DST along contiguous lines, third generation (plain stores): two neighbouring lines x1, x2 form ONE complex line
-// c = x1 + i x2 (see fft_strided_real2_kernel for the algebra) and the complex Stockham passes run at the full length n.  The
-// first pass gathers its legs straight from global memory in Makhoul's order (8-byte loads from both lines, the sign of the sine
-// transform on the way); the lines are separated from the pair (k, n-k) of the spectrum in shared memory and stored with unit
-// stride.  Backward: the pairs are built from unit-stride loads, the last pass leaves the sequence in shared memory and the
-// rows go out in Makhoul's order with unit stride.
+// real-data transforms along contiguous lines, second generation (plain stores): two neighbouring lines x1, x2 form ONE complex
+// line c = x1 + i x2 (see fft_strided_real2_kernel for the algebra) and the complex Stockham passes run at the full length n.
+// Only the passes in between touch shared memory: the schedule starts and ends with the same radix R and a thread owns the
+// butterflies q and n/R - q of the first and of the last pass, so that every pair (k, n-k) of the spectrum sits in the
+// registers of ONE thread --
+//   forward:  the first pass gathers its legs straight from global memory (cosine / sine: in Makhoul's order, the sign of the
+//             sine transform on the way); the last pass separates the two lines from its pairs and stores them: y_k and
+//             y_{n-k} (quarter-wave twiddle), or the two half spectra of r2c, unit stride across the threads;
+//   backward: the first pass builds C_k and C_{n-k} from unit-stride loads of both lines; the last pass stores the two real
+//             lines from its registers (cosine / sine: in Makhoul's order).
+// Thread 0 of a line owns q = 0 and q = n/2R, whose pairs lie inside one butterfly (and the self-conjugate entries 0, n/2).
 // ---------------------------------------------------------------------------------------------------------
-template<typename T, typename RL, int LPB, int MINB, int KIND, bool BWD, int TPL_ = RL::N / RL::rmax>
-__global__ void __launch_bounds__(TPL_ * LPB, MINB) fft_contig_real2_kernel(fft_args a0){
+template<typename T> __device__ __forceinline__ void pair_split(cplx<T> ck, cplx<T> cm, cplx<T> &v1, cplx<T> &v2){
+    const T half = static_cast<T>(0.5);          // V1_k = (C_k + conj C_{n-k}) / 2,   V2_k = -i (C_k - conj C_{n-k}) / 2
+    v1 = mk<T>((ck.x + cm.x) * half, (ck.y - cm.y) * half);
+    v2 = mk<T>((ck.y + cm.y) * half, (cm.x - ck.x) * half);
+}
+template<typename T> __device__ __forceinline__ void pair_merge(cplx<T> v1, cplx<T> v2, cplx<T> &ck, cplx<T> &cm){
+    ck = mk<T>(v1.x - v2.y, v1.y + v2.x);        // C_k = V1_k + i V2_k,   C_{n-k} = conj(V1_k) + i conj(V2_k)
+    cm = mk<T>(v1.x + v2.y, v2.x - v1.y);
+}
+
+template<typename T, typename RL, int LPB, int MINB, int KIND, bool BWD>
+__global__ void __launch_bounds__((RL::N / (2 * RL::radix(0))) * LPB, MINB) fft_contig_real2_kernel(fft_args a0){
     B200_DYN_SMEM(smem_raw);
-    static_assert(KIND == real_cos || KIND == real_sin, "cosine / sine transforms");
     batch_shift shift;
     const fft_args a = batch_entry(a0, shift);
     constexpr unsigned N = RL::N;
-    constexpr int TPL = TPL_;
     constexpr int P = RL::passes;
-    constexpr unsigned PITCH = pad_index(RL::N) + 1;
-    constexpr int N1 = RL::radix(0), N2 = N1 * RL::radix(1), N3 = N2 * RL::radix(2);
+    constexpr unsigned R = RL::radix(0), NB = N / R;
+    constexpr int TPL = NB / 2;
+    static_assert(P >= 2 && RL::radix(P - 1) == R && R % 2 == 0, "the schedule starts and ends with the same even radix");
+    constexpr bool R2C = (KIND == real_r2c);
+    constexpr unsigned PITCH = pad_index(N) + 1;
+    constexpr int N1 = RL::radix(0), N2 = N1 * RL::radix(1);
     const unsigned j = threadIdx.x % TPL, t = threadIdx.x / TPL;
     cplx<T> *row = reinterpret_cast<cplx<T>*>(smem_raw) + t * PITCH;
     const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle0);
     const cplx<T> *tx = reinterpret_cast<const cplx<T>*>(a.twiddle2);
     const T scale = static_cast<T>(a.scale);
     const bool do_scale = a.scale != 1.0;
+    const T factor = (R2C ? T(1) : T(2)) * (do_scale ? scale : T(1));
     const scatter_ctx sc{nullptr, 0, 0, 0};
     const unsigned npairs = static_cast<unsigned>(a.nlines / 2);
     const unsigned ntiles = (npairs + LPB - 1) / LPB;
+    const unsigned qa = j, qb = (j == 0) ? NB / 2 : NB - j;        // the two butterflies of this thread, first and last pass
     for(unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
         const unsigned pair = tile * LPB + t;
         const bool valid = pair < npairs;
-        const T *in1 = reinterpret_cast<const T*>(a.in) + (valid ? tile_line_offset(a.ig, a.count_a, 2 * pair) : 0);
-        const T *in2 = reinterpret_cast<const T*>(a.in) + (valid ? tile_line_offset(a.ig, a.count_a, 2 * pair + 1) : 0);
-        T *out1 = reinterpret_cast<T*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, 2 * pair) : 0);
-        T *out2 = reinterpret_cast<T*>(a.out) + (valid ? tile_line_offset(a.og, a.count_a, 2 * pair + 1) : 0);
+        const long long i1 = valid ? tile_line_offset(a.ig, a.count_a, 2 * pair) : 0, i2 = valid ? tile_line_offset(a.ig, a.count_a, 2 * pair + 1) : 0;
+        const long long o1 = valid ? tile_line_offset(a.og, a.count_a, 2 * pair) : 0, o2 = valid ? tile_line_offset(a.og, a.count_a, 2 * pair + 1) : 0;
+        cplx<T> v[2][R];
+        // f(C_k slot, C_{n-k} slot, k, self): every pair this thread owns, k <= n/2; `self`: k is 0 or n/2 and the two slots are one
+        auto for_each_pair = [&](auto &&f){
+            if (j != 0){
+                #pragma unroll
+                for(unsigned r=0; r<R/2; r++){
+                    f(v[0][r], v[1][R - 1 - r], qa + r * NB, false);
+                    f(v[1][r], v[0][R - 1 - r], qb + r * NB, false);
+                }
+            }else{
+                f(v[0][0], v[0][0], 0u, true);
+                f(v[0][R / 2], v[0][R / 2], N / 2, true);
+                #pragma unroll
+                for(unsigned r=1; r<R/2; r++) f(v[0][r], v[0][R - r], r * NB, false);
+                #pragma unroll
+                for(unsigned r=0; r<R/2; r++) f(v[1][r], v[1][R - 1 - r], NB / 2 + r * NB, false);
+            }
+        };
+        // first pass of a Stockham schedule: no twiddles, butterfly q writes positions q R + r
+        auto first_pass_out = [&](){
+            #pragma unroll
+            for(unsigned u=0; u<2; u++){
+                const unsigned q = u ? qb : qa;
+                butterfly<T, R>::run(v[u]);
+                #pragma unroll
+                for(unsigned r=0; r<R; r++) row[pad_index(q * R + r)] = v[u][r];
+            }
+        };
+        // last pass: legs q + r NB from the row, twiddle W_n^(q r), butterfly; v[u][r] is then entry q + r NB of the result
+        auto last_pass_in = [&](){
+            #pragma unroll
+            for(unsigned u=0; u<2; u++){
+                const unsigned q = u ? qb : qa;
+                #pragma unroll
+                for(unsigned r=0; r<R; r++) v[u][r] = row[pad_index(q + r * NB)];
+                apply_twiddles<T, R, true>(v[u], tw, static_cast<int>(q));
+                butterfly<T, R>::run(v[u]);
+            }
+        };
 
         if constexpr (!BWD){
-            // ---- first pass: legs gathered in Makhoul's order from both lines --------------------------------------------------------
+            // ---- first pass: legs straight from the two lines ---------------------------------------------------------------------------------
             {
-                constexpr unsigned R = RL::radix(0), NB = N / R, BPT = NB / TPL;
-                cplx<T> v[BPT][R];
+                const T *in1 = reinterpret_cast<const T*>(a.in) + i1, *in2 = reinterpret_cast<const T*>(a.in) + i2;
                 #pragma unroll
-                for(unsigned u=0; u<BPT; u++){
-                    const unsigned q = j + u * TPL;
+                for(unsigned u=0; u<2; u++){
+                    const unsigned q = u ? qb : qa;
                     #pragma unroll
                     for(unsigned r=0; r<R; r++){
-                        const unsigned p = q + r * NB;                                          // position in the permuted sequence
-                        const bool upper = 2 * p >= N;
-                        const unsigned i = upper ? 2 * (N - 1 - p) + 1 : 2 * p;                 // the sample that sits there
+                        const unsigned p = q + r * NB;                                          // position in the (permuted) sequence
+                        unsigned i = p;
+                        bool upper = false;
+                        if constexpr (!R2C){ upper = 2 * p >= N; i = upper ? 2 * (N - 1 - p) + 1 : 2 * p; }
                         T x1 = valid ? in1[i] : T(0), x2 = valid ? in2[i] : T(0);
                         if (KIND == real_sin && upper){ x1 = -x1; x2 = -x2; }
                         v[u][r] = mk<T>(x1, x2);
                     }
                 }
-                #pragma unroll
-                for(unsigned u=0; u<BPT; u++){
-                    const unsigned q = j + u * TPL;
-                    butterfly<T, R>::run(v[u]);
-                    #pragma unroll
-                    for(unsigned r=0; r<R; r++) row[pad_index(q * R + r)] = v[u][r];
-                }
+                first_pass_out();
             }
-            if constexpr (P > 1){ __syncthreads(); contig_pass<T, RL, 1, N1, TPL, false, false, false, (P == 2)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
-            if constexpr (P > 2){ __syncthreads(); contig_pass<T, RL, 2, N2, TPL, false, false, false, (P == 3)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
-            if constexpr (P > 3){ __syncthreads(); contig_pass<T, RL, 3, N3, TPL, false, false, false, true>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
+            if constexpr (P > 2){ __syncthreads(); contig_pass<T, RL, 1, N1, TPL, false, false>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
+            if constexpr (P > 3){ __syncthreads(); contig_pass<T, RL, 2, N2, TPL, false, false>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
             __syncthreads();
-            // ---- the two lines apart, quarter-wave twiddle, unit-stride stores -------------------------------------------------------
+            last_pass_in();
+            // ---- the two lines apart, straight from the registers ----------------------------------------------------------------------------
             if (valid){
-                const T half = static_cast<T>(0.5);
-                const T two = do_scale ? T(2) * scale : T(2);
-                for(unsigned k = j; k <= N / 2; k += TPL){
-                    const cplx<T> ck = row[pad_index(k)], cm = row[pad_index((N - k) % N)];
-                    const cplx<T> v1 = mk<T>((ck.x + cm.x) * half, (ck.y - cm.y) * half);
-                    const cplx<T> v2 = mk<T>((ck.y + cm.y) * half, (cm.x - ck.x) * half);
-                    const cplx<T> w = ldg_c<T>(tx + k);
-                    const cplx<T> z1 = cmul(w, v1), z2 = cmul(w, v2);
-                    const unsigned lo = (KIND == real_sin) ? N - 1 - k : k;
-                    out1[lo] = two * z1.x; out2[lo] = two * z2.x;
-                    if (k > 0 && 2 * k != N){
-                        const unsigned hi = (KIND == real_sin) ? k - 1 : N - k;
-                        out1[hi] = -two * z1.y; out2[hi] = -two * z2.y;
-                    }
+                if constexpr (R2C){
+                    cplx<T> *out1 = reinterpret_cast<cplx<T>*>(a.out) + o1, *out2 = reinterpret_cast<cplx<T>*>(a.out) + o2;
+                    for_each_pair([&](cplx<T> &ck, cplx<T> &cm, unsigned k, bool){
+                        cplx<T> v1, v2;
+                        pair_split<T>(ck, cm, v1, v2);
+                        out1[k] = mk<T>(v1.x * factor, v1.y * factor);
+                        out2[k] = mk<T>(v2.x * factor, v2.y * factor);
+                    });
+                }else{
+                    T *out1 = reinterpret_cast<T*>(a.out) + o1, *out2 = reinterpret_cast<T*>(a.out) + o2;
+                    for_each_pair([&](cplx<T> &ck, cplx<T> &cm, unsigned k, bool self){
+                        cplx<T> v1, v2;
+                        pair_split<T>(ck, cm, v1, v2);
+                        const cplx<T> w = ldg_c<T>(tx + k);
+                        const cplx<T> z1 = cmul(w, v1), z2 = cmul(w, v2);
+                        const unsigned lo = (KIND == real_sin) ? N - 1 - k : k;
+                        out1[lo] = factor * z1.x; out2[lo] = factor * z2.x;
+                        if (!self){
+                            const unsigned hi = (KIND == real_sin) ? k - 1 : N - k;
+                            out1[hi] = -factor * z1.y; out2[hi] = -factor * z2.y;
+                        }
+                    });
                 }
             }
         }else{
-            // ---- C_k and C_{n-k} from unit-stride loads of both lines, written swapped for the forward engine ----------------------------------
+            // ---- first pass: C_k and C_{n-k} from unit-stride loads of both lines, swapped for the forward engine ----------------------------
             if (valid){
-                for(unsigned k = j; k <= N / 2; k += TPL){
-                    const unsigned lo = (KIND == real_sin) ? N - 1 - k : k, hi = (KIND == real_sin) ? k - 1 : N - k;
-                    const T y1k = in1[lo], y2k = in2[lo];
-                    const T y1m = (k == 0) ? T(0) : in1[hi], y2m = (k == 0) ? T(0) : in2[hi];
-                    const cplx<T> w = ldg_c<T>(tx + k);
-                    const cplx<T> v1 = cmul(mk<T>(y1k, -y1m), mk<T>(w.x, -w.y));
-                    const cplx<T> v2 = cmul(mk<T>(y2k, -y2m), mk<T>(w.x, -w.y));
-                    const cplx<T> ck = mk<T>(v1.x - v2.y, v1.y + v2.x);
-                    const cplx<T> cm = mk<T>(v1.x + v2.y, v2.x - v1.y);
-                    row[pad_index(k)] = cswap(ck);
-                    if (k > 0 && 2 * k != N) row[pad_index(N - k)] = cswap(cm);
+                if constexpr (R2C){
+                    const cplx<T> *in1 = reinterpret_cast<const cplx<T>*>(a.in) + i1, *in2 = reinterpret_cast<const cplx<T>*>(a.in) + i2;
+                    for_each_pair([&](cplx<T> &ck, cplx<T> &cm, unsigned k, bool self){
+                        cplx<T> v1 = in1[k], v2 = in2[k];
+                        if (self){ v1.y = 0; v2.y = 0; }                 // c2r ignores the imaginary part of the self-conjugate entries
+                        cplx<T> c, m;
+                        pair_merge<T>(v1, v2, c, m);
+                        ck = cswap(c);
+                        if (!self) cm = cswap(m);
+                    });
+                }else{
+                    const T *in1 = reinterpret_cast<const T*>(a.in) + i1, *in2 = reinterpret_cast<const T*>(a.in) + i2;
+                    for_each_pair([&](cplx<T> &ck, cplx<T> &cm, unsigned k, bool self){
+                        // V_k = conj(w_k) (y_k - i y_{n-k}), y_n := 0
+                        const unsigned lo = (KIND == real_sin) ? N - 1 - k : k, hi = (KIND == real_sin) ? k - 1 : N - k;
+                        const T y1k = in1[lo], y2k = in2[lo];
+                        const T y1m = (k == 0) ? T(0) : in1[hi], y2m = (k == 0) ? T(0) : in2[hi];
+                        const cplx<T> w = ldg_c<T>(tx + k);
+                        const cplx<T> v1 = cmul(mk<T>(y1k, -y1m), mk<T>(w.x, -w.y));
+                        const cplx<T> v2 = cmul(mk<T>(y2k, -y2m), mk<T>(w.x, -w.y));
+                        cplx<T> c, m;
+                        pair_merge<T>(v1, v2, c, m);
+                        ck = cswap(c);
+                        if (!self) cm = cswap(m);
+                    });
                 }
+            }else{
+                #pragma unroll
+                for(unsigned r=0; r<R; r++){ v[0][r] = mk<T>(0, 0); v[1][r] = mk<T>(0, 0); }
             }
+            first_pass_out();
+            if constexpr (P > 2){ __syncthreads(); contig_pass<T, RL, 1, N1, TPL, false, false>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
+            if constexpr (P > 3){ __syncthreads(); contig_pass<T, RL, 2, N2, TPL, false, false>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
             __syncthreads();
-            contig_pass<T, RL, 0, 1, TPL, true, false, true, (P == 1)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc);
-            if constexpr (P > 1){ __syncthreads(); contig_pass<T, RL, 1, N1, TPL, true, false, false, (P == 2)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
-            if constexpr (P > 2){ __syncthreads(); contig_pass<T, RL, 2, N2, TPL, true, false, false, (P == 3)>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
-            if constexpr (P > 3){ __syncthreads(); contig_pass<T, RL, 3, N3, TPL, true, false, false, true>(row, j, valid, nullptr, nullptr, 1, 1, tw, scale, do_scale, sc); }
-            __syncthreads();
-            // ---- the sequence v (swapped: .y is line 1, .x is line 2) goes out in Makhoul's order: x_2e = 2 v_e, x_2e+1 = 2 v_{n-1-e} ----------
+            last_pass_in();
+            // ---- entry p of the result (swapped: .y is line 1, .x is line 2); cosine / sine: x_2e = 2 v_e, x_2e+1 = 2 v_{n-1-e} --------------
             if (valid){
-                const T two = do_scale ? T(2) * scale : T(2);
-                for(unsigned i = j; i < N; i += TPL){
-                    const unsigned p = (i & 1) ? N - 1 - (i >> 1) : (i >> 1);
-                    const cplx<T> c = row[pad_index(p)];
-                    const T f = (KIND == real_sin && (i & 1)) ? -two : two;
-                    out1[i] = f * c.y; out2[i] = f * c.x;
+                T *out1 = reinterpret_cast<T*>(a.out) + o1, *out2 = reinterpret_cast<T*>(a.out) + o2;
+                #pragma unroll
+                for(unsigned u=0; u<2; u++){
+                    const unsigned q = u ? qb : qa;
+                    #pragma unroll
+                    for(unsigned r=0; r<R; r++){
+                        const unsigned p = q + r * NB;
+                        unsigned i = p;
+                        T f = factor;
+                        if constexpr (!R2C){
+                            const bool upper = 2 * p >= N;
+                            i = upper ? 2 * (N - 1 - p) + 1 : 2 * p;
+                            if (KIND == real_sin && upper) f = -f;
+                        }
+                        out1[i] = f * v[u][r].y; out2[i] = f * v[u][r].x;
+                    }
                 }
             }
         }

@@ -4,6 +4,7 @@
 #pragma once
 
 #include "fft_device.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -28,6 +29,10 @@ constexpr bool is_mixed_fast_length(long long n){
 constexpr bool is_mixed_fast_half(long long m){ return is_mixed_fast_length(m) && m != 48 && m != 100 && m != 3584; }
 constexpr bool is_fast_length(long long n){ return (is_pow2(n) && n >= pow2_min && n <= pow2_max) || is_mixed_fast_length(n); }
 
+inline int strided_1024_variant(){
+    static int const v = []{ const char *e = std::getenv("HEFFTE_B200_STRIDED_1024"); return (e != nullptr) ? std::atoi(e) : 0; }();
+    return v;
+}
 template<typename T, typename RL, int TPL, int LPB, int MINB, bool SCATTER, typename Launcher>
 int launch_strided(fft_args const &a, Launcher &L){
     long long blocks = (a.nlines + LPB - 1) / LPB;
@@ -65,7 +70,14 @@ int dispatch_strided(int n, fft_args const &a, Launcher &L){
         case 128:  return launch_strided<T, radix_list<8, 4, 4, 1>,  16 / M,  8 * M, 2, SCATTER>(a, L);
         case 256:  return launch_strided<T, radix_list<8, 8, 4, 1>,  32 / M,  8 * M, 2, SCATTER>(a, L);
         case 512:  return launch_strided<T, radix_list<8, 8, 8, 1>,  32 / M,  8 * M, 3, SCATTER>(a, L);
-        case 1024: return launch_strided<T, radix_list<16, 8, 8, 1>, 32 / M,  8 * M, 1, SCATTER>(a, L);
+        case 1024:
+            // a 128 KB tile leaves ONE CTA per SM: its loads, passes and stores follow each other and nothing hides them.  Half
+            // the lines (64-byte rows, 64 KB) let three CTAs share the SM; developer knob HEFFTE_B200_STRIDED_1024 = 0 | 1 | 2
+            switch(strided_1024_variant()){
+                case 1:  return launch_strided<T, radix_list<16, 8, 8, 1>, 64,      8 * M, 1, SCATTER>(a, L);   // more threads on the big tile
+                case 2:  return launch_strided<T, radix_list<16, 8, 8, 1>, 64 / M,  4 * M, 3, SCATTER>(a, L);   // half tile, three CTAs per SM
+                default: return launch_strided<T, radix_list<16, 8, 8, 1>, 32 / M,  8 * M, 1, SCATTER>(a, L);
+            }
         case 2048: return launch_strided<T, radix_list<8, 8, 8, 4>, 128 / M,  4 * M, 1, SCATTER>(a, L);
         case 4096: return launch_strided<T, radix_list<8, 8, 8, 8>, 256 / M,  2 * M, 1, SCATTER>(a, L);
         // lengths with factors 3 and 5: TPL divides N / R for every radix R of the schedule; rows of the tile stay 128 bytes
@@ -357,26 +369,28 @@ int dispatch_strided_real2(int kind, int n, fft_args const &a, Launcher &L){
     }
 }
 
-// contiguous-axis DCT / DST, two lines per complex line (fft_contig_real2_kernel): the shapes of the complex contiguous kernel
+// contiguous-axis real transforms, two lines per complex line (fft_contig_real2_kernel): schedules that start and end with the
+// same radix R; a line pair is worked on by n / 2R threads
 template<typename T, typename RL, int LPB, int MINB, int KIND, typename Launcher>
 int launch_contig_real2(fft_args const &a, Launcher &L){
     long long const pairs = a.nlines / 2;
     long long blocks = (pairs + LPB - 1) / LPB;
     constexpr int PITCH = pad_index(RL::N) + 1;
+    constexpr int threads = (RL::N / (2 * RL::radix(0))) * LPB;
     size_t smem = ((sizeof(cplx<T>) * (size_t)PITCH * LPB + 15) / 16) * 16;
-    if (a.backward) return L.launch(fft_contig_real2_kernel<T, RL, LPB, MINB, KIND, true>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
-    return L.launch(fft_contig_real2_kernel<T, RL, LPB, MINB, KIND, false>, blocks, (RL::N / RL::rmax) * LPB, smem, a);
+    if (a.backward) return L.launch(fft_contig_real2_kernel<T, RL, LPB, MINB, KIND, true>, blocks, threads, smem, a);
+    return L.launch(fft_contig_real2_kernel<T, RL, LPB, MINB, KIND, false>, blocks, threads, smem, a);
 }
 template<typename T, int KIND, typename Launcher>
 int dispatch_contig_real2_kind(int n, fft_args const &a, Launcher &L){
     switch(n){
-        case 32:   return launch_contig_real2<T, radix_list<8, 4, 1, 1>,   32, 6, KIND>(a, L);
+        case 32:   return launch_contig_real2<T, radix_list<4, 2, 4, 1>,   16, 6, KIND>(a, L);
         case 64:   return launch_contig_real2<T, radix_list<8, 8, 1, 1>,   16, 6, KIND>(a, L);
-        case 128:  return launch_contig_real2<T, radix_list<8, 4, 4, 1>,    8, 6, KIND>(a, L);
-        case 256:  return launch_contig_real2<T, radix_list<16, 16, 1, 1>,  4, 6, KIND>(a, L);
-        case 512:  return launch_contig_real2<T, radix_list<4, 8, 16, 1>,   2, 8, KIND>(a, L);
-        case 1024: return launch_contig_real2<T, radix_list<16, 8, 8, 1>,   1, 4, KIND>(a, L);
-        case 2048: return launch_contig_real2<T, radix_list<8, 8, 8, 4>,    1, 2, KIND>(a, L);
+        case 128:  return launch_contig_real2<T, radix_list<4, 8, 4, 1>,    4, 6, KIND>(a, L);
+        case 256:  return launch_contig_real2<T, radix_list<8, 4, 8, 1>,    4, 6, KIND>(a, L);
+        case 512:  return launch_contig_real2<T, radix_list<8, 8, 8, 1>,    2, 8, KIND>(a, L);
+        case 1024: return launch_contig_real2<T, radix_list<8, 16, 8, 1>,   1, 4, KIND>(a, L);
+        case 2048: return launch_contig_real2<T, radix_list<8, 8, 4, 8>,    1, 2, KIND>(a, L);
         case 4096: return launch_contig_real2<T, radix_list<8, 8, 8, 8>,    1, 1, KIND>(a, L);
         default: return -1;
     }
@@ -384,6 +398,7 @@ int dispatch_contig_real2_kind(int n, fft_args const &a, Launcher &L){
 template<typename T, typename Launcher>
 int dispatch_contig_real2(int kind, int n, fft_args const &a, Launcher &L){
     switch(kind){
+        case real_r2c: return dispatch_contig_real2_kind<T, real_r2c>(n, a, L);
         case real_cos: return dispatch_contig_real2_kind<T, real_cos>(n, a, L);
         case real_sin: return dispatch_contig_real2_kind<T, real_sin>(n, a, L);
         default: return -1;

@@ -118,10 +118,10 @@ inline int make_host_plan(b200_fft1d_desc const &desc, host_plan &plan, const ch
 inline line_geom to_geom(b200_line_geom const &g){ return line_geom{g.stride, g.stride_a, g.stride_b}; }
 
 // the second-generation strided real kernel pairs adjacent lines: an even number of them per row, rows aligned to a complex number
-// contiguous lines, cosine / sine transforms: pairs of neighbouring lines (any alignment: the loads are scalar)
+// contiguous lines: pairs of neighbouring lines (real lines at any alignment: those loads are scalar)
 inline bool contig_real2_applies(int kind, int m, fft_args const &a){
     static bool const off = (std::getenv("HEFFTE_B200_REAL_KERNELS_V1") != nullptr);
-    return not off and (kind == real_cos or kind == real_sin) and is_real2_length(2LL * m) and a.nlines % 2 == 0 and a.count_a % 2 == 0 and
+    return not off and (kind == real_cos or kind == real_sin or kind == real_r2c) and is_real2_length(2LL * m) and a.nlines % 2 == 0 and a.count_a % 2 == 0 and
            a.ig.stride == 1 and a.og.stride == 1;
 }
 inline bool real2_applies(bool is_float, int kind, int m, fft_args const &a){

@@ -450,6 +450,7 @@ int transform3d::peer_fence(int precision){
     peer_state &P = peer[precision];
     P.epoch++;
     if (std::getenv("HEFFTE_B200_TRACE")) std::fprintf(stderr, "[b200 rank %d] fence %llu\n", me, P.epoch);
+    ccomm->before_peer_barrier();
     int rc = b200_peer_barrier(ccomm->size(), me, P.remote_slots.data(), P.arena, P.epoch, cstream);
     ccomm->after_peer_barrier();
     return rc;

@@ -56,6 +56,8 @@ int b200_device_free(void *device_pointer);
 int b200_copy_to_device(const void *host, void *device, size_t bytes, void *stream);
 int b200_copy_to_host(const void *device, void *host, size_t bytes, void *stream);
 int b200_copy_on_device(const void *source, void *destination, size_t bytes, void *stream);
+/* synchronous copy between any two host / device pointers (what a GPU-aware MPI does with the buffers it is handed) */
+int b200_copy_any(void *destination, const void *source, size_t bytes);
 int b200_stream_synchronize(void *stream);
 /* a non-blocking CUDA stream (cudaStream_t as void*).  Ranks that are host threads of one process (heffte_comm_create_threads)
  * need ONE STREAM PER RANK: the stream-ordered barrier between the ranks of a plan cannot complete on a shared stream.

@@ -109,6 +109,10 @@ def patch_tree(scratch):
         "std::is_same<backend_tag, backend::cufft_cos1>::value or", "std::is_same<backend_tag, backend::cufft_cos1>::value or std::is_same<backend_tag, backend::b200_cos1>::value or", 1))
     # 3. test/test_common.h: stream helpers of the tests, then the generic twin of every CUDA block of the tests and benchmarks
     edit(os.path.join(test, "test_common.h"), lambda t: insert_after(t, "void free_stream(cudaStream_t stream){ cudaStreamDestroy(stream); }\n#endif", TEST_COMMON_BLOCK))
+    # the ranks of these programs are host threads of one process (oracle/mpi_shim): the per-process bookkeeping of the test
+    # harness becomes per-thread (every rank assigns the name of the running test: a data race on one std::string otherwise)
+    edit(os.path.join(test, "test_common.h"), lambda t: t.replace("std::string heffte_test_name;", "thread_local std::string heffte_test_name;", 1)
+         .replace("bool heffte_test_pass  = true;", "thread_local bool heffte_test_pass  = true;", 1))
     for folder in (test, bench):
         for name in sorted(os.listdir(folder)):
             if name.endswith((".cpp", ".h")):
@@ -173,6 +177,7 @@ def build(only=None, keep=False, verbose=False, emulated=False):
         patch_tree(scratch)
         flags = ["-O2", "-std=c++14", "-pthread", "-Wno-deprecated-declarations", "-I", os.path.join(scratch, "include"), "-I", os.path.join(ROOT, "include"),
                  "-I", SHIM, "-I", os.path.join(scratch, "test"), "-I", os.path.join(scratch, "benchmarks")]
+        flags += os.environ.get("HEFFTE_B200_PLUGIN_CXXFLAGS", "").split()      # e.g. -fsanitize=address -g when chasing a bug
         objects = []
         jobs = []
         for src in ("src/heffte_plan_logic.cpp", "src/heffte_reshape3d.cpp", "src/heffte_compute_transform.cpp"):

@@ -17,8 +17,19 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <dlfcn.h>
 
 namespace {
+
+// "GPU-aware MPI": when the program is linked with the b200 library the buffers may be device pointers.  The copy goes through
+// the library's own b200_copy_any (cudaMemcpy with cudaMemcpyDefault, found at run time); pure host programs use memcpy.
+void copy_bytes(void *dst, const void *src, size_t bytes){
+    using copy_fn = int (*)(void*, const void*, size_t);
+    static copy_fn const device_copy = reinterpret_cast<copy_fn>(dlsym(RTLD_DEFAULT, "b200_copy_any"));
+    if (bytes == 0) return;
+    if (device_copy == nullptr){ std::memcpy(dst, src, bytes); return; }
+    if (device_copy(dst, src, bytes) != 0){ std::fprintf(stderr, "the MPI stand-in could not copy %zu bytes\n", bytes); std::abort(); }
+}
 
 inline size_t type_bytes(MPI_Datatype t){ return static_cast<size_t>(t & 0xff); }
 
@@ -95,7 +106,7 @@ bool try_match(shim_request_s *r){
     // caller holds mb.lock
     for(auto it = mb.inbox.begin(); it != mb.inbox.end(); ++it){
         if (it->src == r->src and (r->tag == MPI_ANY_TAG or it->tag == r->tag)){
-            std::memcpy(r->buf, it->payload.data(), std::min(r->bytes, it->payload.size()));
+            copy_bytes(r->buf, it->payload.data(), std::min(r->bytes, it->payload.size()));
             mb.inbox.erase(it);
             r->done = true;
             return true;
@@ -219,8 +230,8 @@ int MPI_Alltoall(const void *sendbuf, int sendcount, MPI_Datatype sendtype,
     comm->slot[me] = sendbuf;
     comm->barrier();
     for(int r=0; r<comm->size; r++)
-        std::memcpy(static_cast<char*>(recvbuf) + r * bytes,
-                    static_cast<const char*>(comm->slot[r]) + me * bytes, bytes);
+        copy_bytes(static_cast<char*>(recvbuf) + r * bytes,
+                   static_cast<const char*>(comm->slot[r]) + me * bytes, bytes);
     comm->barrier();
     return MPI_SUCCESS;
 }
@@ -238,8 +249,8 @@ int MPI_Alltoallv(const void *sendbuf, const int sendcounts[], const int sdispls
         auto const *peer = static_cast<const a2av_args*>(comm->slot[r]);
         size_t const bytes = std::min<size_t>(peer->counts[me] * peer->tsize, recvcounts[r] * rsize);
         if (bytes > 0)
-            std::memcpy(static_cast<char*>(recvbuf) + rdispls[r] * rsize,
-                        static_cast<const char*>(peer->buf) + peer->displs[me] * peer->tsize, bytes);
+            copy_bytes(static_cast<char*>(recvbuf) + rdispls[r] * rsize,
+                       static_cast<const char*>(peer->buf) + peer->displs[me] * peer->tsize, bytes);
     }
     comm->barrier();
     return MPI_SUCCESS;
@@ -284,7 +295,8 @@ int MPI_Send(const void *buf, int count, MPI_Datatype type, int dest, int tag, M
     m.src = rank_in(comm);
     m.tag = tag;
     size_t const bytes = count * type_bytes(type);
-    m.payload.assign(static_cast<const char*>(buf), static_cast<const char*>(buf) + bytes);
+    m.payload.resize(bytes);
+    copy_bytes(m.payload.data(), buf, bytes);
     mailbox &mb = *comm->boxes[dest];
     {
         std::lock_guard<std::mutex> guard(mb.lock);

@@ -138,7 +138,7 @@ typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 struct cudaIpcMemHandle_t { char reserved[64]; };
 enum { cudaSuccess = 0, cudaErrorEmulation = 999, cudaErrorPeerAccessAlreadyEnabled = 704 };
-enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum { cudaEventDisableTiming = 2, cudaIpcMemLazyEnablePeerAccess = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 inline cudaError_t cudaMalloc(void **p, size_t bytes){ *p = std::malloc(bytes ? bytes : 1); return *p ? cudaSuccess : 2; }
 template<typename T> inline cudaError_t cudaMalloc(T **p, size_t bytes){ return cudaMalloc(reinterpret_cast<void**>(p), bytes); }

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-def _run_group(nranks, todo, expect_peer, budget_s=240):
+def _run_group(nranks, todo, expect_peer, budget_s=240, label=""):
     import heffte_b200 as hf
     comms = hf.comm_threads(nranks)
     gate = threading.Barrier(nranks)
@@ -27,7 +27,7 @@ def _run_group(nranks, todo, expect_peer, budget_s=240):
     done = [0] * nranks
     stop = threading.Event()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    log = open(os.path.join(ROOT, "gpurun_out", "threads_%d_%s.log" % (nranks, "peer" if expect_peer else "exchange")), "w")
+    log = open(os.path.join(ROOT, "gpurun_out", "threads_%d_%s%s.log" % (nranks, "peer" if expect_peer else "exchange", label)), "w")
 
     def body(rank):
         try:
@@ -64,7 +64,11 @@ def _run_group(nranks, todo, expect_peer, budget_s=240):
     log.close()
     if any(t.is_alive() for t in threads):
         # a rank is stuck inside a collective: nothing can be recovered in this process
-        print("thread-ranks hung; failures so far:", [f for f in failures if f], flush=True)
+        print("thread-ranks hung; failures so far:", [f for f in failures if f], "configs done per rank:", done, flush=True)
+        import faulthandler
+        import sys
+        faulthandler.dump_traceback(file=sys.stdout, all_threads=True)
+        sys.stdout.flush()
         os._exit(3)
     assert not any(failures), [f for f in failures if f]
     return min(done), max(worst)

@@ -35,7 +35,7 @@ def test_subcomm_plans_on_thread_ranks(lib, nranks):
     os.environ.pop("HEFFTE_B200_DISABLE_P2P", None)
     todo = [(c, 1) for c in configs(nranks, quick=True, subcomm=True) if c.get("subranks")]
     assert len(todo) == 3
-    done, _ = _run_group(nranks, todo, expect_peer=True)
+    done, _ = _run_group(nranks, todo, expect_peer=True, label="_subcomm")
     assert done == len(todo)
 
 

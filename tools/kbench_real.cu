@@ -95,20 +95,29 @@ int main(){
         }
         a.backward = 0;
     }
-    // ---- third-generation contiguous DCT kernel: two neighbouring lines per complex line, full-length Stockham passes -----------
+    // ---- second-generation contiguous kernel: two neighbouring lines per complex line, pairs (k, n-k) in the registers of one thread ----
     {
-        a.count_a = n * n; a.in = x; a.out = x; a.ig = a.og = line_geom{1, n, 0}; a.twiddle0 = tw; a.in_step = a.out_step = 0;
-        using C4816 = radix_list<4,8,16,1>; using C888 = radix_list<8,8,8,1>; using C1684 = radix_list<16,8,4,1>;
-        for(int backward=0; backward<2; backward++){
-            a.backward = backward;
-            printf("-- contig real2 kind cos %s\n", backward ? "backward" : "forward");
-#define C2(RL, LPB, MINB, label) report(label, gb_r2r, timeit([&]{ launch_contig_real2<double, RL, LPB, MINB, real_cos>(a, l); }));
-            C2(C4816, 2, 8, "contig_real2 <4,8,16> LPB2 minb8 (64thr)")
-            C2(C4816, 4, 4, "contig_real2 <4,8,16> LPB4 minb4 (128thr)")
-            C2(C4816, 2, 12, "contig_real2 <4,8,16> LPB2 minb12 (64thr)")
-            C2(C888, 2, 6, "contig_real2 <8,8,8> LPB2 minb6 (128thr)")
-            C2(C888, 4, 3, "contig_real2 <8,8,8> LPB4 minb3 (256thr)")
-            C2(C1684, 2, 8, "contig_real2 <16,8,4> LPB2 minb8 (64thr)")
+        a.count_a = n * n; a.twiddle0 = tw; a.in_step = a.out_step = 0;
+        using C888 = radix_list<8,8,8,1>;
+        for(int kind : {real_cos, real_r2c}){
+            for(int backward=0; backward<2; backward++){
+                a.backward = backward;
+                if (kind == real_r2c){
+                    line_geom rg{1, n, 0}, cg{1, n/2+1, 0};
+                    a.in = backward ? (void*)y : (void*)x; a.out = backward ? (void*)x : (void*)y;
+                    a.ig = backward ? cg : rg; a.og = backward ? rg : cg;
+                }else{ a.in = x; a.out = x; a.ig = a.og = line_geom{1, n, 0}; }
+                double gb = (kind == real_r2c) ? gb_r2c : gb_r2r;
+                printf("-- contig real2 kind %s %s\n", kind == real_r2c ? "r2c" : "cos", backward ? "backward" : "forward");
+#define C2(RL, LPB, MINB, label) if (kind == real_r2c) report(label, gb, timeit([&]{ launch_contig_real2<double, RL, LPB, MINB, real_r2c>(a, l); })); \
+                                 else report(label, gb, timeit([&]{ launch_contig_real2<double, RL, LPB, MINB, real_cos>(a, l); }));
+                C2(C888, 2, 8, "contig_real2 <8,8,8> LPB2 minb8 (64thr)")
+                C2(C888, 2, 6, "contig_real2 <8,8,8> LPB2 minb6 (64thr)")
+                C2(C888, 2, 12, "contig_real2 <8,8,8> LPB2 minb12 (64thr)")
+                C2(C888, 4, 4, "contig_real2 <8,8,8> LPB4 minb4 (128thr)")
+                C2(C888, 1, 12, "contig_real2 <8,8,8> LPB1 minb12 (32thr)")
+                C2(C888, 1, 16, "contig_real2 <8,8,8> LPB1 minb16 (32thr)")
+            }
         }
         a.backward = 0;
     }
