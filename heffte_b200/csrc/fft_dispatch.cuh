@@ -29,9 +29,9 @@ constexpr bool is_mixed_fast_length(long long n){
 constexpr bool is_mixed_fast_half(long long m){ return is_mixed_fast_length(m) && m != 48 && m != 100 && m != 3584; }
 constexpr bool is_fast_length(long long n){ return (is_pow2(n) && n >= pow2_min && n <= pow2_max) || is_mixed_fast_length(n); }
 
-inline int strided_1024_variant(){
-    static int const v = []{ const char *e = std::getenv("HEFFTE_B200_STRIDED_1024"); return (e != nullptr) ? std::atoi(e) : 0; }();
-    return v;
+inline int strided_big_variant(bool scatter){
+    static int const v = []{ const char *e = std::getenv("HEFFTE_B200_STRIDED_BIG"); return (e != nullptr) ? std::atoi(e) : -1; }();
+    return (v >= 0) ? v : (scatter ? 1 : 0);
 }
 template<typename T, typename RL, int TPL, int LPB, int MINB, bool SCATTER, typename Launcher>
 int launch_strided(fft_args const &a, Launcher &L){
@@ -70,16 +70,22 @@ int dispatch_strided(int n, fft_args const &a, Launcher &L){
         case 128:  return launch_strided<T, radix_list<8, 4, 4, 1>,  16 / M,  8 * M, 2, SCATTER>(a, L);
         case 256:  return launch_strided<T, radix_list<8, 8, 4, 1>,  32 / M,  8 * M, 2, SCATTER>(a, L);
         case 512:  return launch_strided<T, radix_list<8, 8, 8, 1>,  32 / M,  8 * M, 3, SCATTER>(a, L);
+        // 1024 points and more: the tile takes 128 KB, ONE CTA per SM.  Against NVLink what counts is the number of stores in
+        // flight: 1024 (fp32) / 512 (fp64) threads on the tile instead of 256 took the fused stages of 1024^3 fp32 on 2 GPUs from
+        // 268 to 706 GB/s (profiles/r02_multi_2gpu/bench_c2c_f32_1024_tile_variant_*.log); half tiles with three CTAs per SM reach
+        // 442.  Developer knob HEFFTE_B200_STRIDED_BIG = 0 (few threads) | 1 (many) | 2 (half tiles, 1024 only).
         case 1024:
-            // a 128 KB tile leaves ONE CTA per SM: its loads, passes and stores follow each other and nothing hides them.  Half
-            // the lines (64-byte rows, 64 KB) let three CTAs share the SM; developer knob HEFFTE_B200_STRIDED_1024 = 0 | 1 | 2
-            switch(strided_1024_variant()){
-                case 1:  return launch_strided<T, radix_list<16, 8, 8, 1>, 64,      8 * M, 1, SCATTER>(a, L);   // more threads on the big tile
-                case 2:  return launch_strided<T, radix_list<16, 8, 8, 1>, 64 / M,  4 * M, 3, SCATTER>(a, L);   // half tile, three CTAs per SM
+            switch(strided_big_variant(SCATTER)){
+                case 1:  return launch_strided<T, radix_list<16, 8, 8, 1>, 64,      8 * M, 1, SCATTER>(a, L);
+                case 2:  return launch_strided<T, radix_list<16, 8, 8, 1>, 64 / M,  4 * M, 3, SCATTER>(a, L);
                 default: return launch_strided<T, radix_list<16, 8, 8, 1>, 32 / M,  8 * M, 1, SCATTER>(a, L);
             }
-        case 2048: return launch_strided<T, radix_list<8, 8, 8, 4>, 128 / M,  4 * M, 1, SCATTER>(a, L);
-        case 4096: return launch_strided<T, radix_list<8, 8, 8, 8>, 256 / M,  2 * M, 1, SCATTER>(a, L);
+        case 2048:
+            if (strided_big_variant(SCATTER) == 1) return launch_strided<T, radix_list<8, 8, 8, 4>, 256 / M, 4 * M, 1, SCATTER>(a, L);
+            return launch_strided<T, radix_list<8, 8, 8, 4>, 128 / M,  4 * M, 1, SCATTER>(a, L);
+        case 4096:
+            if (strided_big_variant(SCATTER) == 1) return launch_strided<T, radix_list<8, 8, 8, 8>, 512 / M, 2 * M, 1, SCATTER>(a, L);
+            return launch_strided<T, radix_list<8, 8, 8, 8>, 256 / M,  2 * M, 1, SCATTER>(a, L);
         // lengths with factors 3 and 5: TPL divides N / R for every radix R of the schedule; rows of the tile stay 128 bytes
         case 48:   return launch_strided<T, radix_list<4, 4, 3, 1>,     4, 32 * M, 2, SCATTER>(a, L);
         case 96:   return launch_strided<T, radix_list<12, 8, 1, 1>,    4, 16 * M, 2, SCATTER>(a, L);
@@ -127,7 +133,9 @@ int dispatch_strided_conv(int n, fft_args const &a, Launcher &L){
         case 128:  return launch_strided_conv<T, radix_list<8, 4, 4, 1>,  16 / M,  8 * M, 2, SCATTER>(a, L);
         case 256:  return launch_strided_conv<T, radix_list<8, 8, 4, 1>,  32 / M,  8 * M, 2, SCATTER>(a, L);
         case 512:  return launch_strided_conv<T, radix_list<8, 8, 8, 1>,  32 / M,  8 * M, 3, SCATTER>(a, L);
-        case 1024: return launch_strided_conv<T, radix_list<16, 8, 8, 1>, 32 / M,  8 * M, 1, SCATTER>(a, L);
+        case 1024:
+            if (strided_big_variant(SCATTER) == 1) return launch_strided_conv<T, radix_list<16, 8, 8, 1>, 64, 8 * M, 1, SCATTER>(a, L);
+            return launch_strided_conv<T, radix_list<16, 8, 8, 1>, 32 / M,  8 * M, 1, SCATTER>(a, L);
         case 2048: return launch_strided_conv<T, radix_list<8, 8, 8, 4>, 128 / M,  4 * M, 1, SCATTER>(a, L);
         case 4096: return launch_strided_conv<T, radix_list<8, 8, 8, 8>, 256 / M,  2 * M, 1, SCATTER>(a, L);
         default: return -1;
@@ -146,9 +154,16 @@ int dispatch_contig(int n, fft_args const &a, Launcher &L){
         // 512-point fp64 <4,8,16> with two lines per CTA 6.95 vs 6.25 TB/s for <8,8,8> with one
         case 256:  return launch_contig<T, radix_list<16, 16, 1, 1>,  4, 6, SCATTER>(a, L);
         case 512:  return launch_contig<T, radix_list<4, 8, 16, 1>,   2, 8, SCATTER>(a, L);
-        case 1024: return launch_contig<T, radix_list<16, 8, 8, 1>,   1, 4, SCATTER>(a, L);
-        case 2048: return launch_contig<T, radix_list<8, 8, 8, 4>,    1, 2, SCATTER>(a, L);
-        case 4096: return launch_contig<T, radix_list<8, 8, 8, 8>,    1, 1, SCATTER>(a, L);
+        // long lines with a fused reshape: twice the CTAs per SM keep more remote stores in flight (see dispatch_strided)
+        case 1024:
+            if (strided_big_variant(SCATTER) == 1) return launch_contig<T, radix_list<16, 8, 8, 1>, 1, 8, SCATTER>(a, L);
+            return launch_contig<T, radix_list<16, 8, 8, 1>,   1, 4, SCATTER>(a, L);
+        case 2048:
+            if (strided_big_variant(SCATTER) == 1) return launch_contig<T, radix_list<8, 8, 8, 4>, 1, 4, SCATTER>(a, L);
+            return launch_contig<T, radix_list<8, 8, 8, 4>,    1, 2, SCATTER>(a, L);
+        case 4096:
+            if (strided_big_variant(SCATTER) == 1) return launch_contig<T, radix_list<8, 8, 8, 8>, 1, 2, SCATTER>(a, L);
+            return launch_contig<T, radix_list<8, 8, 8, 8>,    1, 1, SCATTER>(a, L);
         // lengths with factors 3 and 5 (threads per line given explicitly; a thread holds N / TPL values between two passes)
         case 48:   return launch_contig_tpl<T, radix_list<4, 4, 3, 1>,     4, 16, 4, SCATTER>(a, L);
         case 96:   return launch_contig_tpl<T, radix_list<12, 8, 1, 1>,    4, 16, 4, SCATTER>(a, L);
@@ -384,14 +399,16 @@ int launch_contig_real2(fft_args const &a, Launcher &L){
 template<typename T, int KIND, typename Launcher>
 int dispatch_contig_real2_kind(int n, fft_args const &a, Launcher &L){
     switch(n){
-        case 32:   return launch_contig_real2<T, radix_list<4, 2, 4, 1>,   16, 6, KIND>(a, L);
-        case 64:   return launch_contig_real2<T, radix_list<8, 8, 1, 1>,   16, 6, KIND>(a, L);
-        case 128:  return launch_contig_real2<T, radix_list<4, 8, 4, 1>,    4, 6, KIND>(a, L);
-        case 256:  return launch_contig_real2<T, radix_list<8, 4, 8, 1>,    4, 6, KIND>(a, L);
-        case 512:  return launch_contig_real2<T, radix_list<8, 8, 8, 1>,    2, 8, KIND>(a, L);
-        case 1024: return launch_contig_real2<T, radix_list<8, 16, 8, 1>,   1, 4, KIND>(a, L);
-        case 2048: return launch_contig_real2<T, radix_list<8, 8, 4, 8>,    1, 2, KIND>(a, L);
-        case 4096: return launch_contig_real2<T, radix_list<8, 8, 8, 8>,    1, 1, KIND>(a, L);
+        // one warp per CTA, sixteen CTAs per SM (tools/kbench_real.cu on B200, 512-point fp64: r2c 6.24 TB/s against 5.96 for 64
+        // threads x 8; profiles/r02_single/kbench_real_second_generation.log)
+        case 32:   return launch_contig_real2<T, radix_list<4, 2, 4, 1>,    8, 16, KIND>(a, L);
+        case 64:   return launch_contig_real2<T, radix_list<8, 8, 1, 1>,    8, 16, KIND>(a, L);
+        case 128:  return launch_contig_real2<T, radix_list<4, 8, 4, 1>,    2, 16, KIND>(a, L);
+        case 256:  return launch_contig_real2<T, radix_list<8, 4, 8, 1>,    2, 16, KIND>(a, L);
+        case 512:  return launch_contig_real2<T, radix_list<8, 8, 8, 1>,    1, 16, KIND>(a, L);
+        case 1024: return launch_contig_real2<T, radix_list<8, 16, 8, 1>,   1, 8, KIND>(a, L);
+        case 2048: return launch_contig_real2<T, radix_list<8, 8, 4, 8>,    1, 4, KIND>(a, L);
+        case 4096: return launch_contig_real2<T, radix_list<8, 8, 8, 8>,    1, 2, KIND>(a, L);
         default: return -1;
     }
 }
