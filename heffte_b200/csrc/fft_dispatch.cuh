@@ -29,6 +29,10 @@ constexpr bool is_mixed_fast_length(long long n){
 constexpr bool is_mixed_fast_half(long long m){ return is_mixed_fast_length(m) && m != 48 && m != 100 && m != 3584; }
 constexpr bool is_fast_length(long long n){ return (is_pow2(n) && n >= pow2_min && n <= pow2_max) || is_mixed_fast_length(n); }
 
+inline int strided_512_variant(){
+    static int const v = []{ const char *e = std::getenv("HEFFTE_B200_STRIDED_512"); return (e != nullptr) ? std::atoi(e) : 0; }();
+    return v;
+}
 inline int strided_big_variant(bool scatter){
     static int const v = []{ const char *e = std::getenv("HEFFTE_B200_STRIDED_BIG"); return (e != nullptr) ? std::atoi(e) : -1; }();
     return (v >= 0) ? v : (scatter ? 1 : 0);
@@ -69,7 +73,10 @@ int dispatch_strided(int n, fft_args const &a, Launcher &L){
         case 64:   return launch_strided<T, radix_list<8, 8, 1, 1>,   8 / M, 16 * M, 2, SCATTER>(a, L);
         case 128:  return launch_strided<T, radix_list<8, 4, 4, 1>,  16 / M,  8 * M, 2, SCATTER>(a, L);
         case 256:  return launch_strided<T, radix_list<8, 8, 4, 1>,  32 / M,  8 * M, 2, SCATTER>(a, L);
-        case 512:  return launch_strided<T, radix_list<8, 8, 8, 1>,  32 / M,  8 * M, 3, SCATTER>(a, L);
+        case 512:
+            // developer knob HEFFTE_B200_STRIDED_512 = 1: twice the threads on the tile, two CTAs per SM
+            if (SCATTER && strided_512_variant() == 1) return launch_strided<T, radix_list<8, 8, 8, 1>, 64 / M, 8 * M, 2, SCATTER>(a, L);
+            return launch_strided<T, radix_list<8, 8, 8, 1>,  32 / M,  8 * M, 3, SCATTER>(a, L);
         // 1024 points and more: the tile takes 128 KB, ONE CTA per SM.  Against NVLink what counts is the number of stores in
         // flight: 1024 (fp32) / 512 (fp64) threads on the tile instead of 256 took the fused stages of 1024^3 fp32 on 2 GPUs from
         // 268 to 706 GB/s (profiles/r02_multi_2gpu/bench_c2c_f32_1024_tile_variant_*.log); half tiles with three CTAs per SM reach
