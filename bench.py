@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the comparison with the compiled reference (oracle/_ref)")
     ap.add_argument("--no-secondary", action="store_true", help="primary workload only")
+    ap.add_argument("--no-register", action="store_true", help="several GPUs: do not register the benchmark's arrays with the plan (the results then pass through the plan's buffers)")
     ap.add_argument("--cpu-size", type=int, nargs=3, default=None, help="size of the CPU sample (default: the workload itself)")
     return ap.parse_args()
 
@@ -382,6 +383,7 @@ def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, re
 
     nin, nout = fft.size_inbox(), fft.size_outbox()
     work = torch.empty(fft.size_workspace() * batch, dtype=rdtype if r2r else cdtype, device="cuda")
+    register = distributed and batch == 1 and not args.no_register
 
     # ---- parity: forward(scale::full) of a hashed world array against the compiled reference, every rank's sub-box --------
     parity_info = None
@@ -395,11 +397,15 @@ def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, re
         if conv:
             # the fused spectral operator: forward(scale full), spectrum times itself, backward, one plan-level call
             yout = torch.empty(nin, dtype=cdtype, device="cuda")
+            checked_registered = register and fft.register_buffer(yout)
             fft.convolve(xin, yout, None, hf.scale.full)
         else:
             yout = torch.empty(nout, dtype=rdtype if r2r else cdtype, device="cuda")
+            checked_registered = register and fft.register_buffer(yout)      # the timed loop writes registered arrays: so does the check
             fft.forward(xin, yout, hf.scale.full)
         torch.cuda.synchronize()
+        if checked_registered:
+            fft.unregister_buffer(yout)
         expect_dev, checker = None, None
         if too_big:
             checker = "skipped: the reference needs more than 64 GB of host memory for this size"
@@ -462,6 +468,13 @@ def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, re
                                 torch.zeros(max(nin, nout) * batch, dtype=rdtype, device="cuda"))
         data_out = data_in
     reference_copy = data_in.clone()
+    # several GPUs: the arrays of the benchmark are registered with the plan (once, like a buffer registered with a communication
+    # library): the other GPUs store their part of every result straight into them
+    registered = False
+    if register:
+        registered = bool(fft.register_buffer(data_in))
+        if data_out is not data_in:
+            registered = bool(fft.register_buffer(data_out)) or registered
 
     fused_conv = conv and not args.unfused_conv
 
@@ -704,6 +717,7 @@ def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, re
                        "layout": "bricks %s%s, %s, %s, in-place, step = forward(scale full)+backward" % (
                            grid, " (pencil-shaped in/out)" if io_pencils else "", "reorder" if reorder else "no-reorder", "slabs" if slabs else ("pencils" if pencils else "decomposition chosen by the planner")),
                        "batch": batch,
+                       "registered_arrays": registered,
                        "l2": ("working set %.0f MB per GPU exceeds the 126 MB L2" % working_set_mb) if not flush else
                              ("working set %.0f MB per GPU: a 512 MB buffer is overwritten between the timed steps (flush time not counted)" % working_set_mb),
                        "l2_slab_mb": os.environ.get("HEFFTE_B200_L2_SLAB_MB"),

@@ -113,6 +113,8 @@ def load():
     sig("heffte_convolve", c_int, LP_plan, c_int, c_vp, c_vp, c_vp, c_vp, c_int)
     sig("heffte_convolve_box", c_int, LP_plan, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll), ip)
     sig("heffte_b200_prepare", c_int, LP_plan, c_int, c_int)
+    sig("heffte_b200_register_buffer", c_int, LP_plan, c_int, c_vp, ctypes.c_size_t)
+    sig("heffte_b200_unregister_buffer", c_int, LP_plan, c_int, c_vp)
     sig("heffte_plan_create64", c_int, c_int, c_vp, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll), ip, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll), ip,
         c_int, c_vp, ctypes.POINTER(heffte_plan_options), c_int, ctypes.POINTER(LP_plan))
     sig("b200_fft1d_execute_batch", c_int, c_vp, c_int, c_vp, c_vp, c_dbl, c_vp, c_int, c_ll, c_ll)

@@ -313,6 +313,18 @@ int heffte_b200_prepare(heffte_plan const plan, int precision, int batch){
     return s->fft->prepare(precision, batch);
 }
 
+int heffte_b200_register_buffer(heffte_plan const plan, int precision, void *device_array, size_t bytes){
+    plan_state *s = state_of(plan);
+    if (s == nullptr) return fail(B200_ERR_INVALID, "invalid plan handle");
+    return s->fft->register_buffer(precision, device_array, bytes);      // a null array (an empty box) still takes part in the collective
+}
+
+int heffte_b200_unregister_buffer(heffte_plan const plan, int precision, void *device_array){
+    plan_state *s = state_of(plan);
+    if (s == nullptr) return fail(B200_ERR_INVALID, "invalid plan handle");
+    return s->fft->unregister_buffer(precision, device_array);
+}
+
 int heffte_execute_host(heffte_plan const plan, int precision, int direction, int batch, void const *host_input, void *host_output, int scale){
     plan_state *s = state_of(plan);
     if (s == nullptr) return fail(B200_ERR_INVALID, "invalid plan handle");

@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdint>
+#include <map>
+#include <string>
 #include <memory>
 #include <mutex>
 
@@ -156,7 +159,74 @@ public:
         for(int r=0; r<static_cast<int>(peers.size()); r++)
             if (r != my_rank and peers[r] != nullptr) cudaIpcCloseMemHandle(peers[r]);
     }
+    bool map_user_buffer(void *ptr, std::vector<void*> &peers) override {
+        peers.assign(nranks, nullptr);
+        struct record { cudaIpcMemHandle_t handle; unsigned long long offset; int ok; int device; char host[64]; };
+        record mine{};
+        const char *off = std::getenv("HEFFTE_B200_DISABLE_P2P");
+        void *base = nullptr;
+        if ((off == nullptr or off[0] == '0') and ptr != nullptr and allocation_base(ptr, &base)){
+            if (cudaIpcGetMemHandle(&mine.handle, base) == cudaSuccess){
+                mine.ok = 1;
+                mine.offset = static_cast<unsigned long long>(static_cast<char*>(ptr) - static_cast<char*>(base));
+            }else cudaGetLastError();
+        }
+        cudaGetDevice(&mine.device);
+        gethostname_safe(mine.host, sizeof(mine.host));
+        std::vector<record> all(nranks);
+        if (allgather(&mine, all.data(), sizeof(record)) != 0) return false;
+        int opened = 1;
+        for(int r=0; r<nranks; r++) if (not all[r].ok or std::strncmp(all[r].host, mine.host, sizeof(mine.host)) != 0) opened = 0;
+        for(int r=0; r<nranks and opened; r++){
+            if (r == my_rank){ peers[r] = ptr; continue; }
+            void *remote = open_once(all[r].handle);
+            if (remote == nullptr){ opened = 0; break; }
+            peers[r] = static_cast<char*>(remote) + all[r].offset;
+        }
+        std::vector<int> votes(nranks);
+        if (allgather(&opened, votes.data(), sizeof(int)) != 0) opened = 0;
+        for(int v : votes) if (not v) opened = 0;
+        if (not opened) peers.clear();
+        return opened != 0;
+    }
 private:
+    // the allocation a device pointer lives in (a caching allocator hands out pieces of large allocations; CUDA IPC exports whole ones)
+    static bool allocation_base(void *ptr, void **base){
+#ifdef B200_HOST_EMULATION
+        *base = ptr;
+        return true;
+#else
+        typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+        static range_fn const fn = []() -> range_fn {
+            void *f = nullptr;
+            cudaDriverEntryPointQueryResult status;
+            if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &status) != cudaSuccess or status != cudaDriverEntryPointSuccess){
+                cudaGetLastError();
+                return nullptr;
+            }
+            return reinterpret_cast<range_fn>(f);
+        }();
+        if (fn == nullptr) return false;
+        unsigned long long start = 0;
+        size_t size = 0;
+        if (fn(&start, &size, static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(ptr))) != 0) return false;
+        *base = reinterpret_cast<void*>(static_cast<uintptr_t>(start));
+        return true;
+#endif
+    }
+    // an IPC handle can be opened once per process: the mappings are kept for the life of the process
+    static void* open_once(cudaIpcMemHandle_t const &handle){
+        static std::mutex guard;
+        static std::map<std::string, void*> opened;
+        std::string const key(reinterpret_cast<const char*>(&handle), sizeof(handle));
+        std::lock_guard<std::mutex> lock(guard);
+        auto it = opened.find(key);
+        if (it != opened.end()) return it->second;
+        void *remote = nullptr;
+        if (cudaIpcOpenMemHandle(&remote, handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess){ cudaGetLastError(); return nullptr; }
+        opened[key] = remote;
+        return remote;
+    }
     static void gethostname_safe(char *out, size_t n){
         std::memset(out, 0, n);
         FILE *f = std::fopen("/proc/sys/kernel/random/boot_id", "r");   // same kernel instance == same node (containers share it)
@@ -278,6 +348,17 @@ public:
         for(int v : votes) if (not v) usable = 0;
         peers.clear();
         if (not usable) return false;
+        for(int r=0; r<nranks; r++) peers.push_back(all[r].ptr);
+        return true;
+    }
+    bool map_user_buffer(void *ptr, std::vector<void*> &peers) override {
+        struct record { void *ptr; int ok; };
+        const char *off = std::getenv("HEFFTE_B200_DISABLE_P2P");
+        record mine{ptr, (ptr != nullptr and (off == nullptr or off[0] == '0')) ? 1 : 0};
+        std::vector<record> all(nranks);
+        allgather(&mine, all.data(), sizeof(record));
+        peers.clear();
+        for(int r=0; r<nranks; r++) if (not all[r].ok) return false;
         for(int r=0; r<nranks; r++) peers.push_back(all[r].ptr);
         return true;
     }

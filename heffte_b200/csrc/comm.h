@@ -36,6 +36,10 @@ public:
     // Returns false on every rank when peer mapping is not available (the plan then uses exchange()).
     virtual bool map_peers(void *local, size_t bytes, std::vector<void*> &peers){ (void) local; (void) bytes; peers.clear(); return false; }
     virtual void unmap_peers(std::vector<void*> const &peers){ (void) peers; }
+    // Collective: the address of every rank's `ptr` -- device memory the CALLER allocated -- as seen from this device (peers[me] =
+    // ptr).  One process per GPU: the allocation that holds ptr is opened through CUDA IPC (once per process, kept open).
+    // False on every rank when any rank cannot share its memory (a pool the driver does not export, another node).
+    virtual bool map_user_buffer(void *ptr, std::vector<void*> &peers){ (void) ptr; peers.clear(); return false; }
     // Called right after a peer barrier kernel has been enqueued.  Ranks that are host threads sharing one GPU rendezvous here:
     // kernels of different streams can share a hardware queue, and a spinning barrier kernel followed by dependent work of the
     // same stream would otherwise block the barrier kernel of another rank queued behind it.  One process per GPU: nothing to do.

@@ -273,6 +273,8 @@ void transform3d::release_peer(int precision){
     }
     P.arenas.clear();
     if (P.maps){ cudaFree(P.maps); P.maps = nullptr; }
+    for(auto &u : P.user) if (u.maps) cudaFree(u.maps);
+    P.user.clear();                                // registrations do not survive a rebuilt arena: the caller registers again
     P.active = false;
 }
 
@@ -354,24 +356,10 @@ bool transform3d::ensure_peer(int precision, int batch){
     for(int view=0; view<nviews and built; view++){
         for(int st=0; st<4 and built; st++){
             if (not P.fused[view][st]) continue;
-            shape const &dest = vout(view, st);
-            // the box this rank writes in that stage, the axis of the transform in front of the reshape, the element size
-            box3 const written = vin(view, st)[me];
-            int k_pos = 0, bytes = complex_data ? cplx_bytes : real_bytes;
-            if (st == 0){
-                if (tkind == kind_r2c and view == view_forward) bytes = real_bytes;
-            }else{
-                int const e = st - 1;                                       // transform in front of this reshape
-                if (not written.empty()) k_pos = written.position_of(vdim(view, e));
-                if (tkind == kind_r2c and view == view_mirror and real_id(view, e) == 0) bytes = real_bytes;   // c2r output
-            }
-            stage_elems[view][st] = written.count();
-            sent_elems[view][st] = 0;
-            for(int r=0; r<n; r++) if (r != me) sent_elems[view][st] += written.overlap(dest[r]).count();
             for(int w=0; w<3; w++){
                 std::vector<void*> bases(n);
                 for(int r=0; r<n; r++) bases[r] = static_cast<char*>(arenas[r]) + 4096 + static_cast<size_t>(w) * P.buffer_bytes;
-                if (not build_scatter_map(written, k_pos, dest, bases, bytes, maps[(view * 4 + st) * 3 + w], why, nullptr, me)){ built = 0; break; }
+                if (not stage_map(precision, view, st, bases, maps[(view * 4 + st) * 3 + w], why, w == 0)){ built = 0; break; }
             }
         }
     }
@@ -389,6 +377,96 @@ bool transform3d::ensure_peer(int precision, int batch){
     P.host_maps = maps;
     P.active = true;
     return true;
+}
+
+// the scatter map of stage (view, st) for destination boxes that start at bases[rank]
+bool transform3d::stage_map(int precision, int view, int st, std::vector<void*> const &bases, scatter_map &map, std::string &why, bool count){
+    int const n = ccomm->size();
+    int const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
+    int const cplx_bytes = 2 * real_bytes;
+    bool const complex_data = (tkind == kind_c2c or tkind == kind_r2c);
+    shape const &dest = vout(view, st);
+    // the box this rank writes in that stage, the axis of the transform in front of the reshape, the element size
+    box3 const written = vin(view, st)[me];
+    int k_pos = 0, bytes = complex_data ? cplx_bytes : real_bytes;
+    if (st == 0){
+        if (tkind == kind_r2c and view == view_forward) bytes = real_bytes;
+    }else{
+        int const e = st - 1;                                       // transform in front of this reshape
+        if (not written.empty()) k_pos = written.position_of(vdim(view, e));
+        if (tkind == kind_r2c and view == view_mirror and real_id(view, e) == 0) bytes = real_bytes;   // c2r output
+    }
+    if (count){
+        stage_elems[view][st] = written.count();
+        sent_elems[view][st] = 0;
+        for(int r=0; r<n; r++) if (r != me) sent_elems[view][st] += written.overlap(dest[r]).count();
+    }
+    return build_scatter_map(written, k_pos, dest, bases, bytes, map, why, nullptr, me);
+}
+
+int transform3d::register_buffer(int precision, void *ptr, size_t bytes){
+    if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
+    int rc = ensure_executors(precision);
+    if (rc) return rc;
+    if (not ensure_peer(precision, 1)) return B200_ERR_UNSUPPORTED;        // the same answer on every rank
+    peer_state &P = peer[precision];
+    int const n = ccomm->size();
+    int const real_bytes = (precision == B200_PREC_FLOAT) ? 4 : 8;
+    int const cplx_bytes = 2 * real_bytes;
+    bool const complex_data = (tkind == kind_c2c or tkind == kind_r2c);
+    std::vector<void*> peers;
+    bool const mapped = ccomm->map_user_buffer(ptr, peers);                // collective
+    // which views can end in this array: the last reshape moves data, and the array holds the box that lands in it (on every rank)
+    int const nviews = lb_active ? 3 : 2;
+    int fits[3] = {0, 0, 0};
+    for(int v=0; v<nviews and mapped; v++){
+        if (not P.fused[v][3]) continue;
+        bool const real_out = (tkind == kind_r2c and v != view_forward) or not complex_data;
+        size_t const need = static_cast<size_t>(vout(v, 3)[me].count()) * (real_out ? real_bytes : cplx_bytes);
+        fits[v] = (bytes >= need) ? 1 : 0;
+    }
+    std::vector<int> all(3 * static_cast<size_t>(n));
+    if (ccomm->allgather(fits, all.data(), sizeof(fits)) != 0) return fail(B200_ERR_PEER, "allgather failed");
+    for(int r=0; r<n; r++) for(int v=0; v<3; v++) if (not all[3 * static_cast<size_t>(r) + v]) fits[v] = 0;
+    peer_state::registered entry;
+    entry.ptr = ptr; entry.bytes = bytes;
+    std::vector<scatter_map> maps(3);
+    std::string why;
+    int built = mapped ? 1 : 0;
+    bool any = false;
+    for(int v=0; v<nviews and built; v++){
+        if (not fits[v]) continue;
+        if (not stage_map(precision, v, 3, peers, maps[v], why, false)){ built = 0; break; }
+        entry.has[v] = true;
+        any = true;
+    }
+    if (built and any and cudaMalloc(&entry.maps, maps.size() * sizeof(scatter_map)) != cudaSuccess){ entry.maps = nullptr; cudaGetLastError(); built = 0; }
+    if (built and any and cudaMemcpy(entry.maps, maps.data(), maps.size() * sizeof(scatter_map), cudaMemcpyHostToDevice) != cudaSuccess) built = 0;
+    {
+        std::vector<int> votes(n);
+        if (ccomm->allgather(&built, votes.data(), sizeof(int)) != 0) built = 0;
+        for(int v : votes) if (not v) built = 0;
+    }
+    if (not built or not any){
+        if (entry.maps) cudaFree(entry.maps);
+        return B200_ERR_UNSUPPORTED;
+    }
+    for(auto &u : P.user) if (u.ptr == ptr){ if (u.maps) cudaFree(u.maps); u = entry; return B200_SUCCESS; }
+    P.user.push_back(entry);
+    return B200_SUCCESS;
+}
+
+int transform3d::unregister_buffer(int precision, void *ptr){
+    if (precision != B200_PREC_FLOAT and precision != B200_PREC_DOUBLE) return fail(B200_ERR_INVALID, "bad precision");
+    peer_state &P = peer[precision];
+    for(size_t i=0; i<P.user.size(); i++){
+        if (P.user[i].ptr != ptr) continue;
+        cudaStreamSynchronize(cstream);          // a launch that reads the map may still be in flight
+        if (P.user[i].maps) cudaFree(P.user[i].maps);
+        P.user.erase(P.user.begin() + static_cast<long>(i));
+        break;
+    }
+    return B200_SUCCESS;
 }
 
 bool transform3d::ensure_side_stream(){
@@ -475,6 +553,7 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
     // local transform has no SM time to hide in.  Opt-in for experiments.
     static bool const allow_pair = (std::getenv("HEFFTE_B200_OVERLAP") != nullptr);
     static bool const allow_direct = (std::getenv("HEFFTE_B200_NO_DIRECT_OUTPUT") == nullptr);
+    static bool const allow_registered = (std::getenv("HEFFTE_B200_NO_REGISTERED_OUTPUT") == nullptr);
     static int const thin_blocks = []{ const char *e = std::getenv("HEFFTE_B200_THIN_CTAS_PER_SM"); int const k = e ? std::atoi(e) : 2; return 148 * ((k > 0) ? k : 2); }();
     bool const shared_device = (std::strcmp(ccomm->kind(), "threads") == 0) and std::getenv("HEFFTE_B200_OVERLAP_ON_SHARED_DEVICE") == nullptr;
     static bool const trace = (std::getenv("HEFFTE_B200_TRACE") != nullptr);
@@ -516,6 +595,7 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
     long long cur_step = in_entry;
     int cur_buffer = -1;             // -1: caller memory
     bool landed_direct = false;
+    int fences_done = 0;
     int const last_fft_op = static_cast<int>(ops.size()) - 1;
 
     for(size_t i=0; i<ops.size(); i++){
@@ -536,6 +616,7 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
             mark("reshape0 (scatter copy)", batch * (2 * stage_elems[o.dir][0] - sent_elems[o.dir][0]) * bytes, batch * sent_elems[o.dir][0] * bytes);
             rc = peer_fence(precision);
             if (rc) return rc;
+            fences_done++;
             mark("fence", 0, 0);
             cur_buffer = w; cur = P.buffer(w); cur_step = arena_entry;
             continue;
@@ -552,19 +633,35 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
         for(size_t t=i+1; t<ops.size(); t++) later_fused = later_fused or P.fused[ops[t].dir][ops[t].st];
 
         if (fused){
-            int const w = P.take();
+            int const w = P.take();                 // also when the stage ends in a registered array: the rotation stays in step
             long long local_shift = 0, local_step = 0;
+            const char *map_here = map_of(o, w);
+            bool into_registered = false;
             if (is_last and allow_direct){
-                // last stage: the part of my output that I produce myself goes straight into the caller's array (the cells of the
-                // map that stay in my own memory are re-based by the kernel); only what the other GPUs send lands in the arena
-                local_shift = static_cast<long long>(reinterpret_cast<intptr_t>(out)) - static_cast<long long>(reinterpret_cast<intptr_t>(P.buffer(w)));
-                local_step = out_entry - arena_entry;
-                landed_direct = true;
+                // The caller registered this array (register_buffer): every GPU stores its part of the result straight into it.
+                // The other ranks write while I may still be reading `in` (an in-place call): allowed once a fence of THIS call
+                // lies behind us, because `in` is only read by the first stage.
+                if (allow_registered and batch == 1 and fences_done > 0){
+                    for(auto const &u : P.user){
+                        if (u.ptr == out and u.has[o.dir]){
+                            map_here = static_cast<const char*>(u.maps) + sizeof(scatter_map) * static_cast<size_t>(o.dir);
+                            into_registered = true;
+                            break;
+                        }
+                    }
+                }
+                if (not into_registered){
+                    // last stage: the part of my output that I produce myself goes straight into the caller's array (the cells of the
+                    // map that stay in my own memory are re-based by the kernel); only what the other GPUs send lands in the arena
+                    local_shift = static_cast<long long>(reinterpret_cast<intptr_t>(out)) - static_cast<long long>(reinterpret_cast<intptr_t>(P.buffer(w)));
+                    local_step = out_entry - arena_entry;
+                    landed_direct = true;
+                }
             }
-            if (trace) std::fprintf(stderr, "[b200 rank %d] stage (%d,%d) fused -> buffer %d\n", me, o.dir, o.st, w);
+            if (trace) std::fprintf(stderr, "[b200 rank %d] stage (%d,%d) fused -> %s %d\n", me, o.dir, o.st, into_registered ? "registered array, skipped buffer" : "buffer", w);
             if (Xe){
                 if (o.conv){
-                    rc = b200_fft1d_execute_convolve(Xe, cur, nullptr, map_of(o, w), multiplier, stage_scale, cstream, batch, cur_step, 0, arena_entry, local_shift, local_step);
+                    rc = b200_fft1d_execute_convolve(Xe, cur, nullptr, map_here, multiplier, stage_scale, cstream, batch, cur_step, 0, arena_entry, local_shift, local_step);
                     if (rc == B200_ERR_UNSUPPORTED){
                         // no operator kernel for this axis: transform in place, multiply, and let the backward kernel carry the reshape
                         void *here = const_cast<void*>(cur);
@@ -572,10 +669,10 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
                         rc = b200_fft1d_execute_batch(Xe, B200_FORWARD, cur, here, 1.0, cstream, batch, cur_step, cur_step);
                         for(int b=0; b<batch and rc == 0; b++)
                             rc = b200_pointwise_multiply(precision, vout(o.dir, e)[me].count(), static_cast<char*>(here) + b * cur_step, multiplier, stage_scale, cstream);
-                        if (rc == 0) rc = b200_fft1d_execute_scatter_batch(Xe, B200_BACKWARD, cur, map_of(o, w), 1.0, cstream, batch, cur_step, arena_entry, local_shift, local_step);
+                        if (rc == 0) rc = b200_fft1d_execute_scatter_batch(Xe, B200_BACKWARD, cur, map_here, 1.0, cstream, batch, cur_step, arena_entry, local_shift, local_step);
                     }
                 }else{
-                    rc = b200_fft1d_execute_scatter_batch(Xe, direction, cur, map_of(o, w), stage_scale, cstream, batch, cur_step, arena_entry, local_shift, local_step);
+                    rc = b200_fft1d_execute_scatter_batch(Xe, direction, cur, map_here, stage_scale, cstream, batch, cur_step, arena_entry, local_shift, local_step);
                 }
                 if (rc) return rc;
             }
@@ -589,8 +686,10 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
             }
             rc = peer_fence(precision);
             if (rc) return rc;
+            fences_done++;
             mark("fence", 0, 0);
-            cur_buffer = w; cur = P.buffer(w); cur_step = arena_entry;
+            if (into_registered){ cur_buffer = -1; cur = out; cur_step = out_entry; }
+            else{ cur_buffer = w; cur = P.buffer(w); cur_step = arena_entry; }
             continue;
         }
 
@@ -638,6 +737,7 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
                         mark(label, batch * (3 * count * cplx_bytes + wrote - sent), batch * sent);
                         rc = peer_fence(precision);
                         if (rc) return rc;
+                        fences_done++;
                         mark("fence", 0, 0);
                         cur_buffer = w; cur = P.buffer(w); cur_step = arena_entry;
                         i++;                     // the fused stage is done

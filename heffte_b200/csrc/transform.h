@@ -93,6 +93,14 @@ public:
 
     // true once the plan runs its reshapes through peer memory (NVLink stores fused into the FFT kernels)
     bool uses_peer_memory(int precision) const { return peer[precision].active; }
+    // Collective.  Registers `bytes` of caller memory at `ptr` as an array the transforms of this plan may be asked to write:
+    // when forward / backward / convolve get it as their output, the other GPUs store their part of the result straight
+    // into it (like a registered user buffer of a communication library) instead of into the plan's buffers, and the final
+    // sub-box copy disappears.  EVERY rank must then pass the pointer it registered in the same call.  B200_ERR_UNSUPPORTED
+    // (on every rank) when the memory cannot be shared or the plan does not run in peer-memory mode: nothing changes then.
+    int register_buffer(int precision, void *ptr, size_t bytes);
+    // local: forget a registered array (before its memory is released)
+    int unregister_buffer(int precision, void *ptr);
 
 private:
     enum run_mode { mode_forward = 0, mode_backward = 1, mode_convolve = 2 };
@@ -124,7 +132,11 @@ private:
         bool fused[3][4] = {{false, false, false, false}, {false, false, false, false}, {false, false, false, false}};   // [view][stage]: the reshape moves data (global fact)
         char* buffer(int index) const { return static_cast<char*>(arena) + 4096 + static_cast<size_t>(index) * buffer_bytes; }
         int take(){ int const w = next_buffer; next_buffer = (next_buffer + 1) % 3; return w; }
+        // caller arrays the peers may write directly: one scatter map of the last stage per view
+        struct registered { void *ptr = nullptr; size_t bytes = 0; void *maps = nullptr; bool has[3] = {false, false, false}; };
+        std::vector<registered> user;
     };
+    bool stage_map(int precision, int view, int st, std::vector<void*> const &bases, scatter_map &map, std::string &why, bool count);
     peer_state peer[2];
     long long sent_elems[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};     // elements that leave this GPU in stage (view, st)
     long long stage_elems[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};    // elements this rank writes in that stage

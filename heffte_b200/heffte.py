@@ -427,6 +427,29 @@ class heffte_fft_plan:
         if rc != 0:
             raise heffte_input_error("heFFTe(b200) prepare failed with code %d: %s" % (rc, _lib.last_error()))
 
+    def register_buffer(self, array):
+        """collective: register a device array this plan will be asked to write (every rank its own); the other GPUs then store
+        their part of a result straight into it.  Every rank must pass its registered array as the output of the same call.
+        Returns True when the array was registered, False when the plan cannot share it (nothing changes then)."""
+        if _dtype_name(array) not in _DTYPE_INFO:
+            raise heffte_input_error("use float32, float64, complex64, or complex128 arrays")
+        precision, _ = _DTYPE_INFO[_dtype_name(array)]
+        if _is_torch(array):
+            if not array.is_contiguous():
+                raise heffte_input_error("register_buffer needs a contiguous array")
+            nbytes = array.numel() * array.element_size()
+        else:
+            nbytes = array.nbytes
+        rc = _lib.load().heffte_b200_register_buffer(self.plan, precision, self._ptr(array), nbytes)
+        if rc not in (0, 2):
+            raise heffte_input_error("heFFTe(b200) register_buffer failed with code %d: %s" % (rc, _lib.last_error()))
+        return rc == 0
+
+    def unregister_buffer(self, array):
+        """local: forget a registered array (call it before the array is released)"""
+        precision, _ = _DTYPE_INFO[_dtype_name(array)]
+        _lib.load().heffte_b200_unregister_buffer(self.plan, precision, self._ptr(array))
+
     def forward(self, inarray, outarray, scaling=scale.none, batch=1):
         self._run(True, inarray, outarray, None, scaling, batch)
 

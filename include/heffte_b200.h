@@ -162,6 +162,16 @@ int heffte_convolve_box(heffte_plan const plan, long long low[3], long long high
  * for transforms of up to `batch` entries ahead of time.  Without it the first transform of each precision -- and the first one
  * with a larger batch -- does it: that call then blocks the host and must be entered by every rank with the same precision. */
 int heffte_b200_prepare(heffte_plan const plan, int precision, int batch);
+/* COLLECTIVE over the ranks of the plan: registers `bytes` of device memory the caller owns as an array the transforms of this plan
+ * will be asked to WRITE (what ncclCommRegister is to NCCL; the reference has no counterpart: MPI moves the data there).  When a
+ * transform of one entry (batch 1) gets a registered array as its output, the other GPUs store their part of the result straight
+ * into it over NVLink and the final copy of the received sub-boxes disappears.  Contract: EVERY rank passes the array it registered
+ * in the same call as the output of that transform (in place or not).  Returns Heffte_SUCCESS, or -- on every rank alike, with no
+ * effect -- B200_ERR_UNSUPPORTED (2) when the memory cannot be shared with the other ranks (exchange mode, a memory pool without
+ * CUDA IPC export, an array too small for this rank's box).  Registrations end with the plan or with a prepare() for more entries. */
+int heffte_b200_register_buffer(heffte_plan const plan, int precision, void *device_array, size_t bytes);
+/* local (not collective): forget a registered array, before its memory is released or handed to somebody else */
+int heffte_b200_unregister_buffer(heffte_plan const plan, int precision, void *device_array);
 /* same through pinned host staging: copies input host->device, transforms, copies the result device->host, synchronises */
 int heffte_execute_host(heffte_plan const plan, int precision, int direction, int batch, void const *host_input, void *host_output, int scale);
 /* 1 when the plan moves data between ranks through peer memory (NVLink stores fused into the FFT kernels), 0 when it uses

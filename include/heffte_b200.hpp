@@ -257,6 +257,13 @@ namespace b200_detail {
         double get_scale_factor(scale scaling) const { return heffte_get_scale_factor(plan, static_cast<int>(scaling)); }
         //! true when the reshapes of this plan run through peer memory (NVLink stores fused into the FFT kernels)
         bool uses_peer_memory(int precision = B200_PREC_DOUBLE) const { return heffte_b200_uses_peer_memory(plan, precision) == 1; }
+        //! \brief Collective: registers a device array this plan will be asked to write (see heffte_b200_register_buffer); true when registered.
+        template<typename T> bool register_buffer(T *array, size_t num_entries){
+            return heffte_b200_register_buffer(plan, b200_detail::precision_of<T>::value, array, num_entries * sizeof(T)) == 0;
+        }
+        template<typename T> void unregister_buffer(T *array){
+            heffte_b200_unregister_buffer(plan, b200_detail::precision_of<T>::value, array);
+        }
     protected:
         plan_base(int backend_id, void *stream, box3d<index> const &inbox, box3d<index> const &outbox, int r2c_direction, comm const &c, plan_options const &o)
             : plan(nullptr), cstream(stream){

@@ -7,6 +7,7 @@
 #include "mpi.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -26,9 +27,13 @@ namespace {
 void copy_bytes(void *dst, const void *src, size_t bytes){
     using copy_fn = int (*)(void*, const void*, size_t);
     static copy_fn const device_copy = reinterpret_cast<copy_fn>(dlsym(RTLD_DEFAULT, "b200_copy_any"));
+    static std::atomic<bool> usable{true};      // the library can be present in a process without a GPU (the CPU test-suite)
     if (bytes == 0) return;
-    if (device_copy == nullptr){ std::memcpy(dst, src, bytes); return; }
-    if (device_copy(dst, src, bytes) != 0){ std::fprintf(stderr, "the MPI stand-in could not copy %zu bytes\n", bytes); std::abort(); }
+    if (device_copy != nullptr and usable.load()){
+        if (device_copy(dst, src, bytes) == 0) return;
+        usable.store(false);
+    }
+    std::memcpy(dst, src, bytes);
 }
 
 inline size_t type_bytes(MPI_Datatype t){ return static_cast<size_t>(t & 0xff); }

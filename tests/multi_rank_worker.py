@@ -183,6 +183,41 @@ def run_config(hf, torch, comm, rank, c, batch=1, stream=None, expect_peer=None,
         err = O.rel_l2(arrays.to_host(d), local) if local.size else 0.0
         if not err <= 2 * tol:
             problems.append("in-place round trip: %.3e" % err)
+    # caller arrays registered with the plan: the other GPUs store their part of the result straight into them (peer-memory
+    # mode; elsewhere the registration is refused on every rank alike and the transforms run as before)
+    if comm.size() > 1 and batch == 1:
+        dx = arrays.to_device(local)
+        dy = arrays.empty(outbox.count(), out_dtype)
+        dz = arrays.empty(inbox.count(), x.dtype)
+        registered = [fft.register_buffer(dy), fft.register_buffer(dz)]
+        if isinstance(arrays, HostArrays):
+            # numpy arrays take the host entry point (staged through the plan's own buffers); with the emulated library host
+            # memory IS device memory, so the device entry point can be driven directly and the registered arrays are reached
+            import ctypes
+            from heffte_b200 import _lib as L
+
+            def run_device(direction, a, b, scaling):
+                rc = L.load().heffte_execute(fft.plan, prec, direction, 1, ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(b.ctypes.data), None, scaling)
+                assert rc == 0, L.last_error()
+            forward_, backward_ = (lambda a, b, s: run_device(0, a, b, s)), (lambda a, b, s: run_device(1, a, b, s))
+        else:
+            forward_, backward_ = fft.forward, fft.backward
+        # (a registration is also refused when the last reshape of a direction moves nothing: there is nothing to store remotely)
+        if any(registered) and not fft.uses_peer_memory(prec):
+            problems.append("register_buffer answered %s in exchange mode" % registered)
+        forward_(dx, dy, 0)
+        err = O.rel_l2(arrays.to_host(dy), expect) if expect.size else 0.0
+        backward_(dy, dz, 0)
+        errb = O.rel_l2(arrays.to_host(dz), expect_b) if expect_b.size else 0.0
+        worst = max(worst, err, errb)
+        if not (err <= tol and errb <= 2 * tol):
+            problems.append("registered output arrays: forward %.3e backward %.3e" % (err, errb))
+        if kind != "r2c" and all(a.count() == b.count() for a, b in zip(inboxes, outboxes)):
+            forward_(dz, dz, 1)                     # in place into a registered array
+            backward_(dz, dz, 0)
+            err = O.rel_l2(arrays.to_host(dz), expect_b) if expect_b.size else 0.0
+            if not err <= 4 * tol:
+                problems.append("registered array, in-place round trip: %.3e" % err)
     # fused spectral operator (reference benchmarks/convolution.cpp:86-97): forward(scale full), pointwise product, backward, as
     # ONE plan call -- the spectrum times itself, then times a caller array laid out over convolve_box()
     if kind == "c2c" and batch == 1 and all(a.count() == b.count() for a, b in zip(inboxes, outboxes)):
