@@ -588,6 +588,17 @@ int transform3d::run_peer(int precision, int mode, int batch, const void *in, vo
     long long const out_entry = static_cast<long long>(last_is_backward ? inbox_count : outbox_count) * out_unit;
     long long const arena_entry = static_cast<long long>(P.entry_bytes);
 
+    // HEFFTE_B200_CHECK_REGISTERED=1 (debugging aid, one host allgather per call): the contract of register_buffer -- either every
+    // rank passes the array it registered as the output of this call, or none does
+    static bool const check_registered = (std::getenv("HEFFTE_B200_CHECK_REGISTERED") != nullptr);
+    if (check_registered and not P.user.empty()){
+        int mine = 0;
+        for(auto const &u : P.user) if (u.ptr == out and u.has[last_view]) mine = 1;
+        std::vector<int> all(static_cast<size_t>(ccomm->size()));
+        if (ccomm->allgather(&mine, all.data(), sizeof(int)) != 0) return fail(B200_ERR_PEER, "allgather failed");
+        for(int v : all) if (v != mine) return fail(B200_ERR_INVALID, "registered arrays: every rank must pass the array it registered as the output of the same call");
+    }
+
     pending.clear();
     mark("start", 0, 0);
     int rc = B200_SUCCESS;
