@@ -4,6 +4,9 @@
 #include "fft_host_plan.h"
 #include "composite.cuh"
 #include "runtime.h"
+#ifndef B200_HOST_EMULATION
+#include <cuda.h>      // the types of the tensor-map encoder; the function itself comes from cudaGetDriverEntryPoint (no libcuda at link time)
+#endif
 
 #include <complex>
 #include <memory>
@@ -31,6 +34,41 @@ void allow_smem(const void *kernel, size_t){
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     done.insert(kernel);
 }
+
+#ifndef B200_HOST_EMULATION
+bool encode_tile_map(tma_tile_map &map, const void *base, int real_bytes, long long count_a, long long n, long long stride, long long count_b, long long stride_b,
+                     int batch, long long step_bytes, int lpb){
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn const encode = []() -> encode_fn {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &status) != cudaSuccess or status != cudaDriverEntryPointSuccess){
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<encode_fn>(f);
+    }();
+    static_assert(sizeof(tma_tile_map) == sizeof(CUtensorMap) and alignof(tma_tile_map) >= alignof(CUtensorMap), "tma_tile_map stands for a CUtensorMap");
+    if (encode == nullptr or count_a <= 0 or n <= 0 or count_b <= 0 or batch <= 0) return false;
+    long long const cb = 2LL * real_bytes;                       // a complex element
+    // (2 count_a reals | n rows | count_b | batch); the strides of axes of extent one only have to be legal
+    cuuint64_t const s1 = static_cast<cuuint64_t>(stride * cb);
+    cuuint64_t const s2 = (count_b > 1) ? static_cast<cuuint64_t>(stride_b * cb) : s1 * static_cast<cuuint64_t>(n);
+    cuuint64_t const s3 = (batch > 1) ? static_cast<cuuint64_t>(step_bytes) : s2 * static_cast<cuuint64_t>(count_b);
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(2 * count_a), static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(count_b), static_cast<cuuint64_t>(batch)};
+    cuuint64_t gstride[3] = {s1, s2, s3};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(2 * lpb), static_cast<cuuint32_t>(std::min<long long>(n, 256)), 1, 1};
+    cuuint32_t estride[4] = {1, 1, 1, 1};
+    for(cuuint64_t v : gstride) if (v == 0 or v % 16 != 0 or v >= (1ULL << 40)) return false;
+    for(cuuint64_t v : gdim) if (v == 0 or v > 0xffffffffULL) return false;
+    if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return false;
+    CUresult const rc = encode(reinterpret_cast<CUtensorMap*>(&map), (real_bytes == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4,
+                               const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS;
+}
+#endif
 
 
 #define B200_DECLARE_SLICE(name) int name(int n, fft_args const &a, cuda_launcher &L)

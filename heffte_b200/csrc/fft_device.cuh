@@ -626,6 +626,77 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_kernel(fft_args a
     }
 }
 
+#ifndef B200_HOST_EMULATION
+// ---------------------------------------------------------------------------------------------------------
+// The strided kernel with its tile brought in by TMA: ONE elected thread asks for the [n][LPB] box of the tile with
+// cp.async.bulk.tensor (two requests of 256 rows; the tensor map -- built on the host per launch, a kernel parameter --
+// describes the box of the stage as (line axis, transform axis, slower line axis, batch entry)), completion arrives on an
+// mbarrier, the passes are those of fft_strided_kernel.  Measured on B200 (tools/kbench_tma.cu, 512-point fp64 lines,
+// profiles/r02_single/kbench_tma.log): rows 4 MB apart (the slow axis of 512^3) 6.15 instead of 5.94 TB/s -- no per-thread address
+// arithmetic and no LSU / MIO slots for 512 scattered rows; rows 8 KB apart (the middle axis) 6.64 instead of 6.77 TB/s, so
+// the host side takes this kernel only for widely spaced rows.  Plain stores, no plane hooks (see fft_args::done).
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(64) tma_tile_map { unsigned long long opaque[16]; };      // a CUtensorMap
+// host side (fft1d.cu): the tensor map of a strided stage, false when the driver or the box does not allow one
+bool encode_tile_map(tma_tile_map &map, const void *base, int real_bytes, long long count_a, long long n, long long stride, long long count_b, long long stride_b,
+                     int batch, long long step_bytes, int lpb);
+__device__ __forceinline__ unsigned shared_address(const void *p){ return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+
+template<typename T, typename RL, int TPL, int LPB, int MINB, bool BWD>
+__global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_tma_kernel(fft_args a0, const __grid_constant__ tma_tile_map tmap){
+    extern __shared__ __align__(128) unsigned char tma_smem_raw[];
+    batch_shift shift;
+    const fft_args a = batch_entry(a0, shift);
+    constexpr unsigned N = RL::N;
+    constexpr unsigned TILE_BYTES = N * LPB * sizeof(cplx<T>);
+    constexpr int P = RL::passes;
+    cplx<T> *sm = reinterpret_cast<cplx<T>*>(tma_smem_raw);
+    unsigned long long *bar_word = reinterpret_cast<unsigned long long*>(tma_smem_raw + TILE_BYTES);
+    const unsigned bar = shared_address(bar_word);
+    const unsigned t = threadIdx.x % LPB, j = threadIdx.x / LPB;
+    const cplx<T> *tw = reinterpret_cast<const cplx<T>*>(a.twiddle);
+    const T scale = static_cast<T>(a.scale);
+    const bool do_scale = a.scale != 1.0;
+    const scatter_ctx sc{nullptr, 0, 0, 0};
+    if (threadIdx.x == 0){
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned ntiles = tile_count<LPB>(a);
+    unsigned phase = 0;
+    for(unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x){
+        if (threadIdx.x == 0){
+            const unsigned line0 = tile * LPB;
+            const unsigned b = line0 / static_cast<unsigned>(a.count_a);
+            const unsigned first = line0 - b * static_cast<unsigned>(a.count_a);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(TILE_BYTES) : "memory");
+            #pragma unroll
+            for(unsigned r0 = 0; r0 < N; r0 += 256){
+                const unsigned dst = shared_address(sm + static_cast<size_t>(r0) * LPB);
+                asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
+                             :: "r"(dst), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(static_cast<int>(2 * first)), "r"(static_cast<int>(r0)),
+                                "r"(static_cast<int>(b)), "r"(static_cast<int>(blockIdx.y)), "r"(bar) : "memory");
+            }
+        }
+        unsigned arrived = 0;
+        while(!arrived)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(arrived) : "r"(bar), "r"(phase) : "memory");
+        phase ^= 1;
+        const unsigned line = tile * LPB + t;
+        cplx<T> *gout = reinterpret_cast<cplx<T>*>(a.out) + tile_line_offset(a.og, a.count_a, line);
+        strided_pass<T, RL, 0, TPL, LPB, BWD, false>(sm, t, j, true, gout, a.og.stride, tw, scale, do_scale, sc);
+        if constexpr (P > 1){ __syncthreads(); strided_pass<T, RL, 1, TPL, LPB, BWD, false>(sm, t, j, true, gout, a.og.stride, tw, scale, do_scale, sc); }
+        if constexpr (P > 2){ __syncthreads(); strided_pass<T, RL, 2, TPL, LPB, BWD, false>(sm, t, j, true, gout, a.og.stride, tw, scale, do_scale, sc); }
+        if constexpr (P > 3){ __syncthreads(); strided_pass<T, RL, 3, TPL, LPB, BWD, false>(sm, t, j, true, gout, a.og.stride, tw, scale, do_scale, sc); }
+        if (tile + gridDim.x < ntiles){
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // the threads' accesses of the tile come before the next bulk write
+            __syncthreads();
+        }
+    }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------
 // fused spectral operator along a strided axis: forward transform, pointwise product, backward transform of every line in ONE
 // pass over memory (reference benchmarks/convolution.cpp:86-97 runs forward(scale::full), x[i] *= x[i], backward as three

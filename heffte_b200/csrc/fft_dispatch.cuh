@@ -63,6 +63,31 @@ int launch_contig_tpl(fft_args const &a, Launcher &L){
     return L.launch(fft_contig_kernel<T, RL, LPB, MINB, false, SCATTER, TPL>, blocks, TPL * LPB, smem, a);
 }
 
+#ifndef B200_HOST_EMULATION
+// When the TMA-loaded tile is taken: rows at least 1 MiB apart in double precision (measured: +3.5 % on the slow axis of 512^3,
+// -2 % on the middle axis, tools/kbench_tma.cu).  HEFFTE_B200_TMA = 0: never; = force: whenever the box allows (tests).
+template<typename T>
+bool tma_tile_wanted(fft_args const &a){
+    static int const mode = []{ const char *e = std::getenv("HEFFTE_B200_TMA"); return (e == nullptr) ? 1 : ((e[0] == '0') ? 0 : ((e[0] == 'f') ? 2 : 1)); }();
+    if (mode == 0 or a.done_mode != 0 or a.order_nb > 1) return false;
+    if (mode == 2) return true;
+    return sizeof(T) == 8 and a.ig.stride * static_cast<long long>(sizeof(cplx<T>)) >= (1LL << 20);
+}
+// -1: the box of the stage does not suit a tensor map (the caller keeps the cp.async kernel)
+template<typename T, typename RL, int TPL, int LPB, int MINB, typename Launcher>
+int launch_strided_tma(fft_args const &a, Launcher &L){
+    if (a.count_a <= 0 or a.nlines <= 0 or a.count_a % LPB != 0 or a.nlines % a.count_a != 0) return -1;
+    if (a.ig.stride_a != 1 or a.og.stride_a != 1) return -1;
+    long long const count_b = a.nlines / a.count_a;
+    tma_tile_map map;
+    if (not encode_tile_map(map, a.in, static_cast<int>(sizeof(T)), a.count_a, RL::N, a.ig.stride, count_b, a.ig.stride_b, L.batch, a.in_step, LPB)) return -1;
+    long long const blocks = a.nlines / LPB;
+    size_t const smem = sizeof(cplx<T>) * (size_t)RL::N * LPB + 16;
+    if (a.backward) return L.launch_tma(fft_strided_tma_kernel<T, RL, TPL, LPB, MINB, true>, blocks, TPL * LPB, smem, a, map);
+    return L.launch_tma(fft_strided_tma_kernel<T, RL, TPL, LPB, MINB, false>, blocks, TPL * LPB, smem, a, map);
+}
+#endif
+
 // M = lines-per-row multiplier: 1 for double (8 lines = 128 B), 2 for float (16 lines = 128 B)
 template<typename T, bool SCATTER, typename Launcher>
 int dispatch_strided(int n, fft_args const &a, Launcher &L){
@@ -74,6 +99,15 @@ int dispatch_strided(int n, fft_args const &a, Launcher &L){
         case 128:  return launch_strided<T, radix_list<8, 4, 4, 1>,  16 / M,  8 * M, 2, SCATTER>(a, L);
         case 256:  return launch_strided<T, radix_list<8, 8, 4, 1>,  32 / M,  8 * M, 2, SCATTER>(a, L);
         case 512:
+#ifndef B200_HOST_EMULATION
+            // rows far apart (the slow axis of a large box): the tile comes by TMA (fft_strided_tma_kernel)
+            if constexpr (!SCATTER){
+                if (tma_tile_wanted<T>(a)){
+                    int const rc = launch_strided_tma<T, radix_list<8, 8, 8, 1>, 32 / M, 8 * M, 3>(a, L);
+                    if (rc != -1) return rc;
+                }
+            }
+#endif
             // developer knob HEFFTE_B200_STRIDED_512 = 1: twice the threads on the tile, two CTAs per SM
             if (SCATTER && strided_512_variant() == 1) return launch_strided<T, radix_list<8, 8, 8, 1>, 64 / M, 8 * M, 2, SCATTER>(a, L);
             return launch_strided<T, radix_list<8, 8, 8, 1>,  32 / M,  8 * M, 3, SCATTER>(a, L);

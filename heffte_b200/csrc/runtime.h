@@ -20,6 +20,13 @@ int fail(int code, std::string const &message);
 int check_cuda(cudaError_t status, const char *what);
 extern std::atomic<long long> launch_counter;
 
+#ifndef B200_HOST_EMULATION
+// The tensor map of a strided stage for the TMA-loaded kernel: (line axis, transform axis, slower line axis, batch entry) over
+// elements of `real_bytes` (4 or 8), a box of `lpb` lines x 256 rows.  False when the driver offers no encoder or the box of
+// the stage does not fit the rules of a tensor map: the caller then keeps the cp.async kernel.
+bool encode_tile_map(tma_tile_map &map, const void *base, int real_bytes, long long count_a, long long n, long long stride, long long count_b, long long stride_b,
+                     int batch, long long step_bytes, int lpb);
+#endif
 // raises the dynamic shared-memory limit of a kernel once (needed above 48 KB)
 void allow_smem(const void *kernel, size_t bytes);
 
@@ -41,6 +48,19 @@ struct cuda_launcher {
         launch_counter.fetch_add(1, std::memory_order_relaxed);
         return check_cuda(cudaPeekAtLastError(), "kernel launch");
     }
+#ifndef B200_HOST_EMULATION
+    // a kernel whose tile arrives by TMA: the tensor map is its second parameter
+    template<typename kernel_t>
+    int launch_tma(kernel_t kernel, long long blocks, int threads, size_t smem, fft_args const &args, tma_tile_map const &map){
+        if (blocks <= 0 or batch <= 0) return B200_SUCCESS;
+        if (max_blocks > 0 and blocks > max_blocks) blocks = max_blocks;
+        if (blocks > 2147483647LL or batch > 65535) return fail(B200_ERR_UNSUPPORTED, "grid too large");
+        if (smem > 48 * 1024) allow_smem(reinterpret_cast<const void*>(kernel), smem);
+        kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(batch)), threads, smem, stream>>>(args, map);
+        launch_counter.fetch_add(1, std::memory_order_relaxed);
+        return check_cuda(cudaPeekAtLastError(), "kernel launch");
+    }
+#endif
     // persistent launch of the paired kernel: the whole grid must be resident at once (its CTAs wait for one another), so it is
     // sized by the occupancy of the kernel; grid.y = batch entries
     template<typename kernel_t>

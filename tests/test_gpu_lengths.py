@@ -14,6 +14,8 @@ from oracle import heffte_oracle as O
 from tests.helpers import TOL, seeded
 from tests.test_gpu_fft1d import _exec
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
@@ -95,3 +97,13 @@ def test_bluestein_beats_the_quadratic_path(lib):
         times["composite"] * 1e3, times["composite_kernel"], times["generic"] * 1e3, times["generic_kernel"]))
     assert "Bluestein" in times["composite_kernel"] and times["generic_kernel"] == "generic"
     assert times["composite"] * 3 < times["generic"]
+
+
+def test_tma_loaded_tile_on_small_boxes(built_library):
+    """fft_strided_tma_kernel (cp.async.bulk.tensor tile loads) is taken by default only for rows >= 1 MiB apart (the slow axis of
+    512^3: covered by tests/test_y_fullsize_gpu.py and the bench parity); here it is forced on small boxes, see tests/gpu_tma_worker.py"""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gpu_tma_worker.py")], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + "\n" + out.stderr[-3000:]
+    assert "gpu_tma_worker: ok" in out.stdout
