@@ -640,6 +640,11 @@ def run_workload(ctx, args, kind, size, precision, steps, warmup, *, primary, re
                     torch.cuda.synchronize()
                     ms = a.elapsed_time(b) / reps
                 name = lib.b200_fft1d_kernel_name(plan).decode()
+                # the library takes the TMA-loaded variant of the 512-point fp64 strided kernel for rows at least 1 MiB apart
+                # (csrc/fft_dispatch.cuh tma_tile_wanted; the choice is made per launch, the plan only knows the family)
+                if name == "strided" and k == 0 and length == 512 and prec == 1 and gi[0] * csize >= (1 << 20) and ca % 8 == 0 \
+                        and os.environ.get("HEFFTE_B200_TMA", "1")[:1] != "0":
+                    name = "strided_tma"
                 lib.b200_fft1d_destroy(plan)
                 stages.append({"dim": dim, "direction": "backward" if direction else "forward", "kernel": name, "n": length, "ms": ms,
                                "GB/s": algo_bytes / ms * 1e-6, "algorithmic_bytes": algo_bytes,
