@@ -37,7 +37,7 @@ __device__ __forceinline__ unsigned smem_u32(const void *p){ return static_cast<
 
 // PIPE = 1: one tile buffer, the next tile is requested after the passes of this one; PIPE = 2: two buffers, the load of the next
 // tile is in flight while this one is transformed
-template<typename T, typename RL, int TPL, int LPB, int MINB, bool BWD, int PIPE>
+template<typename T, typename RL, int TPL, int LPB, int MINB, bool BWD, int PIPE, int ROWS = 256>
 __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_tma_kernel(fft_args a, const __grid_constant__ CUtensorMap tmap){
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr unsigned N = RL::N;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(TPL * LPB, MINB) fft_strided_tma_kernel(fft_ar
         const unsigned bar = smem_u32(bars + slot);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(TILE_BYTES) : "memory");
         #pragma unroll
-        for(unsigned r0 = 0; r0 < N; r0 += 256){
+        for(unsigned r0 = 0; r0 < N; r0 += ROWS){
             const unsigned dst = smem_u32(smem_raw + static_cast<size_t>(slot) * TILE_BYTES + static_cast<size_t>(r0) * LPB * sizeof(cplx<T>));
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
                          :: "r"(dst), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(static_cast<int>(2 * a0 * (sizeof(T) == 8 ? 1 : 1))), "r"(static_cast<int>(r0)), "r"(static_cast<int>(b)), "r"(bar) : "memory");
@@ -118,11 +118,17 @@ int main(){
         long long count_b, stride_b;
         if (dim == 1){ a.ig = a.og = line_geom{n, 1, (long long)n*n}; a.count_a = n; count_b = n; stride_b = (long long)n*n; }
         else { a.ig = a.og = line_geom{(long long)n*n, 1, 0}; a.count_a = n*n; count_b = 1; stride_b = elems; }
-        CUtensorMap tmap;
+        CUtensorMap tmap, tmap128, tmap64rows, tmap_nopromo;
         cuuint64_t gdim[3] = {(cuuint64_t) 2 * a.count_a, (cuuint64_t) n, (cuuint64_t) count_b};
         cuuint64_t gstride[2] = {(cuuint64_t) a.ig.stride * 16, (cuuint64_t) stride_b * 16};
-        cuuint32_t box[3] = {2 * LPB, 256, 1}, estr[3] = {1, 1, 1};
+        cuuint32_t box[3] = {2 * LPB, 256, 1}, box64[3] = {2 * LPB, 64, 1}, estr[3] = {1, 1, 1};
         CUresult rc = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, x, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc == CUDA_SUCCESS) rc = encode(&tmap128, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, x, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc == CUDA_SUCCESS) rc = encode(&tmap_nopromo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, x, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc == CUDA_SUCCESS) rc = encode(&tmap64rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, x, gdim, gstride, box64, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS){ printf("cuTensorMapEncodeTiled failed: %d\n", (int) rc); return 1; }
         printf("-- fp64 512 strided, dim %d (out of place: x -> y)\n", dim);
@@ -136,6 +142,13 @@ int main(){
         };
         long long const tiles = a.nlines / LPB;
         report("TMA tile, one tile per CTA, minb3", timeit([&]{ run_tma(fft_strided_tma_kernel<double, R888, TPL, LPB, 3, false, 1>, 1, tiles); }));
+        {
+            auto run_with = [&](auto kernel, CUtensorMap const &m){ size_t smem = (size_t) n * LPB * 16 + 64; cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024); kernel<<<(unsigned) tiles, TPL * LPB, smem>>>(a, m); };
+            report("TMA tile, L2 promotion 128 B", timeit([&]{ run_with(fft_strided_tma_kernel<double, R888, TPL, LPB, 3, false, 1>, tmap128); }));
+            report("TMA tile, no L2 promotion", timeit([&]{ run_with(fft_strided_tma_kernel<double, R888, TPL, LPB, 3, false, 1>, tmap_nopromo); }));
+            report("TMA tile, eight requests of 64 rows", timeit([&]{ run_with(fft_strided_tma_kernel<double, R888, TPL, LPB, 3, false, 1, 64>, tmap64rows); }));
+            report("TMA tile, minb2 (two CTAs per SM)", timeit([&]{ run_with(fft_strided_tma_kernel<double, R888, TPL, LPB, 2, false, 1>, tmap); }));
+        }
         {
             CK(cudaDeviceSynchronize());
             std::vector<double2> h1(1 << 20), h2(1 << 20);
