@@ -30,6 +30,9 @@ void compute_dft(heffte::comm const &comm){
     heffte::gpu::vector<std::complex<double>> gpu_output(fft.size_outbox());
     heffte::fft3d<backend_tag>::buffer_container<std::complex<double>> workspace(fft.size_workspace());
 
+    // optional, collective: the other rank then stores its part of the spectrum straight into this array (several GPUs: over NVLink)
+    bool const registered = fft.register_buffer(gpu_output.data(), gpu_output.size());
+    if (registered != fft.uses_peer_memory()){ std::printf("rank %d: register_buffer answered %d\n", me, (int) registered); failures++; }
     fft.forward(gpu_input.data(), gpu_output.data(), workspace.data());
     std::vector<std::complex<double>> spectrum = heffte::gpu::transfer::unload(stream.get(), gpu_output);
     // test/test_c.c:47-74
